@@ -1,0 +1,260 @@
+/* ipcfp.h — C ABI of the B200-native witness-generation engine.
+ *
+ * Drop-in boundary for ONE path of consensus-shipyard/ipc-filecoin-proofs: the two-pass
+ * receipt/event AMT scan and the HAMT storage-slot lookup. Every entry point cites the
+ * reference interface it replaces (paths relative to the reference repo root). The header
+ * is bindgen-ready: plain pointers and sizes, POD structs, no C++ or torch types.
+ *
+ * All compute behind these calls runs in hand-written sm_100a CUDA kernels. There is no
+ * CPU implementation in this library: without a CUDA device every call fails with
+ * IPCFP_ERR_NO_DEVICE.
+ *
+ * CIDs are 38-byte binary CIDv1 (`01 | codec | multihash code | 20 | digest[32]`; the
+ * Filecoin chain form is `01 71 a0 e4 02 20 <blake2b-256>`), exactly the bytes behind the
+ * strings `Cid::try_from(&str)` parses at src/proofs/common/witness.rs:60-63.
+ *
+ * Ownership: inputs are borrowed for the duration of the call. Outputs are owned by the
+ * returned result object and released with the matching ipcfp_*_free. A store handle is
+ * bound to one CUDA device; calls on one handle must be serialised by the caller.
+ */
+#ifndef IPCFP_H
+#define IPCFP_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPCFP_CID_LEN 38
+
+typedef int32_t ipcfp_status;
+enum {
+    IPCFP_OK = 0,
+    IPCFP_ERR_INVALID_ARG = -1,
+    IPCFP_ERR_MISSING_BLOCK = -2,   /* anyhow!("missing ...") at witness.rs:47-50, storage/decode.rs:41-43, events/generator.rs:159-161 */
+    IPCFP_ERR_DECODE = -3,          /* any serde / AMT / HAMT decode error bubbled by `?`                */
+    IPCFP_ERR_CID_MISMATCH = -4,    /* IPCFP_STORE_VERIFY_CIDS: blake2b-256(block) != digest in its CID   */
+    IPCFP_ERR_MISSING_EXEC = -5,    /* "Missing message at index" events/generator.rs:244-246             */
+    IPCFP_ERR_CUDA = -6,
+    IPCFP_ERR_NCCL = -7,
+    IPCFP_ERR_STATE_ROOT_MISMATCH = -8, /* "ParentStateRoot mismatch" storage/generator.rs:93-99         */
+    IPCFP_ERR_ACTOR_NOT_FOUND = -9,     /* "actor not found" common/decode.rs:39                         */
+    IPCFP_ERR_NO_DEVICE = -10,
+    IPCFP_ERR_UNSUPPORTED = -11
+};
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* ipcfp_last_error(void);
+/* Index attached to the last failure (receipt index / spec index / block index), or UINT64_MAX. */
+uint64_t ipcfp_last_error_index(void);
+/* Library version string and the list of kernels compiled in. */
+const char* ipcfp_version(void);
+/* Number of kernel launches issued by this library on the calling thread since load. */
+uint64_t ipcfp_kernel_launch_count(void);
+
+/* Pinned host memory for the flat block arrays (so ingest H2D copies run at PCIe rate). */
+ipcfp_status ipcfp_host_alloc(size_t bytes, void** out);
+void ipcfp_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------
+ * Block store — replaces the `fvm_ipld_blockstore::Blockstore` implementations the generators
+ * are generic over (src/client/blockstore.rs:20-37, src/client/cached_blockstore.rs:53-85):
+ * a device-resident arena of IPLD blocks with a CID hash index.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ipcfp_store ipcfp_store;
+
+#define IPCFP_STORE_VERIFY_CIDS 0x1u /* Blake2b-256 every block on the GPU and compare with its CID */
+
+/* cids: n*38 bytes; offsets[i]/lengths[i]: block i inside blob. Blocks whose offsets are all
+ * 16-byte aligned are used in place; otherwise they are re-packed on the device. */
+ipcfp_status ipcfp_store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t* lengths,
+                                const uint8_t* blob, uint64_t blob_size, uint64_t n_blocks,
+                                int device, uint32_t flags, ipcfp_store** out);
+void ipcfp_store_destroy(ipcfp_store* s);
+uint64_t ipcfp_store_n_blocks(const ipcfp_store* s);
+/* Blockstore::get — copies the block into buf (cap bytes). *len receives the block length.
+ * Unknown CID: returns IPCFP_OK with *found = 0 (the reference's Ok(None)). */
+ipcfp_status ipcfp_store_get(ipcfp_store* s, const uint8_t cid[IPCFP_CID_LEN], uint8_t* buf, uint32_t cap,
+                             uint32_t* len, int* found);
+/* Blockstore::has */
+ipcfp_status ipcfp_store_has(ipcfp_store* s, const uint8_t cid[IPCFP_CID_LEN], int* found);
+/* Index of the first block whose CID digest did not match (after a CID_MISMATCH), else UINT64_MAX. */
+uint64_t ipcfp_store_first_bad_block(const ipcfp_store* s);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched hash primitives (unit parity of the kernels).
+ * ------------------------------------------------------------------------------------------ */
+/* out[i] = blake2b-256(blob[offsets[i] .. offsets[i]+lengths[i]))   (multihash-codetable Code::Blake2b256,
+ * src/proofs/events/utils.rs:65) */
+ipcfp_status ipcfp_blake2b256_batch(const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets,
+                                    const uint32_t* lengths, uint64_t n, int device, uint8_t* out /* n*32 */);
+/* keccak256 (src/proofs/common/evm.rs:62-69, :81-88) */
+ipcfp_status ipcfp_keccak256_batch(const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets,
+                                   const uint32_t* lengths, uint64_t n, int device, uint8_t* out /* n*32 */);
+/* SHA-256 (fvm_ipld_hamt default key hasher) */
+ipcfp_status ipcfp_sha256_batch(const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets,
+                                const uint32_t* lengths, uint64_t n, int device, uint8_t* out /* n*32 */);
+/* compute_mapping_slot(key, slot_index) = keccak256(key32 || u256_be(slot_index))
+ * (src/proofs/storage/utils.rs:5-12), batched. */
+ipcfp_status ipcfp_compute_mapping_slots(const uint8_t* keys32 /* n*32 */, const uint64_t* slot_indices, uint64_t n,
+                                         int device, uint8_t* out /* n*32 */);
+
+/* ------------------------------------------------------------------------------------------
+ * Inputs that came over RPC in the reference (src/client/types.rs:13-58).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ipcfp_tipset_desc {
+    int64_t parent_epoch;                  /* parent.height                                   */
+    int64_t child_epoch;                   /* child.height                                    */
+    uint32_t n_parents;                    /* parent.cids.len() == parent.blocks.len()        */
+    const uint8_t* parent_cids;            /* n_parents*38: parent.cids                       */
+    const uint8_t* parent_txmeta_cids;     /* n_parents*38: parent.blocks[i].messages         */
+    const uint8_t* child_cid;              /* 38: child.cids[0]                               */
+    const uint8_t* receipts_root;          /* 38: child.blocks[0].parent_message_receipts     */
+    const uint8_t* child_parent_state_root;/* 38: child.blocks[0].parent_state_root (JSON)    */
+    uint64_t n_receipts;                   /* ChainGetParentReceipts(child) length            */
+    const uint8_t* events_roots;           /* n_receipts*38: ApiReceipt.events_root           */
+    const uint8_t* has_events_root;        /* n_receipts: 0 = None                            */
+} ipcfp_tipset_desc;
+
+/* EventProofSpec (src/proofs/generator.rs:18-22) */
+typedef struct ipcfp_event_spec {
+    const char* event_signature; /* e.g. "NewTopDownMessage(bytes32,uint256)" → topic0 = keccak256 */
+    const char* topic_1;         /* ASCII, right-padded to 32 bytes (evm.rs:72-78)                  */
+    uint8_t has_actor_id_filter;
+    uint64_t actor_id_filter;
+} ipcfp_event_spec;
+
+/* StorageProofSpec (src/proofs/generator.rs:12-15) */
+typedef struct ipcfp_storage_spec {
+    uint64_t actor_id;
+    uint8_t slot[32];
+} ipcfp_storage_spec;
+
+/* ------------------------------------------------------------------------------------------
+ * Outputs.
+ * ------------------------------------------------------------------------------------------ */
+/* Vec<ProofBlock> in `Cid` Ord order (src/proofs/common/witness.rs:43-56, common/bundle.rs:11-18) */
+typedef struct ipcfp_witness {
+    uint64_t n_blocks;
+    const uint8_t* cids;      /* n_blocks*38, sorted by (version, codec, multihash) */
+    const uint64_t* offsets;  /* n_blocks+1 offsets into blob                      */
+    const uint8_t* blob;
+    uint64_t blob_size;
+} ipcfp_witness;
+
+/* EventProof + EventData (src/proofs/events/bundle.rs:6-23) minus the per-call constants
+ * (epochs, parent tipset CIDs, child block CID) which the caller already holds. */
+typedef struct ipcfp_event_proof {
+    uint64_t exec_index;
+    uint64_t event_index;
+    uint64_t emitter;
+    uint32_t n_topics;      /* ≤ 4 in Case B; Case A (`topics` key) may carry more — see data_off   */
+    uint32_t data_len;
+    uint64_t data_off;      /* into ipcfp_event_result.data_blob                                    */
+    uint64_t topics_off;    /* into data_blob: n_topics*32 bytes                                    */
+    uint8_t message_cid[IPCFP_CID_LEN];
+    uint8_t _pad[2];
+} ipcfp_event_proof;
+
+typedef struct ipcfp_event_result {
+    uint64_t n_matching;
+    const uint64_t* matching_indices; /* pass-1 output (events/generator.rs:206-239), ascending */
+    uint64_t n_proofs;
+    const ipcfp_event_proof* proofs;  /* ordered by (exec_index, event_index)                  */
+    const uint8_t* data_blob;
+    uint64_t data_blob_size;
+    ipcfp_witness witness;            /* EventProofBundle.blocks                                */
+    uint64_t n_exec;                  /* length of the reconstructed execution order            */
+    /* device-side timing of the last call, milliseconds (CUDA events on the engine stream) */
+    float ms_total, ms_pass1, ms_pass2, ms_txamt, ms_witness;
+    uint64_t pass1_bytes;             /* algorithmic bytes read by the pass-1 scan kernel       */
+    uint64_t pass1_nodes;
+} ipcfp_event_result;
+
+typedef struct ipcfp_storage_proof {
+    uint64_t actor_id;
+    uint8_t actor_state_cid[IPCFP_CID_LEN];
+    uint8_t storage_root[IPCFP_CID_LEN];
+    uint8_t slot[32];
+    uint8_t value[32];    /* left_pad_32(raw) (evm.rs:91-100); zero when absent */
+    uint8_t found;        /* Hamt::get returned Some                            */
+    uint8_t _pad[3];
+    uint32_t raw_len;     /* length of the raw value                            */
+} ipcfp_storage_proof;
+
+typedef struct ipcfp_storage_result {
+    uint64_t n_proofs;
+    const ipcfp_storage_proof* proofs;
+    ipcfp_witness witness;              /* union over all specs, sorted                          */
+    const uint64_t* spec_witness_offsets; /* n_proofs+1                                          */
+    const uint32_t* spec_witness_index;   /* per spec: indices into witness (its Vec<ProofBlock>) */
+    float ms_total;
+} ipcfp_storage_result;
+
+typedef struct ipcfp_slot_result {
+    uint64_t n;
+    const uint8_t* found;      /* n                                        */
+    const uint32_t* raw_len;   /* n                                        */
+    const uint8_t* values;     /* n*32, left-padded                        */
+    ipcfp_witness witness;     /* blocks touched by the lookups (recorder) */
+    float ms_total;
+} ipcfp_slot_result;
+
+typedef struct ipcfp_bundle {
+    ipcfp_storage_result* storage;  /* may be NULL */
+    uint64_t n_event_results;
+    ipcfp_event_result** events;    /* one per event spec */
+    ipcfp_witness witness;          /* UnifiedProofBundle.blocks: BTreeSet<(Cid, data)> order */
+} ipcfp_bundle;
+
+/* ------------------------------------------------------------------------------------------
+ * Entry points.
+ * ------------------------------------------------------------------------------------------ */
+#define IPCFP_SCAN_SKIP_TX_AMTS 0x1u  /* find_matching_events only: no record_transaction_amts / base witness;
+                                         execution order still built                                          */
+
+/* generate_event_proof (src/proofs/events/generator.rs:60-107): base witness, message-AMT
+ * recording, execution order, two-pass scan (find_matching_events :180-307), materialise. */
+ipcfp_status ipcfp_generate_event_proof(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_spec* spec,
+                                        uint32_t flags, ipcfp_event_result** out);
+void ipcfp_event_result_free(ipcfp_event_result* r);
+
+/* read_storage_slot (src/proofs/storage/decode.rs:36-97), batched over k slot keys against one
+ * contract_state root, with a RecordingBlockStore-equivalent witness. */
+ipcfp_status ipcfp_read_storage_slots(ipcfp_store* s, const uint8_t contract_state_root[IPCFP_CID_LEN],
+                                      const uint8_t* slots /* k*32 */, uint64_t k, ipcfp_slot_result** out);
+void ipcfp_slot_result_free(ipcfp_slot_result* r);
+
+/* generate_storage_proof (src/proofs/storage/generator.rs:29-67), batched over specs. */
+ipcfp_status ipcfp_generate_storage_proofs(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_spec* specs,
+                                           uint64_t n_specs, ipcfp_storage_result** out);
+void ipcfp_storage_result_free(ipcfp_storage_result* r);
+
+/* generate_proof_bundle (src/proofs/generator.rs:25-95). */
+ipcfp_status ipcfp_generate_proof_bundle(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_spec* sspecs,
+                                         uint64_t n_sspecs, const ipcfp_event_spec* especs, uint64_t n_especs,
+                                         ipcfp_bundle** out);
+void ipcfp_bundle_free(ipcfp_bundle* b);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU; the caller owns the communicator — torch.distributed / NCCL).
+ * Receipts shard by index range; each rank scans its shard, then the per-shard witness CID sets
+ * are all-gathered and merged (the BTreeSet union of src/proofs/common/witness.rs:24-40).
+ * ------------------------------------------------------------------------------------------ */
+/* Scan receipts [lo, hi) only. events_roots/has_events_root in t cover ALL n_receipts. */
+ipcfp_status ipcfp_generate_event_proof_shard(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_spec* spec,
+                                              uint64_t lo, uint64_t hi, uint32_t world_size, uint32_t rank,
+                                              uint32_t flags, ipcfp_event_result** out);
+/* Device-resident copy of a result's sorted witness CIDs (n*38 bytes) for the collective. */
+ipcfp_status ipcfp_witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap_cids, uint64_t* n);
+/* Merge all-gathered CID lists on the device: gathered = world*cap*38 bytes, counts[world];
+ * out_dev receives the sorted unique union (cap_out*38), *n_out its length. */
+ipcfp_status ipcfp_merge_witness_cids(int device, const void* gathered_dev, const uint64_t* counts, uint32_t world,
+                                      uint64_t cap, void* out_dev, uint64_t cap_out, uint64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPCFP_H */

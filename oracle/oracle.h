@@ -1,0 +1,79 @@
+/* oracle.h — CPU restatement of the reference's hot path (TEST INFRASTRUCTURE).
+ *
+ * PARITY UNPINNED BY THE REFERENCE: consensus-shipyard/ipc-filecoin-proofs ships no tests,
+ * fixtures or golden vectors, cannot be compiled here (no Rust toolchain, crates
+ * not vendored) and delegates all arithmetic to un-vendored crates (fvm_ipld_amt 0.7.4,
+ * fvm_ipld_hamt 0.10.4, fvm_ipld_encoding 0.5.3, serde_ipld_dagcbor 0.6, fvm_shared 4.7, cid 0.11,
+ * multihash-codetable 0.1.4, sha3 0.10 — Cargo.toml:11-22,38). This oracle restates the reference's
+ * orchestration line by line and the crates' published formats; it is pinned instead by
+ *   (1) known-answer hash vectors + hashlib,
+ *   (2) an independent Python (cbor2 + hashlib) builder/scanner (oracle/pyoracle.py),
+ *   (3) the restated verifiers (every witness must verify; dropping a block must fail).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library. The product library never links or calls it.
+ *
+ * Result structs are the POD types of include/ipcfp.h so tests compare field by field.
+ */
+#ifndef IPCFP_ORACLE_H
+#define IPCFP_ORACLE_H
+#include "../include/ipcfp.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_store oracle_store;
+
+/* Borrows all four arrays for the lifetime of the store (MemoryBlockstore whose get() clones). */
+oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t* lengths,
+                                  const uint8_t* blob, uint64_t n_blocks);
+void oracle_store_destroy(oracle_store* s);
+/* first block whose blake2b-256 differs from its CID digest, or UINT64_MAX */
+uint64_t oracle_store_verify_cids(const oracle_store* s, uint32_t threads);
+
+const char* oracle_last_error(void);
+uint64_t oracle_last_error_index(void);
+
+/* generate_event_proof (events/generator.rs:60-107). threads = 1 mirrors the reference
+ * (single-threaded); threads > 1 parallelises pass 1 over receipts. */
+ipcfp_status oracle_generate_event_proof(const oracle_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_spec* spec,
+                                         uint32_t flags, uint32_t threads, ipcfp_event_result** out);
+/* scan receipts [lo,hi) only (multi-GPU shard semantics of ipcfp_generate_event_proof_shard) */
+ipcfp_status oracle_generate_event_proof_shard(const oracle_store* s, const ipcfp_tipset_desc* t,
+                                               const ipcfp_event_spec* spec, uint64_t lo, uint64_t hi, uint32_t world,
+                                               uint32_t rank, uint32_t flags, uint32_t threads, ipcfp_event_result** out);
+void oracle_event_result_free(ipcfp_event_result* r);
+
+ipcfp_status oracle_read_storage_slots(const oracle_store* s, const uint8_t root[38], const uint8_t* slots, uint64_t k,
+                                       ipcfp_slot_result** out);
+void oracle_slot_result_free(ipcfp_slot_result* r);
+
+ipcfp_status oracle_generate_storage_proofs(const oracle_store* s, const ipcfp_tipset_desc* t,
+                                            const ipcfp_storage_spec* specs, uint64_t n, ipcfp_storage_result** out);
+void oracle_storage_result_free(ipcfp_storage_result* r);
+
+ipcfp_status oracle_generate_proof_bundle(const oracle_store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_spec* ss,
+                                          uint64_t ns, const ipcfp_event_spec* es, uint64_t ne, ipcfp_bundle** out);
+void oracle_bundle_free(ipcfp_bundle* b);
+
+/* verify_event_proof (events/verifier.rs:51-290) over a witness; trust policy = accept all;
+ * filter_spec may be NULL (create_event_filter, verifier.rs:28-40). results[n_proofs] ∈ {0,1}. */
+ipcfp_status oracle_verify_event_proofs(const ipcfp_witness* w, const ipcfp_tipset_desc* t, const ipcfp_event_proof* proofs,
+                                        uint64_t n_proofs, const uint8_t* data_blob, const ipcfp_event_spec* filter_spec,
+                                        uint8_t* results);
+/* verify_storage_proof (storage/verifier.rs:24-63) */
+ipcfp_status oracle_verify_storage_proofs(const ipcfp_witness* w, const ipcfp_tipset_desc* t,
+                                          const ipcfp_storage_proof* proofs, uint64_t n_proofs, uint8_t* results);
+
+/* unit helpers */
+void oracle_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]);
+void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]);
+void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]);
+void oracle_compute_mapping_slot(const uint8_t key32[32], uint64_t slot_index, uint8_t out[32]);
+/* sorts n 38-byte CIDs in `Cid` Ord order in place, removing duplicates; returns new count */
+uint64_t oracle_sort_unique_cids(uint8_t* cids, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
