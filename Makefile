@@ -1,0 +1,29 @@
+# Builds everything in-tree: the product library (hand-written sm_100a CUDA behind the C ABI),
+# the synthetic tipset builder and the CPU oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CSRC      := ipc_filecoin_proofs_b200/csrc
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr
+CU_SRCS   := $(CSRC)/store.cu $(CSRC)/events.cu $(CSRC)/storage.cu $(CSRC)/witness.cu $(CSRC)/prims.cu $(CSRC)/capi.cu
+CU_OBJS   := $(CU_SRCS:.cu=.o)
+CU_HDRS   := $(wildcard $(CSRC)/*.cuh) include/ipcfp.h
+LIB       := ipc_filecoin_proofs_b200/libipcfp.so
+
+all: $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS)
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) -lcudart
+
+synth/libipcfp_synth.so: synth/synth.cpp synth/synth.h synth/cpu_crypto.h
+	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ synth/synth.cpp
+
+oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h synth/cpu_crypto.h include/ipcfp.h
+	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ oracle/oracle.cpp
+
+clean:
+	rm -f $(CU_OBJS) $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
+
+.PHONY: all clean

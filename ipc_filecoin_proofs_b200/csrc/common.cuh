@@ -1,0 +1,140 @@
+// common.cuh — shared device/host utilities of the B200 witness-generation engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ipcfp.h"
+
+namespace ipcfp {
+
+// ------------------------------------------------------------------ host-side error plumbing
+struct Error {
+    ipcfp_status status;
+    std::string msg;
+    uint64_t index;
+    Error(ipcfp_status s, std::string m, uint64_t i = UINT64_MAX) : status(s), msg(std::move(m)), index(i) {}
+};
+void note_launch();  // counts kernel launches (ipcfp_kernel_launch_count)
+
+#define IPCFP_CUDA(expr)                                                                                          \
+    do {                                                                                                          \
+        cudaError_t _e = (expr);                                                                                  \
+        if (_e != cudaSuccess)                                                                                    \
+            throw ::ipcfp::Error(IPCFP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+#define IPCFP_LAUNCH_CHECK()                                                   \
+    do {                                                                       \
+        ::ipcfp::note_launch();                                                \
+        IPCFP_CUDA(cudaGetLastError());                                        \
+    } while (0)
+
+static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// RAII device buffer
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) IPCFP_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// stream-ordered device buffer (cudaMallocAsync pool: no implicit device sync, cached between calls)
+template <class T> struct AsyncBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t st = nullptr;
+    AsyncBuf() {}
+    AsyncBuf(size_t count, cudaStream_t s) { alloc(count, s); }
+    AsyncBuf(const AsyncBuf&) = delete;
+    AsyncBuf& operator=(const AsyncBuf&) = delete;
+    AsyncBuf(AsyncBuf&& o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+    AsyncBuf& operator=(AsyncBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+    ~AsyncBuf() { release(); }
+    void alloc(size_t count, cudaStream_t s) {
+        release();
+        st = s;
+        n = count;
+        if (count) IPCFP_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+    }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
+    void zero() { if (p) IPCFP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+};
+
+// pinned host scratch for small read-backs (counters, error words)
+template <class T> struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinnedBuf() {}
+    explicit PinnedBuf(size_t count) { alloc(count); }
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void alloc(size_t count) { if (p) cudaFreeHost(p); p = nullptr; n = count; if (count) IPCFP_CUDA(cudaMallocHost((void**)&p, count * sizeof(T))); }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+};
+
+// ------------------------------------------------------------------ device error word
+// Kernels report the FIRST failure in the reference's sequential order through one
+// atomicMin on a 64-bit key:  [ stage:8 | index:40 | code:8 | detail:8 ].
+// stage numbers follow the order in which the reference would hit the failure.
+enum Stage : uint32_t {
+    ST_TXMETA = 1, ST_TXAMT = 2, ST_RECEIPTS_ROOT = 3, ST_PASS1 = 4, ST_PASS2 = 5, ST_WITNESS = 6,
+    ST_STORAGE = 7, ST_INGEST = 8
+};
+enum DevCode : uint32_t { DC_MISSING = 1, DC_DECODE = 2, DC_MISSING_EXEC = 3, DC_STATE_MISMATCH = 4, DC_ACTOR_NOT_FOUND = 5, DC_UNSUPPORTED = 6, DC_CID_MISMATCH = 7 };
+
+#define IPCFP_NO_ERROR 0xFFFFFFFFFFFFFFFFull
+
+__host__ __device__ static inline uint64_t err_key(uint32_t stage, uint64_t index, uint32_t code, uint32_t detail) {
+    return ((uint64_t)stage << 56) | ((index & 0xFFFFFFFFFFull) << 16) | ((uint64_t)(code & 0xff) << 8) | (detail & 0xff);
+}
+#ifdef __CUDACC__
+__device__ static inline void report_error(unsigned long long* word, uint32_t stage, uint64_t index, uint32_t code, uint32_t detail) {
+    atomicMin(word, (unsigned long long)err_key(stage, index, code, detail));
+}
+#endif
+
+// ------------------------------------------------------------------ CIDs on the device
+// A CID is its 6-byte prefix (class id into a small per-store table) + 32-byte digest.
+struct Digest { uint64_t w[4]; };  // raw digest bytes, memory order (w[0] = bytes 0..7 little-endian load)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ bool digest_eq(const Digest& a, const Digest& b) {
+    return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3];
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ uint64_t digest_hash(const Digest& d, uint32_t cls) { return mix64(d.w[0] ^ (d.w[2] * 0x9E3779B97F4A7C15ULL) ^ cls); }
+// unaligned loads from block bytes
+__device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+__device__ __forceinline__ Digest load_digest(const uint8_t* p) {
+    Digest d;
+    d.w[0] = load_u64_le(p); d.w[1] = load_u64_le(p + 8); d.w[2] = load_u64_le(p + 16); d.w[3] = load_u64_le(p + 24);
+    return d;
+}
+#endif
+
+}  // namespace ipcfp

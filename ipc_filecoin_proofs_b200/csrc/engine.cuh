@@ -1,0 +1,116 @@
+// engine.cuh — host-side objects of the engine (C++17), shared by the translation units.
+#pragma once
+#include <array>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "store.cuh"
+
+namespace ipcfp {
+
+// Grow-only cache of pinned host buffers so result read-backs run at PCIe rate without paying
+// cudaHostAlloc on every call.
+struct PinnedPool {
+    struct Buf { void* p; size_t cap; };
+    std::mutex mu;
+    std::vector<Buf> free_list;
+    ~PinnedPool();
+    void* take(size_t bytes, size_t* cap_out);
+    void give(void* p, size_t cap);
+};
+struct PinnedArray {
+    std::shared_ptr<PinnedPool> pool;
+    void* p = nullptr;
+    size_t cap = 0;
+    PinnedArray() {}
+    PinnedArray(std::shared_ptr<PinnedPool> pl, size_t bytes) : pool(std::move(pl)) { p = pool->take(bytes ? bytes : 16, &cap); }
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    PinnedArray(PinnedArray&& o) noexcept : pool(std::move(o.pool)), p(o.p), cap(o.cap) { o.p = nullptr; }
+    PinnedArray& operator=(PinnedArray&& o) noexcept { release(); pool = std::move(o.pool); p = o.p; cap = o.cap; o.p = nullptr; return *this; }
+    ~PinnedArray() { release(); }
+    void release() { if (p && pool) pool->give(p, cap); p = nullptr; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct Store {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t n = 0, blob_size = 0;
+    DevBuf<uint8_t> arena;
+    DevBuf<uint64_t> offsets;
+    DevBuf<uint32_t> lengths;
+    DevBuf<Digest> digests;
+    DevBuf<uint8_t> cls;
+    DevBuf<uint64_t> table;
+    StoreView view{};
+    std::vector<std::array<uint8_t, 6>> class_prefix;  // distinct CID prefixes in this store
+    std::vector<uint32_t> class_rank;                  // rank of each class in `Cid` Ord
+    uint64_t first_bad = UINT64_MAX;
+    std::shared_ptr<PinnedPool> pool;
+    // small persistent scratch
+    DevBuf<unsigned long long> dev_words;  // [0] error word, [1..] counters
+    PinnedBuf<uint64_t> host_words;
+    cudaEvent_t ev[8] = {};
+    ~Store();
+    void use() const { IPCFP_CUDA(cudaSetDevice(device)); }
+};
+
+// Device-resident copy of an ipcfp_tipset_desc (events roots etc.)
+struct TipsetDev {
+    int64_t parent_epoch = 0, child_epoch = 0;
+    uint32_t n_parents = 0;
+    std::vector<uint8_t> parent_cids, txmeta_cids;  // host copies (tiny)
+    uint8_t child_cid[38] = {}, receipts_root[38] = {}, child_state_root[38] = {};
+    bool has_state_root = false;
+    uint64_t n_receipts = 0;
+    DevBuf<uint8_t> events_roots;  // n*38
+    DevBuf<uint8_t> has_root;      // n
+};
+
+struct ScopedStatus;  // capi.cu
+
+void set_last_error(const std::string& msg, uint64_t index);
+ipcfp_status status_from_devcode(uint32_t code);
+
+// store.cu
+Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t* lengths, const uint8_t* blob, uint64_t blob_size,
+                    uint64_t n, int device, uint32_t flags);
+void store_get(Store* s, const uint8_t* cid, uint8_t* buf, uint32_t cap, uint32_t* len, int* found);
+void hash_batch(int which, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, const uint32_t* lengths, uint64_t n, int device,
+                uint8_t* out);
+void mapping_slots(const uint8_t* keys32, const uint64_t* slot_indices, uint64_t n, int device, uint8_t* out);
+void check_device(int device);
+
+// events.cu
+void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td);
+ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank);
+void event_result_free(ipcfp_event_result* r);
+void witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap, uint64_t* n);
+void merge_witness_cids(int device, const void* gathered, const uint64_t* counts, uint32_t world, uint64_t cap, void* out, uint64_t cap_out,
+                        uint64_t* n_out);
+
+// storage.cu
+ipcfp_slot_result* read_storage_slots(Store* s, const uint8_t* root, const uint8_t* slots, uint64_t k);
+void slot_result_free(ipcfp_slot_result* r);
+ipcfp_storage_result* generate_storage_proofs(Store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_spec* specs, uint64_t n);
+void storage_result_free(ipcfp_storage_result* r);
+
+// witness.cu — materialise a witness bitmap into a sorted ipcfp_witness (host, pinned)
+struct WitnessOut {
+    PinnedArray cids, offsets, blob;
+    PinnedArray sorted_idx;       // host copy of the block indices in Cid order (u32[n])
+    uint64_t n = 0, blob_size = 0;
+    void fill(ipcfp_witness& w) const {
+        w.n_blocks = n; w.cids = cids.as<uint8_t>(); w.offsets = offsets.as<uint64_t>(); w.blob = blob.as<uint8_t>(); w.blob_size = blob_size;
+    }
+};
+void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out, bool to_host);
+// sort (class rank, digest) pairs: idx list (device, m entries) → sorted in place
+void sort_block_indices_by_cid(Store* s, uint32_t* idx_dev, uint64_t m);
+
+}  // namespace ipcfp

@@ -1,0 +1,782 @@
+// events.cu — the two-pass receipt/event AMT scan on the GPU.
+//
+// Replaces, for the data-parallel path, reference src/proofs/events/generator.rs:60-307:
+//   k_setup            collect_base_witness (:122-145) + TxMeta decode + AMT root loads
+//   k_amt_level/...    record_transaction_amts (:148-177) and build_execution_order
+//                      (events/utils.rs:33-94) as ONE level-synchronous, order-preserving BFS
+//   k_dedup_*          first-seen dedup of the execution order (utils.rs:56-91)
+//   k_pass1            find_matching_events pass 1 (:206-239): one thread decodes one events-AMT
+//                      root node, tests (actor_id, topic_0, topic_1) on every StampedEvent, the
+//                      warp ballots the matching-receipt bitmap
+//   k_pass2<EMIT>      pass 2 (:241-301): per matching receipt, receipts-AMT path walk + full
+//                      events-AMT walk, witness bits, EventProof records
+//   materialize_witness (witness.cu)   WitnessCollector::materialize (:104)
+#include <algorithm>
+#include <cstring>
+
+#include "engine.cuh"
+#include "hashes.cuh"
+#include "ipld.cuh"
+#include "prims.cuh"
+
+namespace ipcfp {
+
+// ------------------------------------------------------------------------------------------ events AMT walk
+enum WalkMode { WALK_ANY = 0, WALK_COUNT = 1, WALK_EMIT = 2 };
+
+struct EmitCtx {
+    ipcfp_event_proof* proofs;   // base for this match
+    uint8_t* blob;               // data blob base (whole result)
+    uint64_t blob_off;           // running offset for this match
+    uint64_t exec_index;
+    const uint8_t* msg_cid;      // 38 bytes
+};
+struct WalkOut { uint32_t nproofs; uint32_t nbytes; bool any; };
+
+__device__ __forceinline__ void emit_proof(const uint8_t* p, const EvLog& ev, uint64_t j, EmitCtx& ec, uint32_t k) {
+    ipcfp_event_proof q;
+    q.exec_index = ec.exec_index;
+    q.event_index = j;
+    q.emitter = ev.emitter;
+    q.n_topics = ev.ntopics;
+    q.data_len = ev.data_len;
+    q.topics_off = ec.blob_off;
+    uint8_t* o = ec.blob + ec.blob_off;
+    for (uint32_t t = 0; t < ev.ntopics; t++) {
+        const uint8_t* src = p + topic_offset(ev, t);
+        for (int b = 0; b < 32; b++) o[32 * t + b] = src[b];
+    }
+    ec.blob_off += 32ull * ev.ntopics;
+    q.data_off = ec.blob_off;
+    o = ec.blob + ec.blob_off;
+    for (uint32_t b = 0; b < ev.data_len; b++) o[b] = p[ev.data_off + b];
+    ec.blob_off += ev.data_len;
+    for (int b = 0; b < 38; b++) q.message_cid[b] = ec.msg_cid[b];
+    q._pad[0] = q._pad[1] = 0;
+    ec.proofs[k] = q;
+}
+
+// Decodes the values of one events-AMT node. Returns false on a decode error (r.err set).
+template <int MODE>
+__device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNodeHdr& h, uint32_t nv, uint64_t base, const Matcher& m,
+                                            WalkOut& wo, EmitCtx* ec) {
+    for (uint32_t v = 0; v < nv && !r.err; v++) {
+        EvLog ev;
+        parse_stamped_event(r, ev);
+        if (r.err) break;
+        if (event_matches(p, ev, m)) {
+            wo.any = true;
+            if (MODE != WALK_ANY) {
+                uint64_t j = base + bm_select(h.bm, v);
+                if (MODE == WALK_EMIT) emit_proof(p, ev, j, *ec, wo.nproofs);
+                wo.nproofs++;
+                wo.nbytes += 32 * ev.ntopics + ev.data_len;
+            }
+        }
+    }
+}
+
+// Full in-order walk of Amt<StampedEvent> (v3) rooted at block root_blk — `for_each` of
+// fvm_ipld_amt [UPSTREAM]: every reachable node is loaded through the store (and recorded when
+// wbits != nullptr). Returns 0 ok, else DevCode; detail in *detail.
+template <int MODE>
+__device__ uint32_t walk_events(const StoreView& s, uint32_t root_blk, const Matcher& m, uint32_t* wbits, WalkOut& wo, EmitCtx* ec,
+                                uint32_t* detail) {
+    struct Frame { uint32_t blk; uint32_t k; uint64_t base; };
+    Frame stk[66];
+    int depth = 0;
+    stk[0].blk = root_blk; stk[0].k = 0; stk[0].base = 0;
+    uint32_t bw = 3, height = 0;
+    while (depth >= 0) {
+        Frame& f = stk[depth];
+        uint32_t len;
+        const uint8_t* p = store_block(s, f.blk, len);
+        Rd r(p, len);
+        if (depth == 0) { uint64_t cnt; amt_root_begin(r, 3, bw, height, cnt); }
+        uint32_t lvl = height - (uint32_t)depth;
+        AmtNodeHdr h;
+        amt_node_begin(r, bw, h);
+        if (f.k == 0) {
+            uint32_t nv = rd_array(r);
+            node_events<MODE>(r, p, h, nv, f.base, m, wo, ec);
+            amt_node_finish(r, h, nv, lvl);
+            if (r.err) { *detail = r.err; return DC_DECODE; }
+        } else if (r.err) { *detail = r.err; return DC_DECODE; }
+        if (h.nl == 0 || f.k >= h.nl) { depth--; continue; }
+        uint32_t slot = bm_select(h.bm, f.k);
+        int32_t child = store_lookup(s, p + h.links_off + 43 * f.k + 5);
+        if (child < 0) { *detail = 0; return DC_MISSING; }
+        if (wbits) witness_mark(wbits, (uint32_t)child);
+        uint64_t cbase = f.base + (uint64_t)slot * pow_sat(bw, lvl);
+        f.k++;
+        depth++;
+        stk[depth].blk = (uint32_t)child; stk[depth].k = 0; stk[depth].base = cbase;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ pass 1
+struct Pass1Args {
+    StoreView store;
+    Matcher m;
+    const uint8_t* events_roots;
+    const uint8_t* has_root;
+    uint64_t lo, hi;
+    uint32_t* match_bits;          // bit (i - lo)
+    unsigned long long* err;
+    unsigned long long* stats;     // [0] nodes scanned, [1] bytes scanned
+};
+
+// One thread per receipt: resolve its events root CID, decode the root node of its events AMT,
+// test every StampedEvent. The common single-node AMT (≤ 2^bw events) never leaves this
+// function; taller AMTs fall through to the generic walker.
+__global__ void __launch_bounds__(128) k_pass1(Pass1Args a) {
+    uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool matched = false;
+    uint32_t bytes = 0, nodes = 0;
+    if (i < a.hi && a.has_root[i]) {
+        int32_t blk = store_lookup(a.store, a.events_roots + 38 * i);
+        if (blk < 0) report_error(a.err, ST_PASS1, i, DC_MISSING, 0);
+        else {
+            uint32_t len;
+            const uint8_t* p = store_block(a.store, (uint32_t)blk, len);
+            bytes = len + 38; nodes = 1;
+            Rd r(p, len);
+            uint32_t bw, height;
+            uint64_t cnt;
+            amt_root_begin(r, 3, bw, height, cnt);
+            AmtNodeHdr h;
+            amt_node_begin(r, bw, h);
+            uint32_t nv = rd_array(r);
+            WalkOut wo{0, 0, false};
+            node_events<WALK_ANY>(r, p, h, nv, 0, a.m, wo, nullptr);
+            amt_node_finish(r, h, nv, height);
+            if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
+            else if (h.nl) {
+                uint32_t detail = 0;
+                WalkOut w2{0, 0, false};
+                uint32_t rc = walk_events<WALK_ANY>(a.store, (uint32_t)blk, a.m, nullptr, w2, nullptr, &detail);
+                if (rc) report_error(a.err, ST_PASS1, i, rc, detail);
+                else matched = w2.any;
+            } else matched = wo.any;
+        }
+    }
+    unsigned b = __ballot_sync(0xffffffffu, matched);
+    if ((threadIdx.x & 31) == 0) a.match_bits[((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5] = b;
+    // per-warp statistics (algorithmic bytes of the scan)
+    for (int o = 16; o; o >>= 1) { bytes += __shfl_xor_sync(0xffffffffu, bytes, o); nodes += __shfl_xor_sync(0xffffffffu, nodes, o); }
+    if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(a.stats, (unsigned long long)nodes); atomicAdd(a.stats + 1, (unsigned long long)bytes); }
+}
+
+// ------------------------------------------------------------------------------------------ receipts AMT
+// Amtv0<Receipt>::get(i) with recording (events/generator.rs:249). 1 = Some, 0 = None, <0 = -DevCode.
+__device__ int receipts_get(const StoreView& s, uint32_t root_blk, uint64_t i, uint32_t* wbits, uint32_t* detail) {
+    uint32_t len;
+    const uint8_t* p = store_block(s, root_blk, len);
+    Rd r(p, len);
+    uint32_t bw, height;
+    uint64_t cnt;
+    amt_root_begin(r, 0, bw, height, cnt);
+    if (r.err) { *detail = r.err; return -(int)DC_DECODE; }
+    if (i >= pow_sat(3, height + 1)) return 0;
+    uint32_t lvl = height;
+    for (;;) {
+        AmtNodeHdr h;
+        amt_node_begin(r, 3, h);
+        uint32_t nv = rd_array(r);
+        for (uint32_t v = 0; v < nv && !r.err; v++) parse_receipt(r);
+        amt_node_finish(r, h, nv, lvl);
+        if (r.err) { *detail = r.err; return -(int)DC_DECODE; }
+        uint32_t idx = (uint32_t)((i / pow_sat(3, lvl)) & 7);
+        if (h.nl == 0) {
+            if (lvl != 0) return 0;
+            return bm_test(h.bm, idx) ? 1 : 0;
+        }
+        if (!bm_test(h.bm, idx)) return 0;
+        uint32_t k = bm_rank(h.bm, idx);
+        int32_t child = store_lookup(s, p + h.links_off + 43 * k + 5);
+        if (child < 0) { *detail = 0; return -(int)DC_MISSING; }
+        witness_mark(wbits, (uint32_t)child);
+        p = store_block(s, (uint32_t)child, len);
+        r = Rd(p, len);
+        lvl--;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ pass 2
+struct Pass2Args {
+    StoreView store;
+    Matcher m;
+    const uint8_t* events_roots;
+    uint64_t lo;
+    const uint32_t* match_rel;     // positions relative to lo, ascending
+    uint64_t n_match;
+    uint32_t receipts_root_blk;
+    const uint8_t* exec_cids;      // exec_raw[pos] 38-byte CIDs
+    const uint32_t* exec_idx;      // execution order → position in exec_raw
+    const unsigned long long* n_exec;
+    uint32_t* wbits;
+    unsigned long long* err;
+    uint32_t* cnt;                 // per match: number of proofs (phase COUNT out / EMIT in)
+    uint32_t* nbytes;              // per match: blob bytes
+    const uint64_t* proof_base;    // EMIT: exclusive scans
+    const uint64_t* byte_base;
+    ipcfp_event_proof* proofs;
+    uint8_t* blob;
+};
+
+template <int MODE> __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_match) return;
+    uint64_t i = a.lo + a.match_rel[t];
+    if (MODE == WALK_COUNT) {
+        a.cnt[t] = 0; a.nbytes[t] = 0;
+        // exec.get(i) comes first (events/generator.rs:244-246)
+        if (i >= *a.n_exec) { report_error(a.err, ST_PASS2, i, DC_MISSING_EXEC, 0); return; }
+        uint32_t detail = 0;
+        int got = receipts_get(a.store, a.receipts_root_blk, i, a.wbits, &detail);
+        if (got < 0) { report_error(a.err, ST_PASS2, i, (uint32_t)(-got), detail); return; }
+        if (got == 0) return;  // `continue` at :249-251
+    } else if (a.cnt[t] == 0) return;
+    int32_t root = store_lookup(a.store, a.events_roots + 38 * i);
+    if (root < 0) { report_error(a.err, ST_PASS2, i, DC_MISSING, 0); return; }
+    if (MODE == WALK_COUNT) witness_mark(a.wbits, (uint32_t)root);
+    WalkOut wo{0, 0, false};
+    uint32_t detail = 0;
+    uint32_t rc;
+    if (MODE == WALK_COUNT) rc = walk_events<WALK_COUNT>(a.store, (uint32_t)root, a.m, a.wbits, wo, nullptr, &detail);
+    else {
+        EmitCtx ec;
+        ec.proofs = a.proofs + a.proof_base[t];
+        ec.blob = a.blob;
+        ec.blob_off = a.byte_base[t];
+        ec.exec_index = i;
+        ec.msg_cid = a.exec_cids + 38ull * a.exec_idx[i];
+        rc = walk_events<WALK_EMIT>(a.store, (uint32_t)root, a.m, nullptr, wo, &ec, &detail);
+    }
+    if (rc) { report_error(a.err, ST_PASS2, i, rc, detail); return; }
+    if (MODE == WALK_COUNT) { a.cnt[t] = wo.nproofs; a.nbytes[t] = wo.nbytes; }
+}
+
+// ------------------------------------------------------------------------------------------ setup + message AMT walk
+#define IPCFP_MAX_PARENTS 64
+struct SetupArgs {
+    StoreView store;
+    uint32_t n_parents;
+    const uint8_t* parent_cids;    // device copies
+    const uint8_t* txmeta_cids;
+    const uint8_t* child_cid;      // 38
+    const uint8_t* receipts_root;  // 38
+    uint32_t skip_tx;
+    uint32_t* wbits;
+    unsigned long long* err;
+    // outputs
+    uint32_t* receipts_root_blk;
+    uint32_t* f_blk; uint32_t* f_meta; uint64_t* f_base;  // initial frontier: one item per message AMT
+    unsigned long long* f_count;
+    uint32_t* amt_height;   // per AMT
+    uint64_t* amt_count;    // per AMT (root.count)
+    uint32_t* missing_base; // flag: a base-witness CID is not in the store (→ materialize error)
+};
+// meta of a frontier item: amt ordinal << 16 | is_root << 8 | level
+__device__ __forceinline__ uint32_t make_meta(uint32_t amt, uint32_t is_root, uint32_t level) { return (amt << 16) | (is_root << 8) | level; }
+
+// Single-thread prologue: marks the base witness, decodes each parent's TxMeta, loads (and
+// validates) the receipts-AMT root and the BLS/SECP AMT roots, seeds the BFS frontier.
+__global__ void k_setup(SetupArgs a) {
+    if (threadIdx.x || blockIdx.x) return;
+    const StoreView& s = a.store;
+    uint32_t namt = 0;
+    if (!a.skip_tx) {
+        auto base = [&](const uint8_t* cid) {
+            int32_t b = store_lookup(s, cid);
+            if (b < 0) *a.missing_base = 1; else witness_mark(a.wbits, (uint32_t)b);
+        };
+        for (uint32_t b = 0; b < a.n_parents; b++) base(a.parent_cids + 38 * b);
+        base(a.child_cid);
+        base(a.receipts_root);
+        for (uint32_t b = 0; b < a.n_parents; b++) base(a.txmeta_cids + 38 * b);
+    }
+    // TxMeta + message AMT roots (needed for the execution order even when skip_tx)
+    for (uint32_t b = 0; b < a.n_parents; b++) {
+        int32_t tb = store_lookup(s, a.txmeta_cids + 38 * b);
+        if (tb < 0) { report_error(a.err, ST_TXMETA, 3 * b, DC_MISSING, 0); return; }
+        if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)tb);
+        uint32_t len;
+        const uint8_t* p = store_block(s, (uint32_t)tb, len);
+        Rd r(p, len);
+        rd_array_exact(r, 2);
+        uint32_t c0 = rd_cid(r), c1 = rd_cid(r);
+        rd_end(r);
+        if (r.err) { report_error(a.err, ST_TXMETA, 3 * b, DC_DECODE, r.err); return; }
+        for (uint32_t k = 0; k < 2; k++) {
+            int32_t rb = store_lookup(s, p + (k ? c1 : c0));
+            if (rb < 0) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_MISSING, 0); return; }
+            if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)rb);
+            uint32_t rl;
+            const uint8_t* rp = store_block(s, (uint32_t)rb, rl);
+            Rd rr(rp, rl);
+            uint32_t bw, h;
+            uint64_t cnt;
+            amt_root_begin(rr, 0, bw, h, cnt);
+            if (rr.err) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_DECODE, rr.err); return; }
+            a.f_blk[namt] = (uint32_t)rb;
+            a.f_meta[namt] = make_meta(namt, 1, h);
+            a.f_base[namt] = 0;
+            a.amt_height[namt] = h;
+            a.amt_count[namt] = cnt;
+            namt++;
+        }
+    }
+    *a.f_count = namt;
+    // Amtv0::<MessageReceipt>::load(&receipts_root, &rec_receipts) (events/generator.rs:195-196)
+    int32_t rb = store_lookup(s, a.receipts_root);
+    if (rb < 0) { report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_MISSING, 0); return; }
+    witness_mark(a.wbits, (uint32_t)rb);
+    *a.receipts_root_blk = (uint32_t)rb;
+    uint32_t len;
+    const uint8_t* p = store_block(s, (uint32_t)rb, len);
+    Rd r(p, len);
+    uint32_t bw, h;
+    uint64_t cnt;
+    amt_root_begin(r, 0, bw, h, cnt);
+    AmtNodeHdr hd;
+    amt_node_begin(r, 3, hd);
+    uint32_t nv = rd_array(r);
+    for (uint32_t v = 0; v < nv && !r.err; v++) parse_receipt(r);
+    amt_node_finish(r, hd, nv, h);
+    if (r.err) report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_DECODE, r.err);
+}
+
+struct LevelArgs {
+    StoreView store;
+    const uint32_t* f_blk; const uint32_t* f_meta; const uint64_t* f_base;
+    const unsigned long long* f_count;
+    uint32_t round, last_round;
+    uint32_t record;               // mark visited blocks in the witness bitmap
+    uint32_t* wbits;
+    unsigned long long* err;
+    uint32_t* child_blk;           // [item*8 + slot]
+    uint8_t* mask8;                // [item] slot bitmap (children, or values in the last round)
+    uint8_t* val_cids;             // last round: [item*8 + slot][38]
+    uint32_t cap;
+};
+// One BFS level over ALL message AMTs at once. Leaves of shallow AMTs are parked (re-emitted
+// unchanged) until the last round so that the final frontier is in (AMT, index) order.
+__global__ void __launch_bounds__(128) k_amt_level(LevelArgs a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t cnt = *a.f_count;
+    if (cnt > a.cap) cnt = a.cap;
+    if (t >= cnt) return;
+    uint32_t blk = a.f_blk[t], meta = a.f_meta[t];
+    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    if (level == 0 && a.round < a.last_round) {  // park
+        a.child_blk[t * 8] = blk;
+        a.mask8[t] = 1;
+        return;
+    }
+    uint32_t len;
+    const uint8_t* p = store_block(a.store, blk, len);
+    Rd r(p, len);
+    if (is_root) { uint32_t bw, h; uint64_t c; amt_root_begin(r, 0, bw, h, c); }
+    AmtNodeHdr h;
+    amt_node_begin(r, 3, h);
+    uint32_t nv = rd_array(r);
+    uint32_t vals_off = r.pos;
+    for (uint32_t v = 0; v < nv && !r.err; v++) (void)rd_cid(r);
+    amt_node_finish(r, h, nv, level);
+    uint64_t eidx = 3ull * (amt >> 1) + 1 + (amt & 1);
+    if (r.err) { report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err); a.mask8[t] = 0; return; }
+    uint32_t mask = 0;
+    if (h.nl) {
+        for (uint32_t k = 0; k < h.nl; k++) {
+            uint32_t slot = bm_select(h.bm, k);
+            int32_t child = store_lookup(a.store, p + h.links_off + 43 * k + 5);
+            if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); continue; }
+            if (a.record) witness_mark(a.wbits, (uint32_t)child);
+            a.child_blk[t * 8 + slot] = (uint32_t)child;
+            mask |= 1u << slot;
+        }
+    } else if (a.round == a.last_round) {
+        for (uint32_t v = 0; v < nv; v++) {
+            uint32_t slot = bm_select(h.bm, v);
+            const uint8_t* src = p + vals_off + 43 * v + 5;
+            uint8_t* dst = a.val_cids + (t * 8 + slot) * 38;
+            for (int b = 0; b < 38; b++) dst[b] = src[b];
+            mask |= 1u << slot;
+        }
+    }
+    a.mask8[t] = (uint8_t)mask;
+}
+
+struct GatherArgs {
+    const uint32_t* slot_idx;                  // ordered set bits of mask8 (item*8 + slot)
+    const unsigned long long* n_out;
+    const uint32_t* f_blk; const uint32_t* f_meta; const uint64_t* f_base;
+    const uint32_t* child_blk;
+    uint32_t* o_blk; uint32_t* o_meta; uint64_t* o_base;
+    unsigned long long* o_count;
+    unsigned long long* err;
+    uint32_t cap;
+};
+__global__ void k_gather_frontier(GatherArgs a) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n = *a.n_out;
+    if (j == 0) {
+        if (n > a.cap) { report_error(a.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); *a.o_count = a.cap; }
+        else *a.o_count = n;
+    }
+    if (n > a.cap) n = a.cap;
+    if (j >= n) return;
+    uint32_t si = a.slot_idx[j];
+    uint32_t item = si >> 3, slot = si & 7;
+    uint32_t meta = a.f_meta[item];
+    uint32_t level = meta & 0xff;
+    a.o_blk[j] = a.child_blk[si];
+    if (level == 0) { a.o_meta[j] = meta; a.o_base[j] = a.f_base[item]; }  // parked leaf
+    else {
+        a.o_meta[j] = make_meta(meta >> 16, 0, level - 1);
+        a.o_base[j] = a.f_base[item] + (uint64_t)slot * pow_sat(3, level);
+    }
+}
+__global__ void k_gather_values(const uint32_t* __restrict__ slot_idx, const unsigned long long* n_out, const uint8_t* __restrict__ val_cids,
+                                uint8_t* exec_raw, uint64_t cap) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n = *n_out;
+    if (n > cap) n = cap;
+    if (j >= n) return;
+    const uint8_t* src = val_cids + 38ull * slot_idx[j];
+    uint8_t* dst = exec_raw + 38 * j;
+    for (int b = 0; b < 38; b++) dst[b] = src[b];
+}
+
+// first-seen dedup of the raw execution list (events/utils.rs:56-91): hash set keyed by the full
+// CID holding the smallest position; an entry survives iff it holds its own position.
+__global__ void k_dedup_insert(const uint8_t* __restrict__ raw, uint64_t n, unsigned long long* table, uint64_t mask) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* c = raw + 38 * i;
+    uint64_t h = mix64(load_u64_le(c + 6) ^ (load_u64_le(c + 22) * 0x9E3779B97F4A7C15ULL) ^ c[1]);
+    uint32_t fp = (uint32_t)(h >> 32) | 1u;
+    unsigned long long mine = ((unsigned long long)fp << 32) | (unsigned long long)(i + 1);
+    uint64_t slot = h & mask;
+    for (;;) {
+        unsigned long long e = table[slot];
+        if (e == 0) { e = atomicCAS(&table[slot], 0ull, mine); if (e == 0) return; }
+        if ((uint32_t)(e >> 32) == fp && cid38_equal(raw + 38ull * ((uint32_t)e - 1), c)) { atomicMin(&table[slot], mine); return; }
+        slot = (slot + 1) & mask;
+    }
+}
+__global__ void k_dedup_flags(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ table, uint64_t mask,
+                              uint32_t* keep_bits) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        const uint8_t* c = raw + 38 * i;
+        uint64_t h = mix64(load_u64_le(c + 6) ^ (load_u64_le(c + 22) * 0x9E3779B97F4A7C15ULL) ^ c[1]);
+        uint32_t fp = (uint32_t)(h >> 32) | 1u;
+        uint64_t slot = h & mask;
+        for (;;) {
+            unsigned long long e = table[slot];
+            if (e == 0) break;  // cannot happen: every entry was inserted
+            if ((uint32_t)(e >> 32) == fp && cid38_equal(raw + 38ull * ((uint32_t)e - 1), c)) { keep = ((uint32_t)e - 1) == (uint32_t)i; break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+    unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0) keep_bits[i >> 5] = b;
+}
+
+// ------------------------------------------------------------------------------------------ host orchestration
+struct EventResultBox {
+    ipcfp_event_result r;  // must stay first
+    PinnedArray matching, proofs, blob;
+    WitnessOut wit;
+};
+
+static void throw_device_error(uint64_t key) {
+    uint32_t stage = (uint32_t)(key >> 56), code = (uint32_t)(key >> 8) & 0xff, detail = (uint32_t)key & 0xff;
+    uint64_t index = (key >> 16) & 0xFFFFFFFFFFull;
+    ipcfp_status st;
+    const char* what;
+    switch (code) {
+        case DC_MISSING: st = IPCFP_ERR_MISSING_BLOCK; what = "missing block"; break;
+        case DC_DECODE: st = IPCFP_ERR_DECODE; what = "decode error"; break;
+        case DC_MISSING_EXEC: st = IPCFP_ERR_MISSING_EXEC; what = "Missing message at index"; break;
+        case DC_UNSUPPORTED: st = IPCFP_ERR_UNSUPPORTED; what = "unsupported input (frontier overflow)"; break;
+        default: st = IPCFP_ERR_DECODE; what = "error"; break;
+    }
+    uint64_t out_index = UINT64_MAX;
+    const char* stage_name = "?";
+    switch (stage) {
+        case ST_TXMETA:
+            stage_name = "message AMTs";
+            if (index != 0xFFFFFFFFFFull && index % 3 == 0 && code == DC_MISSING) out_index = index / 3;  // missing TxMeta of parent b
+            break;
+        case ST_RECEIPTS_ROOT: stage_name = "receipts AMT root"; break;
+        case ST_PASS1: stage_name = "pass 1"; out_index = index; break;
+        case ST_PASS2: stage_name = "pass 2"; out_index = index; break;
+        case ST_WITNESS: stage_name = "materialize"; break;
+        default: break;
+    }
+    throw Error(st, std::string(what) + " in " + stage_name + " (detail " + std::to_string(detail) + ")", out_index);
+}
+
+void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
+    s->use();
+    if (!t || !t->child_cid || !t->receipts_root || (t->n_parents && (!t->parent_cids || !t->parent_txmeta_cids)))
+        throw Error(IPCFP_ERR_INVALID_ARG, "tipset descriptor has null fields");
+    if (t->n_parents > IPCFP_MAX_PARENTS) throw Error(IPCFP_ERR_UNSUPPORTED, "too many parent blocks");
+    if (t->n_receipts >= 0xffffffffull) throw Error(IPCFP_ERR_UNSUPPORTED, "more than 2^32 receipts");
+    if (t->n_receipts && (!t->events_roots || !t->has_events_root)) throw Error(IPCFP_ERR_INVALID_ARG, "events roots missing");
+    td.parent_epoch = t->parent_epoch; td.child_epoch = t->child_epoch; td.n_parents = t->n_parents;
+    td.parent_cids.assign(t->parent_cids, t->parent_cids + 38ull * t->n_parents);
+    td.txmeta_cids.assign(t->parent_txmeta_cids, t->parent_txmeta_cids + 38ull * t->n_parents);
+    memcpy(td.child_cid, t->child_cid, 38);
+    memcpy(td.receipts_root, t->receipts_root, 38);
+    td.has_state_root = t->child_parent_state_root != nullptr;
+    if (td.has_state_root) memcpy(td.child_state_root, t->child_parent_state_root, 38);
+    td.n_receipts = t->n_receipts;
+    td.events_roots.alloc(t->n_receipts * 38 + 64);
+    td.has_root.alloc(t->n_receipts + 64);
+    if (t->n_receipts) {
+        IPCFP_CUDA(cudaMemcpyAsync(td.events_roots.p, t->events_roots, t->n_receipts * 38, cudaMemcpyHostToDevice, s->stream));
+        IPCFP_CUDA(cudaMemcpyAsync(td.has_root.p, t->has_events_root, t->n_receipts, cudaMemcpyHostToDevice, s->stream));
+    }
+}
+
+// keccak256(event_signature) on the device (EventMatcher::new, events/generator.rs:30-35)
+__global__ void k_make_matcher(const uint8_t* sig, uint32_t len, Matcher* out) {
+    Digest d;
+    keccak256(sig, len, d);
+    out->t0[0] = d.w[0]; out->t0[1] = d.w[1]; out->t0[2] = d.w[2]; out->t0[3] = d.w[3];
+}
+
+ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*/, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/) {
+    s->use();
+    cudaStream_t st = s->stream;
+    if (!spec || !spec->event_signature || !spec->topic_1) throw Error(IPCFP_ERR_INVALID_ARG, "event spec has null fields");
+    if (!sharded) { lo = 0; hi = td.n_receipts; }
+    if (lo > hi || hi > td.n_receipts) throw Error(IPCFP_ERR_INVALID_ARG, "receipt range out of bounds");
+    const uint64_t N = hi - lo;
+    const uint64_t nblk = s->n;
+    const bool skip_tx = (flags & IPCFP_SCAN_SKIP_TX_AMTS) != 0;
+    unsigned long long* dw = s->dev_words.p;  // [0] err, [1..] counters
+    uint64_t* hw = s->host_words.p;
+
+    IPCFP_CUDA(cudaEventRecord(s->ev[0], st));
+    IPCFP_CUDA(cudaMemsetAsync(dw, 0xff, 8, st));
+    IPCFP_CUDA(cudaMemsetAsync(dw + 1, 0, 40 * 8, st));
+
+    // ---- matcher
+    Matcher mh;
+    memset(&mh, 0, sizeof mh);
+    {
+        size_t n1 = strlen(spec->topic_1);
+        uint8_t t1[32];
+        memset(t1, 0, 32);
+        memcpy(t1, spec->topic_1, n1 < 32 ? n1 : 32);  // ascii_to_bytes32 (evm.rs:72-78)
+        memcpy(mh.t1, t1, 32);
+        mh.actor = spec->actor_id_filter;
+        mh.has_actor = spec->has_actor_id_filter ? 1 : 0;
+    }
+    size_t siglen = strlen(spec->event_signature);
+    AsyncBuf<uint8_t> small(4096 + siglen + 38ull * (2 * td.n_parents + 2), st);
+    uint8_t* d_sig = small.p + 1024;                       // 8-byte aligned
+    uint8_t* d_cids = small.p + 1024 + ((siglen + 64) & ~(size_t)63);
+    Matcher* d_matcher = (Matcher*)small.p;
+    {
+        std::vector<uint8_t> hb(siglen + 16, 0);
+        memcpy(hb.data(), spec->event_signature, siglen);
+        IPCFP_CUDA(cudaMemcpyAsync(d_sig, hb.data(), siglen + 16, cudaMemcpyHostToDevice, st));
+        std::vector<uint8_t> cb;
+        cb.insert(cb.end(), td.parent_cids.begin(), td.parent_cids.end());
+        cb.insert(cb.end(), td.txmeta_cids.begin(), td.txmeta_cids.end());
+        cb.insert(cb.end(), td.child_cid, td.child_cid + 38);
+        cb.insert(cb.end(), td.receipts_root, td.receipts_root + 38);
+        IPCFP_CUDA(cudaMemcpyAsync(d_cids, cb.data(), cb.size(), cudaMemcpyHostToDevice, st));
+        IPCFP_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
+    }
+    k_make_matcher<<<1, 1, 0, st>>>(d_sig, (uint32_t)siglen, d_matcher); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 16, d_matcher, 32, cudaMemcpyDeviceToHost, st));
+
+    // ---- witness bitmap + setup
+    AsyncBuf<uint32_t> wbits((nblk + 31) / 32 + 8, st);
+    wbits.zero();
+    const uint32_t namt_max = 2 * td.n_parents;
+    const uint64_t cap = 4 * nblk + 1024;
+    AsyncBuf<uint32_t> fA_blk(cap, st), fA_meta(cap, st), fB_blk(cap, st), fB_meta(cap, st);
+    AsyncBuf<uint64_t> fA_base(cap, st), fB_base(cap, st);
+    AsyncBuf<uint32_t> misc(64 + 2 * IPCFP_MAX_PARENTS, st);
+    AsyncBuf<uint64_t> amt_count(2 * IPCFP_MAX_PARENTS, st);
+    misc.zero();
+    SetupArgs sa;
+    sa.store = s->view; sa.n_parents = td.n_parents;
+    sa.parent_cids = d_cids; sa.txmeta_cids = d_cids + 38ull * td.n_parents;
+    sa.child_cid = d_cids + 76ull * td.n_parents; sa.receipts_root = sa.child_cid + 38;
+    sa.skip_tx = skip_tx; sa.wbits = wbits.p; sa.err = dw;
+    sa.receipts_root_blk = misc.p; sa.missing_base = misc.p + 1; sa.amt_height = misc.p + 64;
+    sa.f_blk = fA_blk.p; sa.f_meta = fA_meta.p; sa.f_base = fA_base.p; sa.f_count = dw + 1;
+    sa.amt_count = amt_count.p;
+    k_setup<<<1, 32, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 24, misc.p, (64 + 2 * IPCFP_MAX_PARENTS) * 4, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    memcpy(mh.t0, hw + 16, 32);
+    const uint32_t* misc_h = (const uint32_t*)(hw + 24);
+    const uint32_t receipts_root_blk = misc_h[0];
+    const bool missing_base = misc_h[1] != 0;
+    uint32_t namt = (uint32_t)hw[1];
+    uint32_t last_round = 0;
+    for (uint32_t k = 0; k < namt && k < namt_max; k++) last_round = std::max(last_round, misc_h[64 + k]);
+
+    // ---- message AMT BFS (recording + raw execution list)
+    IPCFP_CUDA(cudaEventRecord(s->ev[1], st));
+    AsyncBuf<uint32_t> child_blk(cap * 8, st), slot_idx(cap * 8 + 32, st);
+    AsyncBuf<uint8_t> mask8(cap + 64, st);
+    AsyncBuf<uint64_t> word_prefix(cap * 8 / 32 + 64, st), scratch(scan_scratch_elems(std::max<uint64_t>(cap, N) + 64) + 64, st);
+    AsyncBuf<uint8_t> val_cids;
+    uint32_t *cb = fA_blk.p, *cm = fA_meta.p, *nb_ = fB_blk.p, *nm = fB_meta.p;
+    uint64_t *cbase = fA_base.p, *nbase = fB_base.p;
+    unsigned long long *ccount = dw + 1, *ncount = dw + 2;
+    uint64_t bound = namt;  // upper bound of the frontier size in this round
+    uint64_t last_bound = 0;
+    for (uint32_t round = 0; round <= last_round; round++) {
+        uint64_t items = std::min<uint64_t>(bound, cap);
+        if (round == last_round) { val_cids.alloc(items * 8 * 38 + 64, st); last_bound = items; }
+        IPCFP_CUDA(cudaMemsetAsync(mask8.p, 0, (items + 3) / 4 * 4 + 4, st));
+        LevelArgs la;
+        la.store = s->view; la.f_blk = cb; la.f_meta = cm; la.f_base = cbase; la.f_count = ccount;
+        la.round = round; la.last_round = last_round; la.record = skip_tx ? 0 : 1; la.wbits = wbits.p; la.err = dw;
+        la.child_blk = child_blk.p; la.mask8 = mask8.p; la.val_cids = val_cids.p; la.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
+        if (items) { k_amt_level<<<div_up(items, 128), 128, 0, st>>>(la); IPCFP_LAUNCH_CHECK(); }
+        bitmap_to_indices((const uint32_t*)mask8.p, items * 8, slot_idx.p, (uint64_t*)ncount, word_prefix.p, scratch.p, st);
+        if (round < last_round) {
+            GatherArgs ga;
+            ga.slot_idx = slot_idx.p; ga.n_out = ncount; ga.f_blk = cb; ga.f_meta = cm; ga.f_base = cbase; ga.child_blk = child_blk.p;
+            ga.o_blk = nb_; ga.o_meta = nm; ga.o_base = nbase; ga.o_count = ncount; ga.err = dw; ga.cap = la.cap;
+            uint64_t nb_bound = std::min<uint64_t>(items * 8, cap);
+            k_gather_frontier<<<div_up(std::max<uint64_t>(nb_bound, 1), 256), 256, 0, st>>>(ga); IPCFP_LAUNCH_CHECK();
+            std::swap(cb, nb_); std::swap(cm, nm); std::swap(cbase, nbase); std::swap(ccount, ncount);
+            bound = nb_bound;
+        }
+    }
+    // ncount now holds the number of raw execution entries
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 2, ncount, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    uint64_t nraw = std::min<uint64_t>(hw[2], last_bound * 8);
+    AsyncBuf<uint8_t> exec_raw(nraw * 38 + 64, st);
+    AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
+    unsigned long long* n_exec_dev = dw + 3;
+    if (nraw) {
+        k_gather_values<<<div_up(nraw, 256), 256, 0, st>>>(slot_idx.p, ncount, val_cids.p, exec_raw.p, nraw); IPCFP_LAUNCH_CHECK();
+        uint64_t slots = 64;
+        while (slots < 2 * nraw) slots <<= 1;
+        AsyncBuf<unsigned long long> dtab(slots, st);
+        dtab.zero();
+        k_dedup_insert<<<div_up(nraw, 256), 256, 0, st>>>(exec_raw.p, nraw, dtab.p, slots - 1); IPCFP_LAUNCH_CHECK();
+        k_dedup_flags<<<div_up((nraw + 31) / 32 * 32, 256), 256, 0, st>>>(exec_raw.p, nraw, dtab.p, slots - 1, keep_bits.p); IPCFP_LAUNCH_CHECK();
+        AsyncBuf<uint64_t> wp2((nraw + 31) / 32 + 8, st);
+        bitmap_to_indices(keep_bits.p, nraw, exec_idx.p, (uint64_t*)n_exec_dev, wp2.p, scratch.p, st);
+    } else IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));
+    val_cids.release();
+    IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
+
+    // ---- PASS 1
+    AsyncBuf<uint32_t> match_bits((N + 31) / 32 + 8, st);
+    Pass1Args p1;
+    p1.store = s->view; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
+    p1.match_bits = match_bits.p; p1.err = dw; p1.stats = dw + 4;
+    if (N) { k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1); IPCFP_LAUNCH_CHECK(); }
+    IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
+    AsyncBuf<uint32_t> match_rel(N + 32, st);
+    AsyncBuf<uint64_t> wp3((N + 31) / 32 + 8, st);
+    unsigned long long* n_match_dev = dw + 6;
+    bitmap_to_indices(match_bits.p, (N + 31) / 32 * 32, match_rel.p, (uint64_t*)n_match_dev, wp3.p, scratch.p, st);
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8 * 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    const uint64_t n_exec = hw[3], M = hw[6];
+    const uint64_t pass1_nodes = hw[4], pass1_bytes = hw[5];
+
+    // ---- PASS 2
+    std::unique_ptr<EventResultBox> box(new EventResultBox());
+    memset(&box->r, 0, sizeof box->r);
+    AsyncBuf<uint32_t> cnt(M + 8, st), nby(M + 8, st);
+    AsyncBuf<uint64_t> pbase(M + 8, st), bbase(M + 8, st);
+    Pass2Args p2;
+    p2.store = s->view; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
+    p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
+    p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.nbytes = nby.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
+    p2.proofs = nullptr; p2.blob = nullptr;
+    uint64_t n_proofs = 0, n_bytes = 0;
+    AsyncBuf<ipcfp_event_proof> d_proofs;
+    AsyncBuf<uint8_t> d_blob;
+    if (M) {
+        k_pass2<WALK_COUNT><<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
+        exclusive_scan_u32(cnt.p, pbase.p, M, (uint64_t*)(dw + 7), scratch.p, st);
+        exclusive_scan_u32(nby.p, bbase.p, M, (uint64_t*)(dw + 10), scratch.p, st);
+        IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 12 * 8, cudaMemcpyDeviceToHost, st));
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+        if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+        n_proofs = hw[7]; n_bytes = hw[10];
+        d_proofs.alloc(n_proofs + 1, st);
+        d_blob.alloc(n_bytes + 16, st);
+        p2.proofs = d_proofs.p; p2.blob = d_blob.p;
+        if (n_proofs) { k_pass2<WALK_EMIT><<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK(); }
+    }
+    IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
+
+    // ---- results to the host
+    box->matching = PinnedArray(s->pool, (M + 1) * 8);
+    box->proofs = PinnedArray(s->pool, (n_proofs + 1) * sizeof(ipcfp_event_proof));
+    box->blob = PinnedArray(s->pool, n_bytes + 16);
+    AsyncBuf<uint32_t> tmp_rel;  // match_rel → absolute u64 on the host below
+    PinnedArray rel(s->pool, (M + 1) * 4);
+    if (M) IPCFP_CUDA(cudaMemcpyAsync(rel.p, match_rel.p, M * 4, cudaMemcpyDeviceToHost, st));
+    if (n_proofs) IPCFP_CUDA(cudaMemcpyAsync(box->proofs.p, d_proofs.p, n_proofs * sizeof(ipcfp_event_proof), cudaMemcpyDeviceToHost, st));
+    if (n_bytes) IPCFP_CUDA(cudaMemcpyAsync(box->blob.p, d_blob.p, n_bytes, cudaMemcpyDeviceToHost, st));
+
+    // ---- witness
+    if (missing_base && !skip_tx) {
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+        throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
+    }
+    materialize_witness(s, wbits.p, box->wit, true);
+    IPCFP_CUDA(cudaEventRecord(s->ev[5], st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    {
+        uint64_t* mo = box->matching.as<uint64_t>();
+        const uint32_t* rp = rel.as<uint32_t>();
+        for (uint64_t k = 0; k < M; k++) mo[k] = lo + rp[k];
+    }
+    ipcfp_event_result& r = box->r;
+    r.n_matching = M; r.matching_indices = box->matching.as<uint64_t>();
+    r.n_proofs = n_proofs; r.proofs = box->proofs.as<ipcfp_event_proof>();
+    r.data_blob = box->blob.as<uint8_t>(); r.data_blob_size = n_bytes;
+    box->wit.fill(r.witness);
+    r.n_exec = n_exec;
+    float ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[5])); r.ms_total = ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[1], s->ev[2])); r.ms_txamt = ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3])); r.ms_pass1 = ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[3], s->ev[4])); r.ms_pass2 = ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[4], s->ev[5])); r.ms_witness = ms;
+    r.pass1_bytes = pass1_bytes; r.pass1_nodes = pass1_nodes;
+    return &box.release()->r;
+}
+
+void event_result_free(ipcfp_event_result* r) { delete reinterpret_cast<EventResultBox*>(r); }
+
+void witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap, uint64_t* n) {
+    uint64_t m = r->witness.n_blocks;
+    if (m > cap) throw Error(IPCFP_ERR_INVALID_ARG, "device buffer too small for the witness CID list");
+    if (m) IPCFP_CUDA(cudaMemcpy(dev_ptr, r->witness.cids, m * 38, cudaMemcpyHostToDevice));
+    *n = m;
+}
+
+}  // namespace ipcfp

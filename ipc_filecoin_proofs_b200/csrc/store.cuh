@@ -1,0 +1,81 @@
+// store.cuh — device-resident IPLD block arena + CID hash index.
+//
+// Replaces the reference's Blockstore implementations (client/blockstore.rs:20-37,
+// client/cached_blockstore.rs:53-85) for the hot path: `get` is a hash probe that returns a
+// block INDEX (offset/length into the arena) instead of an owned copy, and RecordingBlockStore
+// (common/blockstore.rs:8-39) becomes one bit per block in a witness bitmap.
+//
+// HBM layout (n blocks, B blob bytes):
+//   arena    : [16 B pad][blob as given, any offsets][16 B pad]      B + 32
+//   offsets  : u64[n]    lengths: u32[n]
+//   digests  : Digest[n] (32 B, raw digest bytes)       cls: u8[n] (CID prefix class)
+//   table    : u64[2^k], k = ceil(log2(2n)); slot = fingerprint32 << 32 | (block index + 1)
+#pragma once
+#include "common.cuh"
+
+namespace ipcfp {
+
+#define IPCFP_MAX_CID_CLASSES 8
+
+struct StoreView {
+    const uint8_t* blob;      // arena + 16
+    const uint64_t* offsets;
+    const uint32_t* lengths;
+    const Digest* digests;
+    const uint8_t* cls;
+    const uint64_t* table;
+    uint64_t mask;
+    uint32_t n;
+    uint32_t n_classes;
+    uint8_t class_prefix[IPCFP_MAX_CID_CLASSES][8];  // 6 significant bytes each
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int cid_class(const StoreView& s, const uint8_t* cid38) {
+    for (uint32_t c = 0; c < s.n_classes; c++) {
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < 6; k++) eq &= cid38[k] == s.class_prefix[c][k];
+        if (eq) return (int)c;
+    }
+    return -1;
+}
+
+// Blockstore::get by (class, digest): block index or -1.
+__device__ __forceinline__ int32_t store_find(const StoreView& s, uint32_t cls, const Digest& d) {
+    uint64_t h = digest_hash(d, cls);
+    uint32_t fp = (uint32_t)(h >> 32) | 1u;
+    uint64_t slot = h & s.mask;
+    for (;;) {
+        uint64_t e = __ldg(s.table + slot);
+        if (e == 0) return -1;
+        if ((uint32_t)(e >> 32) == fp) {
+            uint32_t idx = (uint32_t)e - 1;
+            const Digest* q = s.digests + idx;
+            Digest o;
+            o.w[0] = __ldg(&q->w[0]); o.w[1] = __ldg(&q->w[1]); o.w[2] = __ldg(&q->w[2]); o.w[3] = __ldg(&q->w[3]);
+            if (digest_eq(o, d) && __ldg(s.cls + idx) == cls) return (int32_t)idx;
+        }
+        slot = (slot + 1) & s.mask;
+    }
+}
+// lookup by the 38 raw CID bytes (any alignment)
+__device__ __forceinline__ int32_t store_lookup(const StoreView& s, const uint8_t* cid38) {
+    int c = cid_class(s, cid38);
+    if (c < 0) return -1;
+    Digest d = load_digest(cid38 + 6);
+    return store_find(s, (uint32_t)c, d);
+}
+__device__ __forceinline__ const uint8_t* store_block(const StoreView& s, uint32_t idx, uint32_t& len) {
+    len = __ldg(s.lengths + idx);
+    return s.blob + __ldg(s.offsets + idx);
+}
+// RecordingBlockStore::get side effect: one bit per block
+__device__ __forceinline__ void witness_mark(uint32_t* wbits, uint32_t idx) {
+    uint32_t m = 1u << (idx & 31);
+    uint32_t* w = wbits + (idx >> 5);
+    if (!(*(volatile uint32_t*)w & m)) atomicOr(w, m);
+}
+#endif
+
+}  // namespace ipcfp
