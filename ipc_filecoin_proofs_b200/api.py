@@ -101,6 +101,12 @@ def lib():
     return _lib
 
 
+def _u8(x):
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(x), dtype=np.uint8).copy()
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
 def _check(st):
     if st != A.OK:
         L = lib()
@@ -179,7 +185,7 @@ class BlockStore:
         return cls(ts.cids, ts.offsets, ts.lengths, ts.blob, device, verify_cids)
 
     def get(self, cid):
-        cid = np.ascontiguousarray(cid, dtype=np.uint8)
+        cid = _u8(cid)
         ln = C.c_uint32()
         found = C.c_int()
         _check(lib().ipcfp_store_get(self._h, cid.ctypes.data, None, 0, C.byref(ln), C.byref(found)))
@@ -190,7 +196,7 @@ class BlockStore:
         return bytes(buf[:ln.value])
 
     def has(self, cid):
-        cid = np.ascontiguousarray(cid, dtype=np.uint8)
+        cid = _u8(cid)
         found = C.c_int()
         _check(lib().ipcfp_store_has(self._h, cid.ctypes.data, C.byref(found)))
         return bool(found.value)
@@ -218,8 +224,8 @@ class BlockStore:
 
     # --- read_storage_slot (storage/decode.rs:36-97), batched
     def read_storage_slots(self, root, slots):
-        root = np.ascontiguousarray(root, dtype=np.uint8)
-        slots = np.ascontiguousarray(slots, dtype=np.uint8).reshape(-1, 32)
+        root = _u8(root)
+        slots = _u8(slots).reshape(-1, 32)
         out = C.POINTER(A.SlotResultC)()
         _check(lib().ipcfp_read_storage_slots(self._h, root.ctypes.data, slots.ctypes.data if slots.size else None, len(slots), C.byref(out)))
         try:
