@@ -221,6 +221,20 @@ ipcfp_status ipcfp_generate_event_proof(ipcfp_store* s, const ipcfp_tipset_desc*
                                         uint32_t flags, ipcfp_event_result** out);
 void ipcfp_event_result_free(ipcfp_event_result* r);
 
+/* Device-resident tipset descriptor: upload once, scan many specs against it (the reference calls
+ * generate_event_proof once per EventProofSpec with the same tipsets, proofs/generator.rs:58-78). */
+typedef struct ipcfp_tipset ipcfp_tipset;
+ipcfp_status ipcfp_tipset_upload(ipcfp_store* s, const ipcfp_tipset_desc* t, ipcfp_tipset** out);
+void ipcfp_tipset_free(ipcfp_tipset* t);
+ipcfp_status ipcfp_generate_event_proof_resident(ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec, uint32_t flags,
+                                                 ipcfp_event_result** out);
+ipcfp_status ipcfp_generate_event_proof_shard_resident(ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec, uint64_t lo,
+                                                       uint64_t hi, uint32_t world_size, uint32_t rank, uint32_t flags,
+                                                       ipcfp_event_result** out);
+/* The CUDA stream (cudaStream_t) all work of this store is issued on — for callers that time with
+ * CUDA events or order their own device work after the engine's. */
+void* ipcfp_store_stream(ipcfp_store* s);
+
 /* read_storage_slot (src/proofs/storage/decode.rs:36-97), batched over k slot keys against one
  * contract_state root, with a RecordingBlockStore-equivalent witness. */
 ipcfp_status ipcfp_read_storage_slots(ipcfp_store* s, const uint8_t contract_state_root[IPCFP_CID_LEN],

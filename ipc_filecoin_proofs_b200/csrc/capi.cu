@@ -205,6 +205,36 @@ ipcfp_status ipcfp_generate_event_proof_shard(ipcfp_store* s, const ipcfp_tipset
 }
 void ipcfp_event_result_free(ipcfp_event_result* r) { if (r) event_result_free(r); }
 
+ipcfp_status ipcfp_tipset_upload(ipcfp_store* s, const ipcfp_tipset_desc* t, ipcfp_tipset** out) {
+    return guard([&] {
+        if (!s || !out) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        Store* st = reinterpret_cast<Store*>(s);
+        std::unique_ptr<TipsetDev> td(new TipsetDev());
+        tipset_upload(st, t, *td);
+        IPCFP_CUDA(cudaStreamSynchronize(st->stream));
+        *out = reinterpret_cast<ipcfp_tipset*>(td.release());
+    });
+}
+void ipcfp_tipset_free(ipcfp_tipset* t) { delete reinterpret_cast<TipsetDev*>(t); }
+ipcfp_status ipcfp_generate_event_proof_resident(ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec, uint32_t flags,
+                                                 ipcfp_event_result** out) {
+    return guard([&] {
+        if (!s || !t || !out) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        *out = generate_event_proof(reinterpret_cast<Store*>(s), nullptr, *reinterpret_cast<TipsetDev*>(t), spec, flags, false, 0, 0, 1, 0);
+    });
+}
+ipcfp_status ipcfp_generate_event_proof_shard_resident(ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec, uint64_t lo, uint64_t hi,
+                                                       uint32_t world_size, uint32_t rank, uint32_t flags, ipcfp_event_result** out) {
+    return guard([&] {
+        if (!s || !t || !out) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        *out = generate_event_proof(reinterpret_cast<Store*>(s), nullptr, *reinterpret_cast<TipsetDev*>(t), spec, flags, true, lo, hi, world_size, rank);
+    });
+}
+void* ipcfp_store_stream(ipcfp_store* s) { return s ? (void*)reinterpret_cast<Store*>(s)->stream : nullptr; }
+
 ipcfp_status ipcfp_read_storage_slots(ipcfp_store* s, const uint8_t root[IPCFP_CID_LEN], const uint8_t* slots, uint64_t k, ipcfp_slot_result** out) {
     return guard([&] {
         if (!s || !out || !root || (k && !slots)) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
