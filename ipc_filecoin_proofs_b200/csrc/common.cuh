@@ -130,11 +130,35 @@ __device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
     for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
     return v;
 }
+// 8 bytes at any alignment with two aligned 8-byte loads (may touch up to 15 bytes past q:
+// every buffer the engine reads this way is padded by ≥ 16 bytes)
+__device__ __forceinline__ uint64_t load_u64_any(const uint8_t* q) {
+    uintptr_t a = (uintptr_t)q;
+    const uint64_t* b = (const uint64_t*)(a & ~(uintptr_t)7);
+    uint32_t s = (uint32_t)(a & 7) * 8;
+    uint64_t x0 = b[0], x1 = b[1];
+    return (x0 >> s) | ((x1 << 1) << (63 - s));
+}
+// 16 bytes at any alignment with three aligned 8-byte loads
+__device__ __forceinline__ void win_load(const uint8_t* q, uint64_t& w0, uint64_t& w1) {
+    uintptr_t a = (uintptr_t)q;
+    const uint64_t* b = (const uint64_t*)(a & ~(uintptr_t)7);
+    uint32_t s = (uint32_t)(a & 7) * 8;
+    uint64_t x0 = b[0], x1 = b[1], x2 = b[2];
+    w0 = (x0 >> s) | ((x1 << 1) << (63 - s));
+    w1 = (x1 >> s) | ((x2 << 1) << (63 - s));
+}
 __device__ __forceinline__ Digest load_digest(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p;
+    const uint64_t* b = (const uint64_t*)(a & ~(uintptr_t)7);
+    uint32_t s = (uint32_t)(a & 7) * 8;
+    uint64_t x0 = b[0], x1 = b[1], x2 = b[2], x3 = b[3], x4 = b[4];
     Digest d;
-    d.w[0] = load_u64_le(p); d.w[1] = load_u64_le(p + 8); d.w[2] = load_u64_le(p + 16); d.w[3] = load_u64_le(p + 24);
+    d.w[0] = (x0 >> s) | ((x1 << 1) << (63 - s)); d.w[1] = (x1 >> s) | ((x2 << 1) << (63 - s));
+    d.w[2] = (x2 >> s) | ((x3 << 1) << (63 - s)); d.w[3] = (x3 >> s) | ((x4 << 1) << (63 - s));
     return d;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
 }  // namespace ipcfp

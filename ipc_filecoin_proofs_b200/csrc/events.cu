@@ -62,7 +62,7 @@ __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNo
                                             WalkOut& wo, EmitCtx* ec) {
     for (uint32_t v = 0; v < nv && !r.err; v++) {
         EvLog ev;
-        parse_stamped_event(r, ev);
+        decode_stamped_event(r, ev);
         if (r.err) break;
         if (event_matches(p, ev, m)) {
             wo.any = true;
@@ -80,7 +80,7 @@ __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNo
 // fvm_ipld_amt [UPSTREAM]: every reachable node is loaded through the store (and recorded when
 // wbits != nullptr). Returns 0 ok, else DevCode; detail in *detail.
 template <int MODE>
-__device__ uint32_t walk_events(const StoreView& s, uint32_t root_blk, const Matcher& m, uint32_t* wbits, WalkOut& wo, EmitCtx* ec,
+static __device__ __noinline__ uint32_t walk_events(const StoreView& s, uint32_t root_blk, const Matcher& m, uint32_t* wbits, WalkOut& wo, EmitCtx* ec,
                                 uint32_t* detail) {
     struct Frame { uint32_t blk; uint32_t k; uint64_t base; };
     Frame stk[66];
@@ -130,7 +130,7 @@ struct Pass1Args {
 // One thread per receipt: resolve its events root CID, decode the root node of its events AMT,
 // test every StampedEvent. The common single-node AMT (≤ 2^bw events) never leaves this
 // function; taller AMTs fall through to the generic walker.
-__global__ void __launch_bounds__(128) k_pass1(Pass1Args a) {
+__global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
     uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool matched = false;
     uint32_t bytes = 0, nodes = 0;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128) k_pass1(Pass1Args a) {
         else {
             uint32_t len;
             const uint8_t* p = store_block(a.store, (uint32_t)blk, len);
+            for (uint32_t o = 0; o < len; o += 128) prefetch_l2(p + o);  // whole node in flight before the dependent walk
             bytes = len + 38; nodes = 1;
             Rd r(p, len);
             uint32_t bw, height;

@@ -24,8 +24,8 @@ __device__ __forceinline__ uint64_t pow_sat(uint32_t bw, uint32_t exp) {
 }
 
 __device__ __forceinline__ bool eq32(const uint8_t* p, const uint64_t w[4]) {
-    if (load_u64_le(p) != w[0]) return false;
-    return load_u64_le(p + 8) == w[1] && load_u64_le(p + 16) == w[2] && load_u64_le(p + 24) == w[3];
+    if (load_u64_any(p) != w[0]) return false;
+    return load_u64_any(p + 8) == w[1] && load_u64_any(p + 16) == w[2] && load_u64_any(p + 24) == w[3];
 }
 
 __device__ __forceinline__ bool cid38_equal(const uint8_t* a, const uint8_t* b) {
@@ -113,17 +113,50 @@ struct EvLog {
     uint32_t toff[4];    // Case B: offsets of t1..t4 values; Case A: toff[0] = offset of the topics blob
     uint32_t data_off, data_len;
 };
-// Decodes one StampedEvent = [emitter, [[flags,key,codec,value]…]] and evaluates
-// extract_evm_log (common/evm.rs:13-59) on the fly: last duplicate key wins (:14-17); `topics`
-// selects Case A (:20-30); Case B walks t1..t4, any present tK with len != 32 voids the log
-// (:45-47), stops at the first gap (:50-52), no t1 ⇒ None (:54-56).
-__device__ __forceinline__ void parse_stamped_event(Rd& r, EvLog& ev) {
+// Per-event accumulator of the keys extract_evm_log looks at (last duplicate wins, evm.rs:14-17).
+struct EvAcc {
+    uint32_t have;    // bit0..3: t1..t4, bit4: d, bit5: topics, bit6: data
+    uint32_t len_ok;  // bit0..3: tK value is exactly 32 bytes
+    uint32_t t_off0, t_off1, t_off2, t_off3;
+    uint32_t d_off, d_len, tp_off, tp_len, da_off, da_len;
+    __device__ __forceinline__ void clear() { have = len_ok = 0; t_off0 = t_off1 = t_off2 = t_off3 = 0; d_off = d_len = tp_off = tp_len = da_off = da_len = 0; }
+    __device__ __forceinline__ void topic(uint32_t idx, uint32_t voff, uint32_t vlen) {
+        have |= 1u << idx;
+        len_ok = vlen == 32 ? (len_ok | (1u << idx)) : (len_ok & ~(1u << idx));
+        t_off0 = idx == 0 ? voff : t_off0; t_off1 = idx == 1 ? voff : t_off1;
+        t_off2 = idx == 2 ? voff : t_off2; t_off3 = idx == 3 ? voff : t_off3;
+    }
+};
+// extract_evm_log (common/evm.rs:13-59) over the accumulated keys: `topics` selects Case A (:20-30);
+// Case B walks t1..t4, any present tK with len != 32 voids the log (:45-47), stops at the first gap
+// (:50-52), no t1 ⇒ None (:54-56).
+__device__ __forceinline__ void ev_finish(const EvAcc& a, EvLog& ev) {
+    ev.some = 0; ev.case_a = 0; ev.ntopics = 0; ev.data_off = 0; ev.data_len = 0;
+    ev.toff[0] = ev.toff[1] = ev.toff[2] = ev.toff[3] = 0;
+    if (a.have & 32) {
+        ev.case_a = 1;
+        if (a.tp_len % 32 == 0) {
+            ev.some = 1; ev.ntopics = a.tp_len / 32; ev.toff[0] = a.tp_off;
+            if (a.have & 64) { ev.data_off = a.da_off; ev.data_len = a.da_len; }
+        }
+        return;
+    }
+    // number of leading present tK, and whether the first non-32-byte one comes before the first gap
+    uint32_t present = a.have & 15, ok = a.len_ok & 15;
+    uint32_t lead = present == 15 ? 4 : (uint32_t)(__ffs((int)(~present & 15)) - 1);  // t1..t(lead) present
+    uint32_t lead_mask = (1u << lead) - 1;
+    if (lead == 0 || (ok & lead_mask) != lead_mask) return;                              // no t1, or a bad length ⇒ None
+    ev.some = 1; ev.ntopics = lead;
+    ev.toff[0] = a.t_off0; ev.toff[1] = a.t_off1; ev.toff[2] = a.t_off2; ev.toff[3] = a.t_off3;
+    if (a.have & 16) { ev.data_off = a.d_off; ev.data_len = a.d_len; }
+}
+// Generic strict decoder of one StampedEvent = [emitter, [[flags,key,codec,value]…]].
+static __device__ __noinline__ void parse_stamped_event(Rd& r, EvLog& ev) {
     rd_array_exact(r, 2);
     ev.emitter = rd_uint(r);
     uint32_t ne = rd_array(r);
-    uint32_t have = 0;  // bit0..3: t1..t4, bit4: d, bit5: topics, bit6: data
-    uint32_t t_off0 = 0, t_off1 = 0, t_off2 = 0, t_off3 = 0, len_ok = 0;
-    uint32_t d_off = 0, d_len = 0, tp_off = 0, tp_len = 0, da_off = 0, da_len = 0;
+    EvAcc a;
+    a.clear();
     for (uint32_t e = 0; e < ne && !r.err; e++) {
         rd_array_exact(r, 4);
         (void)rd_uint(r);
@@ -135,39 +168,102 @@ __device__ __forceinline__ void parse_stamped_event(Rd& r, EvLog& ev) {
         const uint8_t* k = r.p + koff;
         if (klen == 2 && k[0] == 't') {
             uint32_t idx = (uint32_t)k[1] - (uint32_t)'1';
-            if (idx < 4) {
-                have |= 1u << idx;
-                if (vlen == 32) len_ok |= 1u << idx; else len_ok &= ~(1u << idx);
-                if (idx == 0) t_off0 = voff; else if (idx == 1) t_off1 = voff; else if (idx == 2) t_off2 = voff; else t_off3 = voff;
-            }
-        } else if (klen == 1 && k[0] == 'd') { have |= 16; d_off = voff; d_len = vlen; }
-        else if (klen == 6 && bytes_eq(k, "topics", 6)) { have |= 32; tp_off = voff; tp_len = vlen; }
-        else if (klen == 4 && bytes_eq(k, "data", 4)) { have |= 64; da_off = voff; da_len = vlen; }
+            if (idx < 4) a.topic(idx, voff, vlen);
+        } else if (klen == 1 && k[0] == 'd') { a.have |= 16; a.d_off = voff; a.d_len = vlen; }
+        else if (klen == 6 && bytes_eq(k, "topics", 6)) { a.have |= 32; a.tp_off = voff; a.tp_len = vlen; }
+        else if (klen == 4 && bytes_eq(k, "data", 4)) { a.have |= 64; a.da_off = voff; a.da_len = vlen; }
     }
-    ev.some = 0; ev.case_a = 0; ev.ntopics = 0; ev.data_off = 0; ev.data_len = 0;
-    ev.toff[0] = ev.toff[1] = ev.toff[2] = ev.toff[3] = 0;
-    if (r.err) return;
-    if (have & 32) {
-        ev.case_a = 1;
-        if (tp_len % 32 == 0) {
-            ev.some = 1; ev.ntopics = tp_len / 32; ev.toff[0] = tp_off;
-            if (have & 64) { ev.data_off = da_off; ev.data_len = da_len; }
-        }
-        return;
+    ev_finish(a, ev);
+    if (r.err) { ev.some = 0; ev.ntopics = 0; }
+}
+
+// Fast path: decodes a StampedEvent whose entries all have the canonical FEVM shape
+//   84 <flags<24> <6x key> <codec: imm | 18 xx> <value: 40+n | 58 nn | 59 nnnn> value…
+// with key ∈ {t1..t4, d, topics, data}, matching each entry against a 16-byte register window
+// (three aligned 8-byte loads) instead of walking it byte by byte. Any deviation returns
+// FAST_FAIL and the caller re-decodes the event with the generic strict parser, so results are
+// identical by construction: the fast path only ever accepts encodings the strict parser
+// accepts with the same meaning (minimal heads, ASCII keys, in-bounds values).
+#define FAST_FAIL 0xffffffffu
+__device__ __forceinline__ uint32_t win_byte(uint64_t w0, uint64_t w1, uint32_t k) {  // byte k (0..15) of the window
+    uint64_t w = k < 8 ? w0 : w1;
+    return (uint32_t)(w >> (8 * (k & 7))) & 0xffu;
+}
+__device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_t pos, uint32_t n, EvLog& ev) {
+    if (n - pos < 3) return FAST_FAIL;
+    uint64_t w0, w1;
+    win_load(p + pos, w0, w1);
+    if ((w0 & 0xff) != 0x82) return FAST_FAIL;
+    // emitter: any minimal uint head
+    uint32_t eb = (uint32_t)(w0 >> 8) & 0xff;
+    if (eb >= 0x1c) return FAST_FAIL;                       // not major 0 / reserved ai
+    uint32_t enb = eb < 24 ? 0 : (1u << (eb - 24));          // 0,1,2,4,8 argument bytes
+    uint64_t raw = (w0 >> 16) | (w1 << 48);                  // the 8 bytes after the emitter head byte
+    uint64_t be = ((uint64_t)__byte_perm((uint32_t)raw, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(raw >> 32), 0, 0x0123);
+    uint64_t earg = enb ? (be >> (64 - 8 * enb)) : eb;
+    uint64_t emin = eb == 24 ? 24ull : (eb == 25 ? 0x100ull : (eb == 26 ? 0x10000ull : (eb == 27 ? 0x100000000ull : 0ull)));
+    if (earg < emin) return FAST_FAIL;                       // non-minimal → let the strict parser report it
+    uint32_t hb = win_byte(w0, w1, 2 + enb);                 // entries array head (enb ≤ 8 → byte ≤ 10)
+    if ((hb & 0xe0) != 0x80 || (hb & 31) >= 24) return FAST_FAIL;
+    uint32_t ne = hb & 31;
+    uint32_t cur = pos + 3 + enb;
+    if (cur > n) return FAST_FAIL;
+    EvAcc a;
+    a.clear();
+    for (uint32_t e = 0; e < ne; e++) {
+        if (n - cur < 5) return FAST_FAIL;
+        win_load(p + cur, w0, w1);
+        uint32_t b0 = (uint32_t)w0 & 0xff, fl = (uint32_t)(w0 >> 8) & 0xff, th = (uint32_t)(w0 >> 16) & 0xff;
+        if (b0 != 0x84 || fl >= 24) return FAST_FAIL;
+        uint32_t klen = th - 0x60;                           // text head 0x61/0x62/0x64/0x66
+        uint32_t kind;                                       // 0..3 tK, 4 d, 5 topics, 6 data
+        uint32_t k4 = (uint32_t)(w0 >> 24);                  // key bytes 0..3
+        if (klen == 2) {
+            uint32_t idx = ((k4 >> 8) & 0xff) - (uint32_t)'1';
+            if ((k4 & 0xff) != 't' || idx >= 4) return FAST_FAIL;
+            kind = idx;
+        } else if (klen == 1) {
+            if ((k4 & 0xff) != 'd') return FAST_FAIL;
+            kind = 4;
+        } else if (klen == 6) {
+            uint64_t key = (w0 >> 24) | (w1 << 40);          // key bytes 0..5 in the low 48 bits
+            if ((key & 0xffffffffffffull) != 0x736369706f74ull) return FAST_FAIL;  // "topics"
+            kind = 5;
+        } else if (klen == 4) {
+            if (k4 != 0x61746164u) return FAST_FAIL;          // "data"
+            kind = 6;
+        } else return FAST_FAIL;
+        uint32_t k = 3 + klen;                               // codec head position (≤ 9)
+        uint32_t cb = win_byte(w0, w1, k);
+        uint32_t clen;
+        if (cb < 24) clen = 1;
+        else if (cb == 24 && win_byte(w0, w1, k + 1) >= 24) clen = 2;
+        else return FAST_FAIL;
+        k += clen;                                           // value head position (≤ 11)
+        uint32_t vb = win_byte(w0, w1, k);
+        uint32_t vlen, vh;
+        if (vb >= 0x40 && vb < 0x58) { vlen = vb - 0x40; vh = 1; }
+        else if (vb == 0x58) { vlen = win_byte(w0, w1, k + 1); vh = 2; if (vlen < 24) return FAST_FAIL; }
+        else if (vb == 0x59) { vlen = (win_byte(w0, w1, k + 1) << 8) | win_byte(w0, w1, k + 2); vh = 3; if (vlen < 256) return FAST_FAIL; }
+        else return FAST_FAIL;
+        uint32_t voff = cur + k + vh;
+        if (voff > n || vlen > n - voff) return FAST_FAIL;
+        if (kind < 4) a.topic(kind, voff, vlen);
+        else if (kind == 4) { a.have |= 16; a.d_off = voff; a.d_len = vlen; }
+        else if (kind == 5) { a.have |= 32; a.tp_off = voff; a.tp_len = vlen; }
+        else { a.have |= 64; a.da_off = voff; a.da_len = vlen; }
+        cur = voff + vlen;
     }
-    uint32_t n = 0;
-    bool none = false;
-#pragma unroll
-    for (uint32_t i = 0; i < 4; i++) {
-        if (none || n != i) break;          // stopped at an earlier gap
-        if (!(have & (1u << i))) break;
-        if (!(len_ok & (1u << i))) { none = true; break; }
-        n++;
-    }
-    if (none || n == 0) return;
-    ev.some = 1; ev.ntopics = n;
-    ev.toff[0] = t_off0; ev.toff[1] = t_off1; ev.toff[2] = t_off2; ev.toff[3] = t_off3;
-    if (have & 16) { ev.data_off = d_off; ev.data_len = d_len; }
+    ev.emitter = earg;
+    ev_finish(a, ev);
+    return cur;
+}
+// One StampedEvent at r.pos: fast path first, exact generic decoder on any deviation.
+__device__ __forceinline__ void decode_stamped_event(Rd& r, EvLog& ev) {
+    if (r.err) { ev.some = 0; ev.ntopics = 0; ev.emitter = 0; return; }
+    uint32_t np = fast_stamped_event(r.p, r.pos, r.n, ev);
+    if (np != FAST_FAIL) { r.pos = np; return; }
+    parse_stamped_event(r, ev);
 }
 // actor filter (events/generator.rs:220-224) then matches_log (:38-40)
 __device__ __forceinline__ bool event_matches(const uint8_t* p, const EvLog& ev, const Matcher& m) {
