@@ -33,8 +33,11 @@ if ROOT not in sys.path:
 RECEIPTS_PER_GPU = int(os.environ.get("IPCFP_BENCH_RECEIPTS", 1_000_000))
 
 
+_T0 = time.time()
+
+
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print(f"[{time.time() - _T0:8.2f}s]", *a, file=sys.stderr, flush=True)
 
 
 def build_tipset(world, rank):
@@ -195,8 +198,10 @@ def run_engine(args, world, rank, local):
         pa = api.PinnedArray(a.nbytes)
         pa.array[:] = a.view(np.uint8).reshape(-1)
         return pa
+    log("allocating pinned host buffers")
     p_cids, p_offs, p_lens, p_blob = pinned(ts.cids), pinned(ts.offsets), pinned(ts.lengths), pinned(ts.blob)
     p_roots, p_has = pinned(ts.events_roots), pinned(ts.has_events_root)
+    log("pinned buffers ready")
     d, keep = A.make_tipset_desc(ts)
     d.events_roots = p_roots.array.ctypes.data
     d.has_events_root = p_has.array.ctypes.data
@@ -277,6 +282,7 @@ def run_engine(args, world, rank, local):
             torch.cuda.synchronize()
 
     # ---- resident timing
+    log("store + tipset resident; warm-up")
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -304,19 +310,27 @@ def run_engine(args, world, rank, local):
     dev_ms_max, wall_ms_max = [float(x) for x in t_local.cpu()]
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
+    log(f"resident timing done: {dev_ms_max / args.steps:.3f} ms/step")
     # ---- end-to-end timing (host buffers → results on the host), every step re-ingests the block set
     L.ipcfp_tipset_free(tip)
     L.ipcfp_store_destroy(store)
     e2e_steps = max(1, min(args.steps, 5))
 
+    e2e_parts = []
+
     def step_e2e():
+        t0 = time.time()
         h = store_create(A.STORE_VERIFY_CIDS)
+        t1 = time.time()
         out = C.POINTER(A.EventResultC)()
         rc = L.ipcfp_generate_event_proof_shard(h, C.byref(d), C.byref(spec), lo, hi, world, rank, 0, C.byref(out))
         assert rc == 0, L.ipcfp_last_error()
         collective(out)
+        t2 = time.time()
         L.ipcfp_event_result_free(out)
         L.ipcfp_store_destroy(h)
+        t3 = time.time()
+        e2e_parts.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
 
     step_e2e()
     barrier()
@@ -330,6 +344,7 @@ def run_engine(args, world, rank, local):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e.cpu()[0])
 
+    log(f"e2e timing done: {e2e_ms:.2f} ms/step; (store_create, generate, destroy) ms per step: {e2e_parts}")
     # ---- CPU baseline (rank 0, N = 1 only): the oracle, single-threaded like the reference
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -349,6 +364,7 @@ def run_engine(args, world, rank, local):
                                   "(the reference is single-threaded; its Rust crate cannot be built in this image)",
                         "seconds": dt, "agrees_with_gpu": bool(same)}
 
+    log("cpu baseline done")
     if rank == 0:
         n_total = N_local * world
         value = n_total * args.steps / (dev_ms_max / 1e3)

@@ -134,33 +134,42 @@ __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
     uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool matched = false;
     uint32_t bytes = 0, nodes = 0;
-    if (i < a.hi && a.has_root[i]) {
-        int32_t blk = store_lookup(a.store, a.events_roots + 38 * i);
+    // phase 1: Blockstore::get of the events root (hash probe); every lane takes part so the warp
+    // can be re-converged before the long decode
+    const bool valid = i < a.hi && a.has_root[i];
+    int32_t blk = -1;
+    if (valid) {
+        blk = store_lookup(a.store, a.events_roots + 38 * i);
         if (blk < 0) report_error(a.err, ST_PASS1, i, DC_MISSING, 0);
-        else {
-            uint32_t len;
-            const uint8_t* p = store_block(a.store, (uint32_t)blk, len);
-            for (uint32_t o = 0; o < len; o += 128) prefetch_l2(p + o);  // whole node in flight before the dependent walk
-            bytes = len + 38; nodes = 1;
-            Rd r(p, len);
-            uint32_t bw, height;
-            uint64_t cnt;
-            amt_root_begin(r, 3, bw, height, cnt);
-            AmtNodeHdr h;
-            amt_node_begin(r, bw, h);
-            uint32_t nv = rd_array(r);
-            WalkOut wo{0, 0, false};
-            node_events<WALK_ANY>(r, p, h, nv, 0, a.m, wo, nullptr);
-            amt_node_finish(r, h, nv, height);
-            if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
-            else if (h.nl) {
-                uint32_t detail = 0;
-                WalkOut w2{0, 0, false};
-                uint32_t rc = walk_events<WALK_ANY>(a.store, (uint32_t)blk, a.m, nullptr, w2, nullptr, &detail);
-                if (rc) report_error(a.err, ST_PASS1, i, rc, detail);
-                else matched = w2.any;
-            } else matched = wo.any;
-        }
+    }
+    uint32_t len = 0;
+    const uint8_t* p = nullptr;
+    if (blk >= 0) {
+        p = store_block(a.store, (uint32_t)blk, len);
+        for (uint32_t o = 0; o < len; o += 128) prefetch_l2(p + o);  // whole node in flight before the dependent walk
+    }
+    __syncwarp();
+    // phase 2: decode the root node, test every event
+    if (blk >= 0) {
+        bytes = len + 38; nodes = 1;
+        Rd r(p, len);
+        uint32_t bw, height;
+        uint64_t cnt;
+        amt_root_begin(r, 3, bw, height, cnt);
+        AmtNodeHdr h;
+        amt_node_begin(r, bw, h);
+        uint32_t nv = rd_array(r);
+        WalkOut wo{0, 0, false};
+        node_events<WALK_ANY>(r, p, h, nv, 0, a.m, wo, nullptr);
+        amt_node_finish(r, h, nv, height);
+        if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
+        else if (h.nl) {
+            uint32_t detail = 0;
+            WalkOut w2{0, 0, false};
+            uint32_t rc = walk_events<WALK_ANY>(a.store, (uint32_t)blk, a.m, nullptr, w2, nullptr, &detail);
+            if (rc) report_error(a.err, ST_PASS1, i, rc, detail);
+            else matched = w2.any;
+        } else matched = wo.any;
     }
     unsigned b = __ballot_sync(0xffffffffu, matched);
     if ((threadIdx.x & 31) == 0) a.match_bits[((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5] = b;

@@ -151,7 +151,7 @@ __device__ __forceinline__ void ev_finish(const EvAcc& a, EvLog& ev) {
     if (a.have & 16) { ev.data_off = a.d_off; ev.data_len = a.d_len; }
 }
 // Generic strict decoder of one StampedEvent = [emitter, [[flags,key,codec,value]…]].
-static __device__ __noinline__ void parse_stamped_event(Rd& r, EvLog& ev) {
+__device__ __forceinline__ void parse_stamped_event(Rd& r, EvLog& ev) {
     rd_array_exact(r, 2);
     ev.emitter = rd_uint(r);
     uint32_t ne = rd_array(r);
@@ -258,12 +258,28 @@ __device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_
     ev_finish(a, ev);
     return cur;
 }
-// One StampedEvent at r.pos: fast path first, exact generic decoder on any deviation.
+// One StampedEvent at r.pos: fast path first, exact generic decoder on any deviation. The slow path
+// works on private copies so that the caller's reader and EvLog stay in registers.
+static __device__ __noinline__ uint32_t slow_stamped_event(const uint8_t* p, uint32_t pos, uint32_t n, EvLog* out, uint32_t* err) {
+    Rd r2(p, n);
+    r2.pos = pos;
+    EvLog e2;
+    parse_stamped_event(r2, e2);
+    *out = e2;
+    *err = r2.err;
+    return r2.pos;
+}
 __device__ __forceinline__ void decode_stamped_event(Rd& r, EvLog& ev) {
     if (r.err) { ev.some = 0; ev.ntopics = 0; ev.emitter = 0; return; }
     uint32_t np = fast_stamped_event(r.p, r.pos, r.n, ev);
-    if (np != FAST_FAIL) { r.pos = np; return; }
-    parse_stamped_event(r, ev);
+    if (np == FAST_FAIL) {
+        EvLog e2;
+        uint32_t err = 0;
+        np = slow_stamped_event(r.p, r.pos, r.n, &e2, &err);
+        ev = e2;
+        if (err) { rd_fail(r, err); return; }
+    }
+    r.pos = np;
 }
 // actor filter (events/generator.rs:220-224) then matches_log (:38-40)
 __device__ __forceinline__ bool event_matches(const uint8_t* p, const EvLog& ev, const Matcher& m) {

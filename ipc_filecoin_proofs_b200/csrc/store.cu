@@ -156,7 +156,13 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     s->device = device;
     s->n = n;
     s->blob_size = blob_size;
-    s->pool = std::make_shared<PinnedPool>();
+    {   // one process-wide pinned pool: result buffers are recycled across stores and calls
+        static std::mutex pool_mu;
+        static std::shared_ptr<PinnedPool> g_pool;
+        std::lock_guard<std::mutex> g(pool_mu);
+        if (!g_pool) g_pool = std::make_shared<PinnedPool>();
+        s->pool = g_pool;
+    }
     IPCFP_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) IPCFP_CUDA(cudaEventCreate(&e));
     cudaStream_t st = s->stream;
