@@ -139,8 +139,9 @@ typedef struct ipcfp_storage_spec {
 typedef struct ipcfp_witness {
     uint64_t n_blocks;
     const uint8_t* cids;      /* n_blocks*38, sorted by (version, codec, multihash) */
-    const uint64_t* offsets;  /* n_blocks+1 offsets into blob                      */
-    const uint8_t* blob;
+    const uint64_t* offsets;  /* n_blocks: block i = blob[offsets[i] .. offsets[i]+lengths[i])   */
+    const uint32_t* lengths;  /* n_blocks                                                        */
+    const uint8_t* blob;      /* block bytes; blocks may sit in any order / with padding in here */
     uint64_t blob_size;
 } ipcfp_witness;
 

@@ -61,6 +61,7 @@ class Witness(C.Structure):
         ("n_blocks", C.c_uint64),
         ("cids", C.c_void_p),
         ("offsets", C.c_void_p),
+        ("lengths", C.c_void_p),
         ("blob", C.c_void_p),
         ("blob_size", C.c_uint64),
     ]
@@ -156,15 +157,24 @@ def _arr(ptr, n, dtype):
 @dataclass
 class WitnessPy:
     cids: np.ndarray      # (m, 38) uint8, sorted in Cid Ord
-    offsets: np.ndarray   # (m+1,) uint64
-    blob: np.ndarray      # uint8
+    offsets: np.ndarray   # (m,) uint64
+    lengths: np.ndarray   # (m,) uint32
+    blob: np.ndarray      # uint8 (blocks in any order)
 
     @property
     def n_blocks(self):
         return len(self.cids)
 
+    @property
+    def total_bytes(self):
+        return int(self.lengths.sum())
+
     def block(self, i):
-        return bytes(self.blob[int(self.offsets[i]):int(self.offsets[i + 1])])
+        o = int(self.offsets[i])
+        return bytes(self.blob[o:o + int(self.lengths[i])])
+
+    def blocks(self):
+        return [self.block(i) for i in range(self.n_blocks)]
 
     def as_dict(self):
         return {bytes(self.cids[i]): self.block(i) for i in range(self.n_blocks)}
@@ -173,14 +183,15 @@ class WitnessPy:
         """Returns (Witness struct, keepalive) for passing back into C."""
         cids = np.ascontiguousarray(self.cids)
         offs = np.ascontiguousarray(self.offsets)
+        lens = np.ascontiguousarray(self.lengths)
         blob = np.ascontiguousarray(self.blob)
-        w = Witness(len(cids), cids.ctypes.data, offs.ctypes.data, blob.ctypes.data, len(blob))
-        return w, (cids, offs, blob)
+        w = Witness(len(cids), cids.ctypes.data, offs.ctypes.data, lens.ctypes.data, blob.ctypes.data, len(blob))
+        return w, (cids, offs, lens, blob)
 
 
 def witness_from_c(w):
     m = int(w.n_blocks)
-    return WitnessPy(_arr(w.cids, m * CID_LEN, np.uint8).reshape(m, CID_LEN), _arr(w.offsets, m + 1 if w.offsets else 0, np.uint64),
+    return WitnessPy(_arr(w.cids, m * CID_LEN, np.uint8).reshape(m, CID_LEN), _arr(w.offsets, m, np.uint64), _arr(w.lengths, m, np.uint32),
                      _arr(w.blob, int(w.blob_size), np.uint8))
 
 

@@ -110,6 +110,7 @@ struct BundleBox {
     std::vector<ipcfp_event_result*> ev;
     std::vector<uint8_t> cids, blob;
     std::vector<uint64_t> offsets;
+    std::vector<uint32_t> lengths;
 };
 
 }  // namespace ipcfp
@@ -289,17 +290,17 @@ ipcfp_status ipcfp_generate_proof_bundle(ipcfp_store* s, const ipcfp_tipset_desc
         };
         std::map<std::array<uint8_t, 39>, std::pair<const ipcfp_witness*, uint64_t>> uni;
         for (auto* w : lists) for (uint64_t i = 0; i < w->n_blocks; i++) uni.emplace(key_of(w->cids + 38 * i), std::make_pair(w, i));
-        box->offsets.push_back(0);
         for (auto& kv : uni) {
             const ipcfp_witness* w = kv.second.first;
             uint64_t i = kv.second.second;
             box->cids.insert(box->cids.end(), w->cids + 38 * i, w->cids + 38 * i + 38);
-            box->blob.insert(box->blob.end(), w->blob + w->offsets[i], w->blob + w->offsets[i + 1]);
             box->offsets.push_back(box->blob.size());
+            box->lengths.push_back(w->lengths[i]);
+            box->blob.insert(box->blob.end(), w->blob + w->offsets[i], w->blob + w->offsets[i] + w->lengths[i]);
         }
         box->r.n_event_results = box->ev.size();
         box->r.events = box->ev.data();
-        box->r.witness.n_blocks = uni.size(); box->r.witness.cids = box->cids.data(); box->r.witness.offsets = box->offsets.data();
+        box->r.witness.n_blocks = uni.size(); box->r.witness.cids = box->cids.data(); box->r.witness.offsets = box->offsets.data(); box->r.witness.lengths = box->lengths.data();
         box->r.witness.blob = box->blob.data(); box->r.witness.blob_size = box->blob.size();
         cl.armed = false;
         *out = &box.release()->r;

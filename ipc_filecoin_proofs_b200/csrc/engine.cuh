@@ -38,7 +38,7 @@ struct PinnedArray {
 
 struct Store {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
     uint64_t n = 0, blob_size = 0;
     DevBuf<uint8_t> arena;
     DevBuf<uint64_t> offsets;
@@ -102,15 +102,30 @@ void storage_result_free(ipcfp_storage_result* r);
 
 // witness.cu — materialise a witness bitmap into a sorted ipcfp_witness (host, pinned)
 struct WitnessOut {
-    PinnedArray cids, offsets, blob;
+    PinnedArray cids, offsets, lengths, blob;
     PinnedArray sorted_idx;       // host copy of the block indices in Cid order (u32[n])
     uint64_t n = 0, blob_size = 0;
     void fill(ipcfp_witness& w) const {
-        w.n_blocks = n; w.cids = cids.as<uint8_t>(); w.offsets = offsets.as<uint64_t>(); w.blob = blob.as<uint8_t>(); w.blob_size = blob_size;
+        w.n_blocks = n; w.cids = cids.as<uint8_t>(); w.offsets = offsets.as<uint64_t>(); w.lengths = lengths.as<uint32_t>();
+        w.blob = blob.as<uint8_t>(); w.blob_size = blob_size;
     }
 };
-void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out, bool to_host);
-// sort (class rank, digest) pairs: idx list (device, m entries) → sorted in place
-void sort_block_indices_by_cid(Store* s, uint32_t* idx_dev, uint64_t m);
+// Two-phase witness materialisation (see witness.cu): snapshot → start_copy → finish_enqueue → finish.
+struct WitnessBuilder {
+    Store* s;
+    cudaStream_t st, st2;
+    uint64_t nwords = 0, mA = 0, mB = 0, bytesA = 0, bytesB = 0, host_cap = 0;
+    bool have_snapshot = false;
+    AsyncBuf<uint32_t> idx, plen, bitsA, bitsB;
+    AsyncBuf<uint64_t> offs, word_prefix, scratch;
+    AsyncBuf<uint8_t> dblobA;
+    PinnedArray host_blob;
+    explicit WitnessBuilder(Store* store);
+    void snapshot(const uint32_t* wbits);        // enqueue; count → dev_words[8]
+    void start_copy(uint64_t mA);                // gather + D2H of the snapshot on the side stream
+    void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10]
+    void finish(uint64_t mB, WitnessOut& out);   // late blocks, Cid-order index arrays, join
+};
+void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out);
 
 }  // namespace ipcfp

@@ -673,12 +673,19 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
             bound = nb_bound;
         }
     }
-    // ncount now holds the number of raw execution entries
+    // ncount now holds the number of raw execution entries.
+    // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
+    // them to the host while pass 1 / pass 2 run (witness.cu).
+    WitnessBuilder wbuild(s);
+    wbuild.snapshot(wbits.p);
     IPCFP_CUDA(cudaMemcpyAsync(hw + 2, ncount, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 8, dw + 8, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
     uint64_t nraw = std::min<uint64_t>(hw[2], last_bound * 8);
+    wbuild.start_copy(hw[8]);
     AsyncBuf<uint8_t> exec_raw(nraw * 38 + 64, st);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
@@ -729,11 +736,16 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     if (M) {
         k_pass2<WALK_COUNT><<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
         exclusive_scan_u32(cnt.p, pbase.p, M, (uint64_t*)(dw + 7), scratch.p, st);
-        exclusive_scan_u32(nby.p, bbase.p, M, (uint64_t*)(dw + 10), scratch.p, st);
-        IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 12 * 8, cudaMemcpyDeviceToHost, st));
-        IPCFP_CUDA(cudaStreamSynchronize(st));
-        if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
-        n_proofs = hw[7]; n_bytes = hw[10];
+        exclusive_scan_u32(nby.p, bbase.p, M, (uint64_t*)(dw + 12), scratch.p, st);
+    }
+    // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
+    wbuild.finish_enqueue(wbits.p);
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 14 * 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    const uint64_t mB = hw[10];
+    if (M) {
+        n_proofs = hw[7]; n_bytes = hw[12];
         d_proofs.alloc(n_proofs + 1, st);
         d_blob.alloc(n_bytes + 16, st);
         p2.proofs = d_proofs.p; p2.blob = d_blob.p;
@@ -752,11 +764,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     if (n_bytes) IPCFP_CUDA(cudaMemcpyAsync(box->blob.p, d_blob.p, n_bytes, cudaMemcpyDeviceToHost, st));
 
     // ---- witness
-    if (missing_base && !skip_tx) {
-        IPCFP_CUDA(cudaStreamSynchronize(st));
-        throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
-    }
-    materialize_witness(s, wbits.p, box->wit, true);
+    wbuild.finish(mB, box->wit);
     IPCFP_CUDA(cudaEventRecord(s->ev[5], st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     {

@@ -394,7 +394,7 @@ ipcfp_slot_result* read_storage_slots(Store* s, const uint8_t* root, const uint8
         IPCFP_CUDA(cudaMemcpyAsync(box->raw_len.p, d_len.p, k * 4, cudaMemcpyDeviceToHost, st));
         IPCFP_CUDA(cudaMemcpyAsync(box->values.p, d_vals.p, k * 32, cudaMemcpyDeviceToHost, st));
     }
-    materialize_witness(s, wbits.p, box->wit, true);
+    materialize_witness(s, wbits.p, box->wit);
     IPCFP_CUDA(cudaEventRecord(s->ev[1], st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     box->r.n = k; box->r.found = box->found.as<uint8_t>(); box->r.raw_len = box->raw_len.as<uint32_t>(); box->r.values = box->values.as<uint8_t>();
@@ -446,7 +446,7 @@ ipcfp_storage_result* generate_storage_proofs(Store* s, const ipcfp_tipset_desc*
         IPCFP_CUDA(cudaMemcpyAsync(rec.p, d_rec.p, n * REC_CAP * 4, cudaMemcpyDeviceToHost, st));
         IPCFP_CUDA(cudaMemcpyAsync(recn.p, d_recn.p, n * 4, cudaMemcpyDeviceToHost, st));
     }
-    materialize_witness(s, wbits.p, box->wit, true);
+    materialize_witness(s, wbits.p, box->wit);
     // per-spec Vec<ProofBlock>: map recorded block indices to positions in the sorted union
     PinnedArray& sorted_idx = box->wit.sorted_idx;
     IPCFP_CUDA(cudaEventRecord(s->ev[1], st));

@@ -38,6 +38,7 @@ Store::~Store() {
     cudaSetDevice(device);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
 }
 
 void check_device(int device) {

@@ -1,7 +1,13 @@
 // witness.cu — K4/K6: turn the witness bitmap (one bit per store block, set by every recorded
-// Blockstore::get) into the reference's `Vec<ProofBlock>` in `Cid` Ord order:
-//   bitmap → ordered index list → radix sort by (class rank, digest) → gather CIDs + bytes.
+// Blockstore::get) into the reference's `Vec<ProofBlock>` in `Cid` Ord order.
 // Replaces BTreeSet<Cid> + WitnessCollector::materialize (common/witness.rs:9-57).
+//
+// Two-phase so the bulk of the device→host copy hides behind the scan:
+//   snapshot (after the message-AMT walk): bitmap → ordered index list A → block bytes gathered
+//            into a 16-byte-padded staging blob → D2H on a second stream while pass 1/2 run;
+//   finish   (after pass 2): B = bits set since the snapshot → gathered + copied behind A;
+//            radix sort of A∪B by (class rank, digest) → cids / offsets / lengths arrays.
+// The output keeps block bytes in arrival order and the (cid, offset, length) index in `Cid` order.
 #include "engine.cuh"
 #include "prims.cuh"
 
@@ -23,24 +29,28 @@ __device__ __forceinline__ int digest_cmp(const Digest& a, const Digest& b) {
     return 0;
 }
 
-__global__ void k_digest_keys(const uint32_t* __restrict__ idx, uint64_t m, const Digest* __restrict__ digests, uint32_t* keys) {
+// ord[i] = i, keys[i] = first four digest bytes (big-endian) of block idx[i]
+__global__ void k_digest_keys(const uint32_t* __restrict__ idx, uint64_t m, const Digest* __restrict__ digests, uint32_t* keys, uint32_t* ord) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint64_t w0 = digests[idx[i]].w[0];
-    keys[i] = __byte_perm((uint32_t)w0, 0, 0x0123);  // first four digest bytes, big-endian
+    keys[i] = __byte_perm((uint32_t)w0, 0, 0x0123);
+    ord[i] = (uint32_t)i;
 }
-__global__ void k_class_keys(const uint32_t* __restrict__ idx, uint64_t m, const uint8_t* __restrict__ cls, ClassRanks cr, uint32_t* keys) {
+__global__ void k_class_keys(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ ord, uint64_t m, const uint8_t* __restrict__ cls,
+                             ClassRanks cr, uint32_t* keys) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    keys[i] = cr.r[cls[idx[i]]];
+    keys[i] = cr.r[cls[idx[ord[i]]]];
 }
 // After the radix passes entries are ordered by (class rank, first 4 digest bytes). Runs with equal
 // 4-byte prefixes (≈ m²/2³³ pairs for random digests) are finished by one thread per run.
-__global__ void k_tie_fix(uint32_t* idx, uint64_t m, const Digest* __restrict__ digests, const uint8_t* __restrict__ cls, ClassRanks cr) {
+__global__ void k_tie_fix(const uint32_t* __restrict__ idx, uint32_t* ord, uint64_t m, const Digest* __restrict__ digests,
+                          const uint8_t* __restrict__ cls, ClassRanks cr) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     auto key_eq = [&](uint64_t a, uint64_t b) {
-        uint32_t x = idx[a], y = idx[b];
+        uint32_t x = idx[ord[a]], y = idx[ord[b]];
         return cr.r[cls[x]] == cr.r[cls[y]] && (uint32_t)digests[x].w[0] == (uint32_t)digests[y].w[0];
     };
     if (i > 0 && key_eq(i - 1, i)) return;          // not a run start
@@ -48,16 +58,17 @@ __global__ void k_tie_fix(uint32_t* idx, uint64_t m, const Digest* __restrict__ 
     uint64_t j = i + 1;
     while (j + 1 < m && key_eq(i, j + 1)) j++;      // run = [i, j]
     for (uint64_t a = i + 1; a <= j; a++) {         // insertion sort by full digest, stable
-        uint32_t v = idx[a];
-        Digest dv = digests[v];
+        uint32_t v = ord[a];
+        Digest dv = digests[idx[v]];
         uint64_t b = a;
-        while (b > i && digest_cmp(digests[idx[b - 1]], dv) > 0) { idx[b] = idx[b - 1]; b--; }
-        idx[b] = v;
+        while (b > i && digest_cmp(digests[idx[ord[b - 1]]], dv) > 0) { ord[b] = ord[b - 1]; b--; }
+        ord[b] = v;
     }
 }
 
-void sort_block_indices_by_cid(Store* s, uint32_t* idx_dev, uint64_t m) {
-    if (m <= 1) return;
+// ord (device, m entries) receives the permutation that sorts idx[] by CID
+static void sort_by_cid(Store* s, const uint32_t* idx_dev, uint32_t* ord, uint64_t m) {
+    if (m == 0) return;
     cudaStream_t st = s->stream;
     AsyncBuf<uint32_t> keys(m, st), keys_alt(m, st), vals_alt(m, st);
     unsigned nb = radix_blocks(m);
@@ -65,25 +76,52 @@ void sort_block_indices_by_cid(Store* s, uint32_t* idx_dev, uint64_t m) {
     AsyncBuf<uint64_t> scan_tmp((size_t)256 * nb + 256, st), scratch(scan_scratch_elems((uint64_t)256 * nb) + 8, st);
     ClassRanks cr{};
     for (size_t c = 0; c < s->class_rank.size(); c++) cr.r[c] = (uint8_t)s->class_rank[c];
-    k_digest_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->digests.p, keys.p); IPCFP_LAUNCH_CHECK();
-    radix_sort_pairs(keys.p, idx_dev, keys_alt.p, vals_alt.p, m, 32, hist.p, scan_tmp.p, scratch.p, st);
+    k_digest_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->digests.p, keys.p, ord); IPCFP_LAUNCH_CHECK();
+    radix_sort_pairs(keys.p, ord, keys_alt.p, vals_alt.p, m, 32, hist.p, scan_tmp.p, scratch.p, st);
     if (s->class_prefix.size() > 1) {
-        k_class_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->cls.p, cr, keys.p); IPCFP_LAUNCH_CHECK();
-        radix_sort_pairs(keys.p, idx_dev, keys_alt.p, vals_alt.p, m, 8, hist.p, scan_tmp.p, scratch.p, st);
+        k_class_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, ord, m, s->cls.p, cr, keys.p); IPCFP_LAUNCH_CHECK();
+        radix_sort_pairs(keys.p, ord, keys_alt.p, vals_alt.p, m, 8, hist.p, scan_tmp.p, scratch.p, st);
     }
-    k_tie_fix<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->digests.p, s->cls.p, cr); IPCFP_LAUNCH_CHECK();
+    k_tie_fix<<<div_up(m, 256), 256, 0, st>>>(idx_dev, ord, m, s->digests.p, s->cls.p, cr); IPCFP_LAUNCH_CHECK();
 }
 
-__global__ void k_gather_lengths(const uint32_t* __restrict__ idx, uint64_t m, const uint32_t* __restrict__ lengths, uint32_t* out) {
+__global__ void k_padded_lengths(const uint32_t* __restrict__ idx, uint64_t m, const uint32_t* __restrict__ lengths, uint32_t* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) out[i] = lengths[idx[i]];
+    if (i < m) out[i] = (lengths[idx[i]] + 15u) & ~15u;
 }
-__global__ void k_witness_cids(const uint32_t* __restrict__ idx, uint64_t m, StoreView v, uint8_t* out, const uint64_t* total, uint64_t* offsets) {
+__global__ void k_andnot(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* out, uint64_t nwords) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) offsets[m] = *total;
+    if (i < nwords) out[i] = a[i] & ~b[i];
+}
+// one warp per witness block: arena → 16-byte-padded staging blob. 16-byte vector copies when the
+// source block is 16-byte aligned (destination slots always are), byte copies otherwise.
+__global__ void __launch_bounds__(256) k_witness_copy(const uint32_t* __restrict__ idx, uint64_t m, StoreView v, const uint64_t* __restrict__ offsets,
+                                                      uint8_t* out) {
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (w >= m) return;
+    uint32_t len;
+    const uint8_t* src = store_block(v, idx[w], len);
+    uint8_t* dst = out + offsets[w];
+    if (((uintptr_t)src & 15) == 0) {
+        uint32_t nv = (len + 15) >> 4;  // the arena is padded, reading the tail of the last 16 bytes is safe
+        const uint4* s4 = (const uint4*)src;
+        uint4* d4 = (uint4*)dst;
+        for (uint32_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+        for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+    }
+}
+__global__ void k_witness_emit(const uint32_t* __restrict__ ord, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ offs, uint64_t m,
+                               uint64_t mA, uint64_t baseB, StoreView v, uint8_t* cids, uint64_t* out_offs, uint32_t* out_lens, uint32_t* out_idx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    uint32_t b = idx[i];
-    uint8_t* o = out + 38 * i;
+    uint32_t p = ord[i];
+    uint32_t b = idx[p];
+    out_offs[i] = offs[p] + (p >= mA ? baseB : 0);
+    out_lens[i] = v.lengths[b];
+    out_idx[i] = b;
+    uint8_t* o = cids + 38 * i;
     uint32_t c = v.cls[b];
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = v.class_prefix[c][k];
@@ -93,55 +131,117 @@ __global__ void k_witness_cids(const uint32_t* __restrict__ idx, uint64_t m, Sto
 #pragma unroll
         for (int k = 0; k < 8; k++) o[6 + 8 * w + k] = (uint8_t)(d.w[w] >> (8 * k));
 }
-// one warp per witness block: coalesced byte copy arena → packed witness blob
-__global__ void __launch_bounds__(256) k_witness_copy(const uint32_t* __restrict__ idx, uint64_t m, StoreView v, const uint64_t* __restrict__ offsets,
-                                                      uint8_t* out) {
-    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (w >= m) return;
-    uint32_t len;
-    const uint8_t* src = store_block(v, idx[w], len);
-    uint8_t* dst = out + offsets[w];
-    // head bytes until dst is 4-byte aligned, then word stores assembled from byte loads
-    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+
+WitnessBuilder::WitnessBuilder(Store* store) : s(store) {
+    st = s->stream;
+    if (!s->stream2) IPCFP_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    st2 = s->stream2;
+    uint64_t n = s->n;
+    nwords = (n + 31) / 32;
+    idx.alloc(n + 64, st);
+    offs.alloc(n + 64, st);
+    plen.alloc(n + 64, st);
+    bitsA.alloc(nwords + 8, st);
+    word_prefix.alloc(nwords + 8, st);
+    scratch.alloc(scan_scratch_elems(std::max<uint64_t>(nwords, n)) + 8, st);
 }
 
-void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out, bool to_host) {
-    cudaStream_t st = s->stream;
-    uint64_t n = s->n;
-    uint64_t nwords = (n + 31) / 32;
-    AsyncBuf<uint32_t> idx(n + 32, st);
-    AsyncBuf<uint64_t> word_prefix(nwords + 8, st), scratch(scan_scratch_elems(nwords > n ? nwords : n) + 8, st);
-    unsigned long long* total = s->dev_words.p + 8;
-    bitmap_to_indices(wbits_dev, n, idx.p, (uint64_t*)total, word_prefix.p, scratch.p, st);
-    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 8, total, 8, cudaMemcpyDeviceToHost, st));
+// enqueue: bitmap → idx[0..mA), padded offsets; totals land in dev_words[8] (mA) and [9] (bytesA)
+void WitnessBuilder::snapshot(const uint32_t* wbits) {
+    unsigned long long* dw = s->dev_words.p;
+    IPCFP_CUDA(cudaMemcpyAsync(bitsA.p, wbits, nwords * 4, cudaMemcpyDeviceToDevice, st));
+    bitmap_to_indices(bitsA.p, s->n, idx.p, (uint64_t*)(dw + 8), word_prefix.p, scratch.p, st);
+    // padded lengths for every candidate slot (count is only known on the device: bound by n)
+    // → done after the host learns mA in start_copy; here only the count is produced.
+    have_snapshot = true;
+}
+// host knows mA: scan padded lengths, gather on the side stream, start the D2H
+void WitnessBuilder::start_copy(uint64_t mA_) {
+    mA = mA_;
+    unsigned long long* dw = s->dev_words.p;
+    if (mA) { k_padded_lengths<<<div_up(mA, 256), 256, 0, st>>>(idx.p, mA, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
+    exclusive_scan_u32(plen.p, offs.p, mA, (uint64_t*)(dw + 9), scratch.p, st);
+    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 9, dw + 9, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    uint64_t m = s->host_words.p[8];
-    out.n = m;
-    sort_block_indices_by_cid(s, idx.p, m);
-    AsyncBuf<uint32_t> lens(m + 8, st);
-    AsyncBuf<uint64_t> offs(m + 8, st);
-    unsigned long long* tbytes = s->dev_words.p + 9;
-    if (m) { k_gather_lengths<<<div_up(m, 256), 256, 0, st>>>(idx.p, m, s->lengths.p, lens.p); IPCFP_LAUNCH_CHECK(); }
-    exclusive_scan_u32(lens.p, offs.p, m, (uint64_t*)tbytes, scratch.p, st);
-    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 9, tbytes, 8, cudaMemcpyDeviceToHost, st));
-    IPCFP_CUDA(cudaStreamSynchronize(st));
-    uint64_t total_bytes = s->host_words.p[9];
-    out.blob_size = total_bytes;
-    AsyncBuf<uint8_t> dcids(m * 38 + 16, st), dblob(total_bytes + 16, st);
-    k_witness_cids<<<div_up(m ? m : 1, 256), 256, 0, st>>>(idx.p, m, s->view, dcids.p, (const uint64_t*)tbytes, offs.p); IPCFP_LAUNCH_CHECK();
-    if (m) { k_witness_copy<<<div_up(m * 32, 256), 256, 0, st>>>(idx.p, m, s->view, offs.p, dblob.p); IPCFP_LAUNCH_CHECK(); }
-    if (to_host) {
-        out.cids = PinnedArray(s->pool, m * 38);
-        out.offsets = PinnedArray(s->pool, (m + 1) * 8);
-        out.blob = PinnedArray(s->pool, total_bytes);
-        if (m) IPCFP_CUDA(cudaMemcpyAsync(out.cids.p, dcids.p, m * 38, cudaMemcpyDeviceToHost, st));
-        IPCFP_CUDA(cudaMemcpyAsync(out.offsets.p, offs.p, (m + 1) * 8, cudaMemcpyDeviceToHost, st));
-        if (total_bytes) IPCFP_CUDA(cudaMemcpyAsync(out.blob.p, dblob.p, total_bytes, cudaMemcpyDeviceToHost, st));
+    bytesA = s->host_words.p[9];
+    host_cap = bytesA + bytesA / 8 + (8u << 20);
+    host_blob = PinnedArray(s->pool, host_cap);
+    host_cap = host_blob.cap;
+    dblobA.alloc(bytesA + 64, st);
+    IPCFP_CUDA(cudaEventRecord(s->ev[6], st));
+    IPCFP_CUDA(cudaStreamWaitEvent(st2, s->ev[6], 0));
+    if (mA) {
+        k_witness_copy<<<div_up(mA * 32, 256), 256, 0, st2>>>(idx.p, mA, s->view, offs.p, dblobA.p); IPCFP_LAUNCH_CHECK();
+        IPCFP_CUDA(cudaMemcpyAsync(host_blob.p, dblobA.p, bytesA, cudaMemcpyDeviceToHost, st2));
     }
+    IPCFP_CUDA(cudaEventRecord(s->ev[7], st2));
+}
+// enqueue: B = bits & ~A → idx[mA..mA+mB); totals in dev_words[10] (mB)
+void WitnessBuilder::finish_enqueue(const uint32_t* wbits) {
+    unsigned long long* dw = s->dev_words.p;
+    bitsB.alloc(nwords + 8, st);
+    k_andnot<<<div_up(nwords ? nwords : 1, 256), 256, 0, st>>>(wbits, bitsA.p, bitsB.p, nwords); IPCFP_LAUNCH_CHECK();
+    bitmap_to_indices(bitsB.p, s->n, idx.p + mA, (uint64_t*)(dw + 10), word_prefix.p, scratch.p, st);
+}
+void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
+    mB = mB_;
+    unsigned long long* dw = s->dev_words.p;
+    uint64_t m = mA + mB;
+    bytesB = 0;
+    if (mB) {
+        k_padded_lengths<<<div_up(mB, 256), 256, 0, st>>>(idx.p + mA, mB, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK();
+        exclusive_scan_u32(plen.p, offs.p + mA, mB, (uint64_t*)(dw + 11), scratch.p, st);
+        IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 11, dw + 11, 8, cudaMemcpyDeviceToHost, st));
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+        bytesB = s->host_words.p[11];
+    }
+    if (bytesA + bytesB > host_cap) {  // rare: more late blocks than the slack — move to a bigger buffer
+        IPCFP_CUDA(cudaStreamSynchronize(st2));
+        PinnedArray bigger(s->pool, bytesA + bytesB + 64);
+        memcpy(bigger.p, host_blob.p, bytesA);
+        host_blob = std::move(bigger);
+        host_cap = host_blob.cap;
+    }
+    AsyncBuf<uint8_t> dblobB(bytesB + 64, st);
+    if (mB) {
+        k_witness_copy<<<div_up(mB * 32, 256), 256, 0, st>>>(idx.p + mA, mB, s->view, offs.p + mA, dblobB.p); IPCFP_LAUNCH_CHECK();
+        IPCFP_CUDA(cudaMemcpyAsync((uint8_t*)host_blob.p + bytesA, dblobB.p, bytesB, cudaMemcpyDeviceToHost, st));
+    }
+    // index arrays in Cid order
+    AsyncBuf<uint32_t> ord(m + 8, st), d_lens(m + 8, st), d_idx(m + 8, st);
+    AsyncBuf<uint64_t> d_offs(m + 8, st);
+    AsyncBuf<uint8_t> d_cids(m * 38 + 64, st);
+    sort_by_cid(s, idx.p, ord.p, m);
+    if (m) {
+        k_witness_emit<<<div_up(m, 256), 256, 0, st>>>(ord.p, idx.p, offs.p, m, mA, bytesA, s->view, d_cids.p, d_offs.p, d_lens.p, d_idx.p);
+        IPCFP_LAUNCH_CHECK();
+    }
+    out.n = m;
+    out.blob_size = bytesA + bytesB;
+    out.cids = PinnedArray(s->pool, m * 38 + 64);
+    out.offsets = PinnedArray(s->pool, (m + 1) * 8);
+    out.lengths = PinnedArray(s->pool, (m + 1) * 4);
     out.sorted_idx = PinnedArray(s->pool, (m + 1) * 4);
-    if (m) IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, idx.p, m * 4, cudaMemcpyDeviceToHost, st));
+    if (m) {
+        IPCFP_CUDA(cudaMemcpyAsync(out.cids.p, d_cids.p, m * 38, cudaMemcpyDeviceToHost, st));
+        IPCFP_CUDA(cudaMemcpyAsync(out.offsets.p, d_offs.p, m * 8, cudaMemcpyDeviceToHost, st));
+        IPCFP_CUDA(cudaMemcpyAsync(out.lengths.p, d_lens.p, m * 4, cudaMemcpyDeviceToHost, st));
+        IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, d_idx.p, m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    IPCFP_CUDA(cudaStreamWaitEvent(st, s->ev[7], 0));  // the big copy on the side stream
     IPCFP_CUDA(cudaStreamSynchronize(st));
+    IPCFP_CUDA(cudaStreamSynchronize(st2));
+    out.blob = std::move(host_blob);
+}
+
+// single-phase convenience (storage path): everything at once
+void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out) {
+    WitnessBuilder wb(s);
+    wb.snapshot(wbits_dev);
+    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 8, s->dev_words.p + 8, 8, cudaMemcpyDeviceToHost, s->stream));
+    IPCFP_CUDA(cudaStreamSynchronize(s->stream));
+    wb.start_copy(s->host_words.p[8]);
+    wb.finish(0, out);
 }
 
 }  // namespace ipcfp

@@ -989,15 +989,16 @@ static StorageProofRec generate_storage_proof(const Blockstore& net, const Tipse
 }
 
 // ---------------------------------------------------------------------------------- result packing
-struct WitnessBuf { std::vector<uint8_t> cids; std::vector<uint64_t> offsets; std::vector<uint8_t> blob; };
+struct WitnessBuf { std::vector<uint8_t> cids; std::vector<uint64_t> offsets; std::vector<uint32_t> lengths; std::vector<uint8_t> blob; };
 static void pack_witness(const std::vector<ProofBlock>& blocks, WitnessBuf& wb, ipcfp_witness& w) {
-    wb.offsets.push_back(0);
     for (auto& b : blocks) {
         wb.cids.insert(wb.cids.end(), b.cid.b.begin(), b.cid.b.end());
-        wb.blob.insert(wb.blob.end(), b.data.begin(), b.data.end());
         wb.offsets.push_back(wb.blob.size());
+        wb.lengths.push_back((uint32_t)b.data.size());
+        wb.blob.insert(wb.blob.end(), b.data.begin(), b.data.end());
     }
-    w.n_blocks = blocks.size(); w.cids = wb.cids.data(); w.offsets = wb.offsets.data(); w.blob = wb.blob.data(); w.blob_size = wb.blob.size();
+    w.n_blocks = blocks.size(); w.cids = wb.cids.data(); w.offsets = wb.offsets.data(); w.lengths = wb.lengths.data();
+    w.blob = wb.blob.data(); w.blob_size = wb.blob.size();
 }
 struct EventResultBox {
     ipcfp_event_result r;  // must be first
@@ -1232,7 +1233,7 @@ void oracle_bundle_free(ipcfp_bundle* r) {
 
 // ---------------------------------------------------------------------------------- verifiers
 static void load_witness_store(const ipcfp_witness* w, MemoryBlockstore& bs) {  // events/verifier.rs:79-89 (no hash check)
-    for (uint64_t i = 0; i < w->n_blocks; i++) bs.put_keyed(cid_from(w->cids + 38 * i), w->blob + w->offsets[i], (uint32_t)(w->offsets[i + 1] - w->offsets[i]));
+    for (uint64_t i = 0; i < w->n_blocks; i++) bs.put_keyed(cid_from(w->cids + 38 * i), w->blob + w->offsets[i], w->lengths[i]);
 }
 ipcfp_status oracle_verify_event_proofs(const ipcfp_witness* w, const ipcfp_tipset_desc* t, const ipcfp_event_proof* proofs,
                                         uint64_t n_proofs, const uint8_t* data_blob, const ipcfp_event_spec* filter_spec,

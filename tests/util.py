@@ -15,15 +15,15 @@ def assert_event_results_equal(got, exp, check_witness_bytes=True):
     assert got.witness.n_blocks == exp.witness.n_blocks
     assert np.array_equal(got.witness.cids, exp.witness.cids)
     if check_witness_bytes:
-        assert np.array_equal(got.witness.offsets, exp.witness.offsets)
-        assert np.array_equal(got.witness.blob, exp.witness.blob)
+        assert np.array_equal(got.witness.lengths, exp.witness.lengths)
+        assert got.witness.blocks() == exp.witness.blocks()
     assert np.array_equal(got.data_blob, exp.data_blob)
 
 
 def assert_witness_equal(a, b):
     assert np.array_equal(a.cids, b.cids)
-    assert np.array_equal(a.offsets, b.offsets)
-    assert np.array_equal(a.blob, b.blob)
+    assert np.array_equal(a.lengths, b.lengths)
+    assert a.blocks() == b.blocks()
 
 
 class ShuffledTipset:
