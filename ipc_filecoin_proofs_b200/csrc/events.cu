@@ -24,12 +24,15 @@ namespace ipcfp {
 // ------------------------------------------------------------------------------------------ events AMT walk
 enum WalkMode { WALK_ANY = 0, WALK_COUNT = 1, WALK_EMIT = 2 };
 
+// A CID value of a message AMT as five aligned words: w[0..3] digest bytes, w[4] low 48 bits = CID prefix bytes 0..5
+struct RawCid { uint64_t w[5]; };
+
 struct EmitCtx {
     ipcfp_event_proof* proofs;   // base for this match
     uint8_t* blob;               // data blob base (whole result)
     uint64_t blob_off;           // running offset for this match
     uint64_t exec_index;
-    const uint8_t* msg_cid;      // 38 bytes
+    RawCid msg_cid;
 };
 struct WalkOut { uint32_t nproofs; uint32_t nbytes; bool any; };
 
@@ -51,7 +54,8 @@ __device__ __forceinline__ void emit_proof(const uint8_t* p, const EvLog& ev, ui
     o = ec.blob + ec.blob_off;
     for (uint32_t b = 0; b < ev.data_len; b++) o[b] = p[ev.data_off + b];
     ec.blob_off += ev.data_len;
-    for (int b = 0; b < 38; b++) q.message_cid[b] = ec.msg_cid[b];
+    for (int b = 0; b < 6; b++) q.message_cid[b] = (uint8_t)(ec.msg_cid.w[4] >> (8 * b));
+    for (int b = 0; b < 32; b++) q.message_cid[6 + b] = (uint8_t)(ec.msg_cid.w[b >> 3] >> (8 * (b & 7)));
     q._pad[0] = q._pad[1] = 0;
     ec.proofs[k] = q;
 }
@@ -222,7 +226,7 @@ struct Pass2Args {
     const uint32_t* match_rel;     // positions relative to lo, ascending
     uint64_t n_match;
     uint32_t receipts_root_blk;
-    const uint8_t* exec_cids;      // exec_raw[pos] 38-byte CIDs
+    const RawCid* exec_cids;       // exec_raw[pos]
     const uint32_t* exec_idx;      // execution order → position in exec_raw
     const unsigned long long* n_exec;
     uint32_t* wbits;
@@ -261,7 +265,7 @@ template <int MODE> __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) 
         ec.blob = a.blob;
         ec.blob_off = a.byte_base[t];
         ec.exec_index = i;
-        ec.msg_cid = a.exec_cids + 38ull * a.exec_idx[i];
+        ec.msg_cid = a.exec_cids[a.exec_idx[i]];
         rc = walk_events<WALK_EMIT>(a.store, (uint32_t)root, a.m, nullptr, wo, &ec, &detail);
     }
     if (rc) { report_error(a.err, ST_PASS2, i, rc, detail); return; }
@@ -358,31 +362,51 @@ __global__ void k_setup(SetupArgs a) {
     if (r.err) report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_DECODE, r.err);
 }
 
-struct LevelArgs {
+// ---- message-AMT walk: order-preserving level-synchronous BFS (count → scan → expand) -----------------
+// A frontier item is one AMT node: block index, meta (amt ordinal << 16 | is_root << 8 | level),
+// base index. Every level first counts each item's outputs (from the node's bitmap), an exclusive
+// scan assigns output slots, then the node is fully decoded/validated and its children (or, in the
+// last round, its values) are written in place — so frontiers and the final value list stay in
+// (AMT, index) order, which is the reference's in-order `for_each` order. Leaves of shallow AMTs are
+// parked (re-emitted unchanged) until the last round.
+#define AMT_SENTINEL 0xffffffffu
+
+struct Frontier { uint32_t* blk; uint32_t* meta; uint64_t* base; };
+
+__device__ __forceinline__ uint32_t amt_item_count(const StoreView& s, uint32_t blk, uint32_t meta, uint32_t round, uint32_t last_round) {
+    if (meta == AMT_SENTINEL) return 0;
+    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1;
+    if (level == 0 && round < last_round) return 1;  // parked
+    uint32_t len;
+    const uint8_t* p = store_block(s, blk, len);
+    Rd r(p, len);
+    if (is_root) { uint32_t bw, h; uint64_t c; amt_root_begin(r, 0, bw, h, c); }
+    rd_array_exact(r, 3);
+    uint32_t bl;
+    uint32_t bo = rd_bytes(r, bl);
+    if (r.err || bl != 1) return 0;  // reported by the expand pass
+    if (level != 0 || round == last_round) return (uint32_t)__popc((uint32_t)p[bo]);
+    return 0;
+}
+
+struct ExpandArgs {
     StoreView store;
-    const uint32_t* f_blk; const uint32_t* f_meta; const uint64_t* f_base;
-    const unsigned long long* f_count;
-    uint32_t round, last_round;
-    uint32_t record;               // mark visited blocks in the witness bitmap
+    Frontier in;
+    const unsigned long long* in_count;
+    const uint64_t* out_off;   // exclusive scan of the counts
+    uint32_t round, last_round, record;
     uint32_t* wbits;
     unsigned long long* err;
-    uint32_t* child_blk;           // [item*8 + slot]
-    uint8_t* mask8;                // [item] slot bitmap (children, or values in the last round)
-    uint8_t* val_cids;             // last round: [item*8 + slot][38]
+    Frontier out;              // rounds < last_round
+    RawCid* vals;              // last round
     uint32_t cap;
 };
-// One BFS level over ALL message AMTs at once. Leaves of shallow AMTs are parked (re-emitted
-// unchanged) until the last round so that the final frontier is in (AMT, index) order.
-__global__ void __launch_bounds__(128) k_amt_level(LevelArgs a) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t cnt = *a.f_count;
-    if (cnt > a.cap) cnt = a.cap;
-    if (t >= cnt) return;
-    uint32_t blk = a.f_blk[t], meta = a.f_meta[t];
+__device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t, uint32_t blk, uint32_t meta, uint64_t base, uint32_t expect) {
+    if (meta == AMT_SENTINEL) return;
     uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    uint64_t o = a.out_off[t];
     if (level == 0 && a.round < a.last_round) {  // park
-        a.child_blk[t * 8] = blk;
-        a.mask8[t] = 1;
+        if (o < a.cap) { a.out.blk[o] = blk; a.out.meta[o] = meta; a.out.base[o] = base; }
         return;
     }
     uint32_t len;
@@ -396,103 +420,143 @@ __global__ void __launch_bounds__(128) k_amt_level(LevelArgs a) {
     for (uint32_t v = 0; v < nv && !r.err; v++) (void)rd_cid(r);
     amt_node_finish(r, h, nv, level);
     uint64_t eidx = 3ull * (amt >> 1) + 1 + (amt & 1);
-    if (r.err) { report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err); a.mask8[t] = 0; return; }
-    uint32_t mask = 0;
-    if (h.nl) {
-        for (uint32_t k = 0; k < h.nl; k++) {
+    uint32_t produced = 0;
+    if (r.err) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err);
+    else if (h.nl) {
+        for (uint32_t k = 0; k < h.nl && k < expect; k++) {
             uint32_t slot = bm_select(h.bm, k);
             int32_t child = store_lookup(a.store, p + h.links_off + 43 * k + 5);
-            if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); continue; }
-            if (a.record) witness_mark(a.wbits, (uint32_t)child);
-            a.child_blk[t * 8 + slot] = (uint32_t)child;
-            mask |= 1u << slot;
+            uint64_t d = o + k;
+            if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
+            else {
+                if (a.record) witness_mark(a.wbits, (uint32_t)child);
+                if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
+            }
+            produced++;
         }
     } else if (a.round == a.last_round) {
-        for (uint32_t v = 0; v < nv; v++) {
-            uint32_t slot = bm_select(h.bm, v);
+        for (uint32_t v = 0; v < nv && v < expect; v++) {
             const uint8_t* src = p + vals_off + 43 * v + 5;
-            uint8_t* dst = a.val_cids + (t * 8 + slot) * 38;
-            for (int b = 0; b < 38; b++) dst[b] = src[b];
-            mask |= 1u << slot;
+            RawCid c;
+            c.w[4] = load_u64_any(src) & 0xffffffffffffull;
+            Digest dg = load_digest(src + 6);
+            c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
+            a.vals[o + v] = c;
+            produced++;
         }
     }
-    a.mask8[t] = (uint8_t)mask;
+    // slots promised by the count pass but not produced (malformed node): neutralise them
+    if (a.round < a.last_round) for (uint32_t k = produced; k < expect; k++) if (o + k < a.cap) a.out.meta[o + k] = AMT_SENTINEL;
+    if (a.round == a.last_round) for (uint32_t k = produced; k < expect; k++) { RawCid z{}; a.vals[o + k] = z; }
 }
 
-struct GatherArgs {
-    const uint32_t* slot_idx;                  // ordered set bits of mask8 (item*8 + slot)
-    const unsigned long long* n_out;
-    const uint32_t* f_blk; const uint32_t* f_meta; const uint64_t* f_base;
-    const uint32_t* child_blk;
-    uint32_t* o_blk; uint32_t* o_meta; uint64_t* o_base;
-    unsigned long long* o_count;
-    unsigned long long* err;
-    uint32_t cap;
-};
-__global__ void k_gather_frontier(GatherArgs a) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t n = *a.n_out;
-    if (j == 0) {
-        if (n > a.cap) { report_error(a.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); *a.o_count = a.cap; }
-        else *a.o_count = n;
-    }
-    if (n > a.cap) n = a.cap;
-    if (j >= n) return;
-    uint32_t si = a.slot_idx[j];
-    uint32_t item = si >> 3, slot = si & 7;
-    uint32_t meta = a.f_meta[item];
-    uint32_t level = meta & 0xff;
-    a.o_blk[j] = a.child_blk[si];
-    if (level == 0) { a.o_meta[j] = meta; a.o_base[j] = a.f_base[item]; }  // parked leaf
-    else {
-        a.o_meta[j] = make_meta(meta >> 16, 0, level - 1);
-        a.o_base[j] = a.f_base[item] + (uint64_t)slot * pow_sat(3, level);
-    }
+__global__ void __launch_bounds__(128) k_amt_count(StoreView store, Frontier in, const unsigned long long* in_count, uint32_t round, uint32_t last_round,
+                                                   uint32_t cap, uint32_t* counts) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t cnt = *in_count;
+    if (cnt > cap) cnt = cap;
+    if (t >= cnt) { counts[t] = 0; return; }   // the grid covers exactly the scanned range
+    counts[t] = amt_item_count(store, in.blk[t], in.meta[t], round, last_round);
 }
-__global__ void k_gather_values(const uint32_t* __restrict__ slot_idx, const unsigned long long* n_out, const uint8_t* __restrict__ val_cids,
-                                uint8_t* exec_raw, uint64_t cap) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t n = *n_out;
-    if (n > cap) n = cap;
-    if (j >= n) return;
-    const uint8_t* src = val_cids + 38ull * slot_idx[j];
-    uint8_t* dst = exec_raw + 38 * j;
-    for (int b = 0; b < 38; b++) dst[b] = src[b];
+__global__ void __launch_bounds__(128) k_amt_expand(ExpandArgs a, const uint32_t* counts, unsigned long long* out_count, const unsigned long long* total) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t cnt = *a.in_count;
+    if (cnt > a.cap) cnt = a.cap;
+    if (t == 0) {
+        unsigned long long n = *total;
+        if (a.round < a.last_round && n > a.cap) { report_error(a.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = a.cap; }
+        *out_count = n;
+    }
+    if (t >= cnt) return;
+    amt_item_expand(a, t, a.in.blk[t], a.in.meta[t], a.in.base[t], counts[t]);
+}
+
+// Rounds whose frontier is guaranteed to fit one CTA (≤ 1024 items) run fused in a single launch:
+// count, block-wide scan and expand per level with __syncthreads between levels.
+#define TOP_CAP 1024
+__global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier ping, Frontier pong, unsigned long long* count_io, uint32_t first_round,
+                                                      uint32_t n_rounds, uint64_t* scan_tmp) {
+    __shared__ uint32_t s_cnt[TOP_CAP];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    Frontier cur = ping, nxt = pong;
+    for (uint32_t rr = 0; rr < n_rounds; rr++) {
+        uint32_t round = first_round + rr;
+        uint64_t cnt = *count_io;
+        if (cnt > TOP_CAP) cnt = TOP_CAP;
+        uint32_t c = t < cnt ? amt_item_count(a0.store, cur.blk[t], cur.meta[t], round, a0.last_round) : 0;
+        // block exclusive scan of c
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = s_warp[lane], w = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += y; }
+            s_warp[lane] = w - v;
+            if (lane == 31) s_total = w;
+        }
+        __syncthreads();
+        uint32_t ex = s_warp[warp] + x - c;
+        scan_tmp[t] = ex;
+        s_cnt[t] = c;
+        __syncthreads();
+        ExpandArgs a = a0;
+        a.in = cur; a.out = nxt; a.round = round; a.out_off = scan_tmp;
+        if (t < cnt) amt_item_expand(a, t, cur.blk[t], cur.meta[t], cur.base[t], s_cnt[t]);
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long n = s_total;
+            if (round < a0.last_round && n > a0.cap) { report_error(a0.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = a0.cap; }
+            *count_io = n;
+        }
+        __threadfence();
+        __syncthreads();
+        Frontier tmp = cur; cur = nxt; nxt = tmp;
+    }
 }
 
 // first-seen dedup of the raw execution list (events/utils.rs:56-91): hash set keyed by the full
 // CID holding the smallest position; an entry survives iff it holds its own position.
-__global__ void k_dedup_insert(const uint8_t* __restrict__ raw, uint64_t n, unsigned long long* table, uint64_t mask) {
+__device__ __forceinline__ bool rawcid_eq(const RawCid& x, const RawCid& y) {
+    return x.w[0] == y.w[0] && x.w[1] == y.w[1] && x.w[2] == y.w[2] && x.w[3] == y.w[3] && x.w[4] == y.w[4];
+}
+__device__ __forceinline__ uint64_t rawcid_hash(const RawCid& c) { return mix64(c.w[0] ^ (c.w[2] * 0x9E3779B97F4A7C15ULL) ^ c.w[4]); }
+__global__ void k_dedup_insert(const RawCid* __restrict__ raw, uint64_t n, unsigned long long* table, uint64_t mask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t* c = raw + 38 * i;
-    uint64_t h = mix64(load_u64_le(c + 6) ^ (load_u64_le(c + 22) * 0x9E3779B97F4A7C15ULL) ^ c[1]);
+    RawCid c = raw[i];
+    uint64_t h = rawcid_hash(c);
     uint32_t fp = (uint32_t)(h >> 32) | 1u;
     unsigned long long mine = ((unsigned long long)fp << 32) | (unsigned long long)(i + 1);
     uint64_t slot = h & mask;
     for (;;) {
         unsigned long long e = table[slot];
         if (e == 0) { e = atomicCAS(&table[slot], 0ull, mine); if (e == 0) return; }
-        if ((uint32_t)(e >> 32) == fp && cid38_equal(raw + 38ull * ((uint32_t)e - 1), c)) { atomicMin(&table[slot], mine); return; }
+        if ((uint32_t)(e >> 32) == fp && rawcid_eq(raw[(uint32_t)e - 1], c)) { atomicMin(&table[slot], mine); return; }
         slot = (slot + 1) & mask;
     }
 }
-__global__ void k_dedup_flags(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ table, uint64_t mask,
+__global__ void k_dedup_flags(const RawCid* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ table, uint64_t mask,
                               uint32_t* keep_bits) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     if (i < n) {
-        const uint8_t* c = raw + 38 * i;
-        uint64_t h = mix64(load_u64_le(c + 6) ^ (load_u64_le(c + 22) * 0x9E3779B97F4A7C15ULL) ^ c[1]);
+        RawCid c = raw[i];
+        uint64_t h = rawcid_hash(c);
         uint32_t fp = (uint32_t)(h >> 32) | 1u;
         uint64_t slot = h & mask;
         for (;;) {
             unsigned long long e = table[slot];
             if (e == 0) break;  // cannot happen: every entry was inserted
-            if ((uint32_t)(e >> 32) == fp && cid38_equal(raw + 38ull * ((uint32_t)e - 1), c)) { keep = ((uint32_t)e - 1) == (uint32_t)i; break; }
+            if ((uint32_t)(e >> 32) == fp && rawcid_eq(raw[(uint32_t)e - 1], c)) { keep = ((uint32_t)e - 1) == (uint32_t)i; break; }
             slot = (slot + 1) & mask;
         }
     }
+    __syncwarp();
     unsigned b = __ballot_sync(0xffffffffu, keep);
     if ((threadIdx.x & 31) == 0) keep_bits[i >> 5] = b;
 }
@@ -644,53 +708,62 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
 
     // ---- message AMT BFS (recording + raw execution list)
     IPCFP_CUDA(cudaEventRecord(s->ev[1], st));
-    AsyncBuf<uint32_t> child_blk(cap * 8, st), slot_idx(cap * 8 + 32, st);
-    AsyncBuf<uint8_t> mask8(cap + 64, st);
-    AsyncBuf<uint64_t> word_prefix(cap * 8 / 32 + 64, st), scratch(scan_scratch_elems(std::max<uint64_t>(cap, N) + 64) + 64, st);
-    AsyncBuf<uint8_t> val_cids;
-    uint32_t *cb = fA_blk.p, *cm = fA_meta.p, *nb_ = fB_blk.p, *nm = fB_meta.p;
-    uint64_t *cbase = fA_base.p, *nbase = fB_base.p;
-    unsigned long long *ccount = dw + 1, *ncount = dw + 2;
-    uint64_t bound = namt;  // upper bound of the frontier size in this round
-    uint64_t last_bound = 0;
-    for (uint32_t round = 0; round <= last_round; round++) {
-        uint64_t items = std::min<uint64_t>(bound, cap);
-        if (round == last_round) { val_cids.alloc(items * 8 * 38 + 64, st); last_bound = items; }
-        IPCFP_CUDA(cudaMemsetAsync(mask8.p, 0, (items + 3) / 4 * 4 + 4, st));
-        LevelArgs la;
-        la.store = s->view; la.f_blk = cb; la.f_meta = cm; la.f_base = cbase; la.f_count = ccount;
-        la.round = round; la.last_round = last_round; la.record = skip_tx ? 0 : 1; la.wbits = wbits.p; la.err = dw;
-        la.child_blk = child_blk.p; la.mask8 = mask8.p; la.val_cids = val_cids.p; la.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
-        if (items) { k_amt_level<<<div_up(items, 128), 128, 0, st>>>(la); IPCFP_LAUNCH_CHECK(); }
-        bitmap_to_indices((const uint32_t*)mask8.p, items * 8, slot_idx.p, (uint64_t*)ncount, word_prefix.p, scratch.p, st);
-        if (round < last_round) {
-            GatherArgs ga;
-            ga.slot_idx = slot_idx.p; ga.n_out = ncount; ga.f_blk = cb; ga.f_meta = cm; ga.f_base = cbase; ga.child_blk = child_blk.p;
-            ga.o_blk = nb_; ga.o_meta = nm; ga.o_base = nbase; ga.o_count = ncount; ga.err = dw; ga.cap = la.cap;
-            uint64_t nb_bound = std::min<uint64_t>(items * 8, cap);
-            k_gather_frontier<<<div_up(std::max<uint64_t>(nb_bound, 1), 256), 256, 0, st>>>(ga); IPCFP_LAUNCH_CHECK();
-            std::swap(cb, nb_); std::swap(cm, nm); std::swap(cbase, nbase); std::swap(ccount, ncount);
-            bound = nb_bound;
-        }
+    AsyncBuf<uint32_t> counts(cap + 1024, st);
+    AsyncBuf<uint64_t> out_off(cap + 1024, st), scratch(scan_scratch_elems(std::max<uint64_t>(cap, N) + 64) + 64, st);
+    Frontier fcur{fA_blk.p, fA_meta.p, fA_base.p}, fnxt{fB_blk.p, fB_meta.p, fB_base.p};
+    unsigned long long *ccount = dw + 1, *ncount = dw + 2, *total_dev = dw + 13;
+    ExpandArgs ea;
+    ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw;
+    ea.vals = nullptr; ea.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
+    // static frontier bound per round: namt * 8^round
+    auto bound_of = [&](uint32_t round) { uint64_t b = namt; for (uint32_t k = 0; k < round && b <= cap; k++) b *= 8; return std::min<uint64_t>(b, cap); };
+    AsyncBuf<RawCid> exec_raw;
+    uint64_t raw_cap = 0;
+    auto alloc_vals = [&]() {
+        raw_cap = std::min<uint64_t>(bound_of(last_round) * 8, 8 * cap);
+        exec_raw.alloc(raw_cap + 64, st);
+        ea.vals = exec_raw.p;
+    };
+    // fused single-CTA rounds while the static bound fits one CTA
+    uint32_t top_rounds = 0;
+    while (top_rounds <= last_round && bound_of(top_rounds) <= TOP_CAP) top_rounds++;
+    uint32_t round = 0;
+    if (top_rounds) {
+        if (top_rounds > last_round) alloc_vals();  // the last round is inside the fused kernel
+        ExpandArgs a0 = ea;
+        a0.in = fcur; a0.in_count = ccount; a0.out = fnxt; a0.round = 0; a0.out_off = out_off.p;
+        k_amt_top<<<1, TOP_CAP, 0, st>>>(a0, fcur, fnxt, ccount, 0, top_rounds, out_off.p); IPCFP_LAUNCH_CHECK();
+        if (top_rounds & 1) std::swap(fcur, fnxt);
+        round = top_rounds;
     }
-    // ncount now holds the number of raw execution entries.
+    for (; round <= last_round; round++) {
+        uint64_t items = bound_of(round);
+        if (round == last_round) alloc_vals();
+        unsigned grid = div_up(std::max<uint64_t>(items, 1), 128);
+        k_amt_count<<<grid, 128, 0, st>>>(s->view, fcur, ccount, round, last_round, ea.cap, counts.p); IPCFP_LAUNCH_CHECK();
+        exclusive_scan_u32(counts.p, out_off.p, (uint64_t)grid * 128, (uint64_t*)total_dev, scratch.p, st);
+        ExpandArgs a = ea;
+        a.in = fcur; a.in_count = ccount; a.out = fnxt; a.round = round; a.out_off = out_off.p;
+        k_amt_expand<<<grid, 128, 0, st>>>(a, counts.p, ncount, total_dev); IPCFP_LAUNCH_CHECK();
+        std::swap(fcur, fnxt);
+        std::swap(ccount, ncount);
+    }
+    // *ccount now holds the number of raw execution entries (k_amt_top leaves it in place as well).
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
     wbuild.snapshot(wbits.p);
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 2, ncount, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 2, ccount, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw + 8, dw + 8, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
-    uint64_t nraw = std::min<uint64_t>(hw[2], last_bound * 8);
+    uint64_t nraw = std::min<uint64_t>(hw[2], raw_cap);
     wbuild.start_copy(hw[8]);
-    AsyncBuf<uint8_t> exec_raw(nraw * 38 + 64, st);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
     if (nraw) {
-        k_gather_values<<<div_up(nraw, 256), 256, 0, st>>>(slot_idx.p, ncount, val_cids.p, exec_raw.p, nraw); IPCFP_LAUNCH_CHECK();
         uint64_t slots = 64;
         while (slots < 2 * nraw) slots <<= 1;
         AsyncBuf<unsigned long long> dtab(slots, st);
@@ -700,7 +773,6 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         AsyncBuf<uint64_t> wp2((nraw + 31) / 32 + 8, st);
         bitmap_to_indices(keep_bits.p, nraw, exec_idx.p, (uint64_t*)n_exec_dev, wp2.p, scratch.p, st);
     } else IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));
-    val_cids.release();
     IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
 
     // ---- PASS 1
