@@ -127,6 +127,8 @@ struct Pass1Args {
     const uint8_t* has_root;
     uint64_t lo, hi;
     uint32_t* match_bits;          // bit (i - lo)
+    uint32_t* cnt;                 // [i - lo] matching events of receipt i  (EventProof count of pass 2)
+    uint32_t* nbytes;              // [i - lo] topics+data bytes of those events
     unsigned long long* err;
     unsigned long long* stats;     // [0] nodes scanned, [1] bytes scanned
 };
@@ -137,7 +139,7 @@ struct Pass1Args {
 __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
     uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool matched = false;
-    uint32_t bytes = 0, nodes = 0;
+    uint32_t bytes = 0, nodes = 0, np_ = 0, nb_ = 0;
     // phase 1: Blockstore::get of the events root (hash probe); every lane takes part so the warp
     // can be re-converged before the long decode
     const bool valid = i < a.hi && a.has_root[i];
@@ -164,17 +166,19 @@ __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
         amt_node_begin(r, bw, h);
         uint32_t nv = rd_array(r);
         WalkOut wo{0, 0, false};
-        node_events<WALK_ANY>(r, p, h, nv, 0, a.m, wo, nullptr);
+        node_events<WALK_COUNT>(r, p, h, nv, 0, a.m, wo, nullptr);
         amt_node_finish(r, h, nv, height);
         if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
         else if (h.nl) {
             uint32_t detail = 0;
-            WalkOut w2{0, 0, false};
-            uint32_t rc = walk_events<WALK_ANY>(a.store, (uint32_t)blk, a.m, nullptr, w2, nullptr, &detail);
-            if (rc) report_error(a.err, ST_PASS1, i, rc, detail);
-            else matched = w2.any;
-        } else matched = wo.any;
+            wo = WalkOut{0, 0, false};
+            uint32_t rc = walk_events<WALK_COUNT>(a.store, (uint32_t)blk, a.m, nullptr, wo, nullptr, &detail);
+            if (rc) { report_error(a.err, ST_PASS1, i, rc, detail); wo = WalkOut{0, 0, false}; }
+        }
+        matched = wo.any;
+        np_ = wo.nproofs; nb_ = wo.nbytes;
     }
+    if (i < a.hi) { a.cnt[i - a.lo] = np_; a.nbytes[i - a.lo] = nb_; }
     unsigned b = __ballot_sync(0xffffffffu, matched);
     if ((threadIdx.x & 31) == 0) a.match_bits[((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5] = b;
     // per-warp statistics (algorithmic bytes of the scan)
@@ -231,45 +235,46 @@ struct Pass2Args {
     const unsigned long long* n_exec;
     uint32_t* wbits;
     unsigned long long* err;
-    uint32_t* cnt;                 // per match: number of proofs (phase COUNT out / EMIT in)
-    uint32_t* nbytes;              // per match: blob bytes
-    const uint64_t* proof_base;    // EMIT: exclusive scans
+    const uint32_t* cnt;           // [i - lo] proofs of receipt i (from pass 1)
+    const uint64_t* proof_base;    // [i - lo] exclusive scans over all receipts of the range
     const uint64_t* byte_base;
     ipcfp_event_proof* proofs;
     uint8_t* blob;
+    uint32_t* any_skip;            // set when a matching receipt is absent from the receipts AMT
 };
 
-template <int MODE> __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
+// One thread per matching receipt (events/generator.rs:242-301): exec.get(i), r_amt.get(i) with path
+// recording, full in-order walk of its events AMT with recording, EventProof emission at the
+// offsets pass 1 already counted.
+__global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_match) return;
-    uint64_t i = a.lo + a.match_rel[t];
-    if (MODE == WALK_COUNT) {
-        a.cnt[t] = 0; a.nbytes[t] = 0;
-        // exec.get(i) comes first (events/generator.rs:244-246)
-        if (i >= *a.n_exec) { report_error(a.err, ST_PASS2, i, DC_MISSING_EXEC, 0); return; }
-        uint32_t detail = 0;
-        int got = receipts_get(a.store, a.receipts_root_blk, i, a.wbits, &detail);
-        if (got < 0) { report_error(a.err, ST_PASS2, i, (uint32_t)(-got), detail); return; }
-        if (got == 0) return;  // `continue` at :249-251
-    } else if (a.cnt[t] == 0) return;
+    uint32_t rel = a.match_rel[t];
+    uint64_t i = a.lo + rel;
+    // exec.get(i) comes first (:244-246)
+    if (i >= *a.n_exec) { report_error(a.err, ST_PASS2, i, DC_MISSING_EXEC, 0); return; }
+    uint32_t detail = 0;
+    int got = receipts_get(a.store, a.receipts_root_blk, i, a.wbits, &detail);
+    if (got < 0) { report_error(a.err, ST_PASS2, i, (uint32_t)(-got), detail); return; }
+    ipcfp_event_proof* out = a.proofs + a.proof_base[rel];
+    if (got == 0) {  // `continue` at :249-251 — the slots pass 1 reserved stay empty and are dropped on the host
+        uint32_t c = a.cnt[rel];
+        for (uint32_t k = 0; k < c; k++) out[k].exec_index = 0xFFFFFFFFFFFFFFFFull;
+        *a.any_skip = 1;
+        return;
+    }
     int32_t root = store_lookup(a.store, a.events_roots + 38 * i);
     if (root < 0) { report_error(a.err, ST_PASS2, i, DC_MISSING, 0); return; }
-    if (MODE == WALK_COUNT) witness_mark(a.wbits, (uint32_t)root);
+    witness_mark(a.wbits, (uint32_t)root);
     WalkOut wo{0, 0, false};
-    uint32_t detail = 0;
-    uint32_t rc;
-    if (MODE == WALK_COUNT) rc = walk_events<WALK_COUNT>(a.store, (uint32_t)root, a.m, a.wbits, wo, nullptr, &detail);
-    else {
-        EmitCtx ec;
-        ec.proofs = a.proofs + a.proof_base[t];
-        ec.blob = a.blob;
-        ec.blob_off = a.byte_base[t];
-        ec.exec_index = i;
-        ec.msg_cid = a.exec_cids[a.exec_idx[i]];
-        rc = walk_events<WALK_EMIT>(a.store, (uint32_t)root, a.m, nullptr, wo, &ec, &detail);
-    }
-    if (rc) { report_error(a.err, ST_PASS2, i, rc, detail); return; }
-    if (MODE == WALK_COUNT) { a.cnt[t] = wo.nproofs; a.nbytes[t] = wo.nbytes; }
+    EmitCtx ec;
+    ec.proofs = out;
+    ec.blob = a.blob;
+    ec.blob_off = a.byte_base[rel];
+    ec.exec_index = i;
+    ec.msg_cid = a.exec_cids[a.exec_idx[i]];
+    uint32_t rc = walk_events<WALK_EMIT>(a.store, (uint32_t)root, a.m, a.wbits, wo, &ec, &detail);
+    if (rc) report_error(a.err, ST_PASS2, i, rc, detail);
 }
 
 // ------------------------------------------------------------------------------------------ setup + message AMT walk
@@ -776,53 +781,48 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
 
     // ---- PASS 1
-    AsyncBuf<uint32_t> match_bits((N + 31) / 32 + 8, st);
+    AsyncBuf<uint32_t> match_bits((N + 31) / 32 + 8, st), cnt(N + 8, st), nby(N + 8, st);
+    AsyncBuf<uint64_t> pbase(N + 8, st), bbase(N + 8, st);
     Pass1Args p1;
     p1.store = s->view; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
-    p1.match_bits = match_bits.p; p1.err = dw; p1.stats = dw + 4;
+    p1.match_bits = match_bits.p; p1.cnt = cnt.p; p1.nbytes = nby.p; p1.err = dw; p1.stats = dw + 4;
     if (N) { k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1); IPCFP_LAUNCH_CHECK(); }
     IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
     AsyncBuf<uint32_t> match_rel(N + 32, st);
     AsyncBuf<uint64_t> wp3((N + 31) / 32 + 8, st);
     unsigned long long* n_match_dev = dw + 6;
     bitmap_to_indices(match_bits.p, (N + 31) / 32 * 32, match_rel.p, (uint64_t*)n_match_dev, wp3.p, scratch.p, st);
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8 * 8, cudaMemcpyDeviceToHost, st));
+    exclusive_scan_u32(cnt.p, pbase.p, N, (uint64_t*)(dw + 7), scratch.p, st);
+    exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 14 * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     const uint64_t n_exec = hw[3], M = hw[6];
     const uint64_t pass1_nodes = hw[4], pass1_bytes = hw[5];
+    uint64_t n_proofs = hw[7], n_bytes = hw[12];
 
     // ---- PASS 2
     std::unique_ptr<EventResultBox> box(new EventResultBox());
     memset(&box->r, 0, sizeof box->r);
-    AsyncBuf<uint32_t> cnt(M + 8, st), nby(M + 8, st);
-    AsyncBuf<uint64_t> pbase(M + 8, st), bbase(M + 8, st);
-    Pass2Args p2;
-    p2.store = s->view; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
-    p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
-    p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.nbytes = nby.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
-    p2.proofs = nullptr; p2.blob = nullptr;
-    uint64_t n_proofs = 0, n_bytes = 0;
-    AsyncBuf<ipcfp_event_proof> d_proofs;
-    AsyncBuf<uint8_t> d_blob;
+    AsyncBuf<ipcfp_event_proof> d_proofs(n_proofs + 1, st);
+    AsyncBuf<uint8_t> d_blob(n_bytes + 16, st);
+    uint32_t* any_skip_dev = misc.p + 2;
     if (M) {
-        k_pass2<WALK_COUNT><<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
-        exclusive_scan_u32(cnt.p, pbase.p, M, (uint64_t*)(dw + 7), scratch.p, st);
-        exclusive_scan_u32(nby.p, bbase.p, M, (uint64_t*)(dw + 12), scratch.p, st);
+        Pass2Args p2;
+        p2.store = s->view; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
+        p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
+        p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
+        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev;
+        k_pass2<<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
     wbuild.finish_enqueue(wbits.p);
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 14 * 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 20, any_skip_dev, 4, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     const uint64_t mB = hw[10];
-    if (M) {
-        n_proofs = hw[7]; n_bytes = hw[12];
-        d_proofs.alloc(n_proofs + 1, st);
-        d_blob.alloc(n_bytes + 16, st);
-        p2.proofs = d_proofs.p; p2.blob = d_blob.p;
-        if (n_proofs) { k_pass2<WALK_EMIT><<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK(); }
-    }
+    const bool any_skip = (*(const uint32_t*)(hw + 20)) != 0;
     IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
 
     // ---- results to the host
@@ -843,6 +843,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         uint64_t* mo = box->matching.as<uint64_t>();
         const uint32_t* rp = rel.as<uint32_t>();
         for (uint64_t k = 0; k < M; k++) mo[k] = lo + rp[k];
+    }
+    if (any_skip) {  // receipts the AMT does not hold (`continue` at :249-251): compact their reserved slots away
+        ipcfp_event_proof* pp = box->proofs.as<ipcfp_event_proof>();
+        uint64_t w = 0;
+        for (uint64_t k = 0; k < n_proofs; k++) if (pp[k].exec_index != UINT64_MAX) pp[w++] = pp[k];
+        n_proofs = w;
     }
     ipcfp_event_result& r = box->r;
     r.n_matching = M; r.matching_indices = box->matching.as<uint64_t>();
