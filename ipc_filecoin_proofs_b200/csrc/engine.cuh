@@ -47,6 +47,7 @@ struct Store {
     DevBuf<uint8_t> cls;
     DevBuf<uint64_t> table;
     StoreView view{};
+    DevBuf<StoreView> view_dev;   // device copy, for out-of-line device functions (keeps kernel params off the stack)
     std::vector<std::array<uint8_t, 6>> class_prefix;  // distinct CID prefixes in this store
     std::vector<uint32_t> class_rank;                  // rank of each class in `Cid` Ord
     uint64_t first_bad = UINT64_MAX;

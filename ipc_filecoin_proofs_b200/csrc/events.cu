@@ -65,6 +65,7 @@ template <int MODE>
 __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNodeHdr& h, uint32_t nv, uint64_t base, const Matcher& m,
                                             WalkOut& wo, EmitCtx* ec) {
     for (uint32_t v = 0; v < nv && !r.err; v++) {
+        if (r.pos + 384 < r.n) prefetch_l2(r.p + r.pos + 384);  // rolling prefetch: ~3 lines ahead of the dependent walk
         EvLog ev;
         decode_stamped_event(r, ev);
         if (r.err) break;
@@ -84,8 +85,10 @@ __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNo
 // fvm_ipld_amt [UPSTREAM]: every reachable node is loaded through the store (and recorded when
 // wbits != nullptr). Returns 0 ok, else DevCode; detail in *detail.
 template <int MODE>
-static __device__ __noinline__ uint32_t walk_events(const StoreView& s, uint32_t root_blk, const Matcher& m, uint32_t* wbits, WalkOut& wo, EmitCtx* ec,
+static __device__ __noinline__ uint32_t walk_events(const StoreView* sp, uint32_t root_blk, const Matcher* mp, uint32_t* wbits, WalkOut& wo, EmitCtx* ec,
                                 uint32_t* detail) {
+    const StoreView& s = *sp;
+    const Matcher m = *mp;
     struct Frame { uint32_t blk; uint32_t k; uint64_t base; };
     Frame stk[66];
     int depth = 0;
@@ -122,6 +125,8 @@ static __device__ __noinline__ uint32_t walk_events(const StoreView& s, uint32_t
 // ------------------------------------------------------------------------------------------ pass 1
 struct Pass1Args {
     StoreView store;
+    const StoreView* store_dev;    // same view in device memory (for the out-of-line walker)
+    const Matcher* m_dev;
     Matcher m;
     const uint8_t* events_roots;
     const uint8_t* has_root;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
     const uint8_t* p = nullptr;
     if (blk >= 0) {
         p = store_block(a.store, (uint32_t)blk, len);
-        for (uint32_t o = 0; o < len; o += 128) prefetch_l2(p + o);  // whole node in flight before the dependent walk
+        for (uint32_t o = 0; o < len && o < 512; o += 128) prefetch_l2(p + o);  // first lines in flight before the dependent walk
     }
     __syncwarp();
     // phase 2: decode the root node, test every event
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
         else if (h.nl) {
             uint32_t detail = 0;
             wo = WalkOut{0, 0, false};
-            uint32_t rc = walk_events<WALK_COUNT>(a.store, (uint32_t)blk, a.m, nullptr, wo, nullptr, &detail);
+            uint32_t rc = walk_events<WALK_COUNT>(a.store_dev, (uint32_t)blk, a.m_dev, nullptr, wo, nullptr, &detail);
             if (rc) { report_error(a.err, ST_PASS1, i, rc, detail); wo = WalkOut{0, 0, false}; }
         }
         matched = wo.any;
@@ -224,6 +229,8 @@ __device__ int receipts_get(const StoreView& s, uint32_t root_blk, uint64_t i, u
 // ------------------------------------------------------------------------------------------ pass 2
 struct Pass2Args {
     StoreView store;
+    const StoreView* store_dev;
+    const Matcher* m_dev;
     Matcher m;
     const uint8_t* events_roots;
     uint64_t lo;
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     ec.blob_off = a.byte_base[rel];
     ec.exec_index = i;
     ec.msg_cid = a.exec_cids[a.exec_idx[i]];
-    uint32_t rc = walk_events<WALK_EMIT>(a.store, (uint32_t)root, a.m, a.wbits, wo, &ec, &detail);
+    uint32_t rc = walk_events<WALK_EMIT>(a.store_dev, (uint32_t)root, a.m_dev, a.wbits, wo, &ec, &detail);
     if (rc) report_error(a.err, ST_PASS2, i, rc, detail);
 }
 
@@ -677,6 +684,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         IPCFP_CUDA(cudaMemcpyAsync(d_cids, cb.data(), cb.size(), cudaMemcpyHostToDevice, st));
         IPCFP_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
     }
+    IPCFP_CUDA(cudaMemcpyAsync(d_matcher, &mh, sizeof(Matcher), cudaMemcpyHostToDevice, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
     k_make_matcher<<<1, 1, 0, st>>>(d_sig, (uint32_t)siglen, d_matcher); IPCFP_LAUNCH_CHECK();
     IPCFP_CUDA(cudaMemcpyAsync(hw + 16, d_matcher, 32, cudaMemcpyDeviceToHost, st));
 
@@ -784,7 +793,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     AsyncBuf<uint32_t> match_bits((N + 31) / 32 + 8, st), cnt(N + 8, st), nby(N + 8, st);
     AsyncBuf<uint64_t> pbase(N + 8, st), bbase(N + 8, st);
     Pass1Args p1;
-    p1.store = s->view; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
+    p1.store = s->view; p1.store_dev = s->view_dev.p; p1.m_dev = d_matcher; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
     p1.match_bits = match_bits.p; p1.cnt = cnt.p; p1.nbytes = nby.p; p1.err = dw; p1.stats = dw + 4;
     if (N) { k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1); IPCFP_LAUNCH_CHECK(); }
     IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
@@ -809,7 +818,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     uint32_t* any_skip_dev = misc.p + 2;
     if (M) {
         Pass2Args p2;
-        p2.store = s->view; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
+        p2.store = s->view; p2.store_dev = s->view_dev.p; p2.m_dev = d_matcher; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
         p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
         p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
         p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev;

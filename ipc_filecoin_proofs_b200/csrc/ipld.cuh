@@ -35,8 +35,20 @@ __device__ __forceinline__ bool cid38_equal(const uint8_t* a, const uint8_t* b) 
 }
 
 // ------------------------------------------------------------------ AMT node framing
+// 256-bit bitmap as four scalars (no dynamically indexed arrays: those would live in local memory)
+struct Bits256 {
+    uint64_t b0, b1, b2, b3;
+    __device__ __forceinline__ void clear() { b0 = b1 = b2 = b3 = 0; }
+    __device__ __forceinline__ uint64_t word(uint32_t w) const { return w == 0 ? b0 : (w == 1 ? b1 : (w == 2 ? b2 : b3)); }
+    __device__ __forceinline__ void or_byte(uint32_t i, uint32_t byte) {  // byte i (0..31), little-endian bit order
+        uint64_t v = (uint64_t)byte << (8 * (i & 7));
+        uint32_t w = i >> 3;
+        b0 |= w == 0 ? v : 0; b1 |= w == 1 ? v : 0; b2 |= w == 2 ? v : 0; b3 |= w == 3 ? v : 0;
+    }
+    __device__ __forceinline__ uint32_t popc() const { return (uint32_t)(__popcll(b0) + __popcll(b1) + __popcll(b2) + __popcll(b3)); }
+};
 struct AmtNodeHdr {
-    uint64_t bm[4];      // bitmap bits 0..255 (bit i of the node ↔ bm[i/64] >> (i%64))
+    Bits256 bm;          // bit i of the node ↔ bm.word(i/64) >> (i%64)
     uint32_t pc;         // popcount
     uint32_t nl;         // number of links
     uint32_t links_off;  // offset of the first link item (each exactly 43 bytes)
@@ -47,14 +59,14 @@ __device__ __forceinline__ void amt_node_begin(Rd& r, uint32_t bw, AmtNodeHdr& h
     uint32_t blen;
     uint32_t boff = rd_bytes(r, blen);
     uint32_t want = bw <= 3 ? 1u : (1u << (bw - 3));
-    h.bm[0] = h.bm[1] = h.bm[2] = h.bm[3] = 0;
+    h.bm.clear();
     h.pc = 0;
     if (!r.err && blen != want) rd_fail(r, CE_AMT);
     if (!r.err) {
-        for (uint32_t i = 0; i < blen; i++) h.bm[i >> 3] |= (uint64_t)r.p[boff + i] << (8 * (i & 7));
+        for (uint32_t i = 0; i < blen; i++) h.bm.or_byte(i, r.p[boff + i]);
         uint32_t width = 1u << bw;
-        if (width < 8 && (h.bm[0] >> width)) rd_fail(r, CE_AMT);  // bit beyond the node width
-        h.pc = (uint32_t)(__popcll(h.bm[0]) + __popcll(h.bm[1]) + __popcll(h.bm[2]) + __popcll(h.bm[3]));
+        if (width < 8 && (h.bm.b0 >> width)) rd_fail(r, CE_AMT);  // bit beyond the node width
+        h.pc = h.bm.popc();
     }
     h.nl = rd_array(r);
     h.links_off = r.pos;
@@ -68,20 +80,18 @@ __device__ __forceinline__ void amt_node_finish(Rd& r, const AmtNodeHdr& h, uint
     else { if ((nv && height != 0) || h.pc != nv) rd_fail(r, CE_AMT); }
     if (!r.err) rd_end(r);
 }
-__device__ __forceinline__ bool bm_test(const uint64_t bm[4], uint32_t i) { return (bm[i >> 6] >> (i & 63)) & 1; }
-__device__ __forceinline__ uint32_t bm_rank(const uint64_t bm[4], uint32_t i) {  // set bits below i
-    uint32_t c = 0;
-    uint32_t w = i >> 6;
-    for (uint32_t k = 0; k < w; k++) c += (uint32_t)__popcll(bm[k]);
-    uint32_t b = i & 63;
-    if (b) c += (uint32_t)__popcll(bm[w] & ((1ull << b) - 1));
+__device__ __forceinline__ bool bm_test(const Bits256& bm, uint32_t i) { return (bm.word(i >> 6) >> (i & 63)) & 1; }
+__device__ __forceinline__ uint32_t bm_rank(const Bits256& bm, uint32_t i) {  // set bits below i
+    uint32_t w = i >> 6, b = i & 63;
+    uint32_t c = (w > 0 ? (uint32_t)__popcll(bm.b0) : 0) + (w > 1 ? (uint32_t)__popcll(bm.b1) : 0) + (w > 2 ? (uint32_t)__popcll(bm.b2) : 0);
+    if (b) c += (uint32_t)__popcll(bm.word(w) & ((1ull << b) - 1));
     return c;
 }
-__device__ __forceinline__ uint32_t bm_select(const uint64_t bm[4], uint32_t k) {  // position of the k-th set bit
+__device__ __forceinline__ uint32_t bm_select(const Bits256& bm, uint32_t k) {  // position of the k-th set bit
     for (uint32_t w = 0; w < 4; w++) {
-        uint32_t c = (uint32_t)__popcll(bm[w]);
+        uint64_t x = bm.word(w);
+        uint32_t c = (uint32_t)__popcll(x);
         if (k < c) {
-            uint64_t x = bm[w];
             for (uint32_t j = 0; j < k; j++) x &= x - 1;
             return w * 64 + (uint32_t)(__ffsll((long long)x) - 1);
         }
@@ -334,10 +344,11 @@ __device__ __forceinline__ void hamt_node_lookup(Rd& r, int vkind, uint32_t idx,
     uint32_t blen;
     uint32_t boff = rd_bytes(r, blen);
     if (!r.err && blen > 32) rd_fail(r, CE_HAMT);
-    uint64_t bf[4] = {0, 0, 0, 0};  // bf bit i ↔ child i; big-endian byte string, right aligned
-    if (!r.err) for (uint32_t i = 0; i < blen; i++) { uint32_t bytepos = blen - 1 - i; bf[i >> 3] |= (uint64_t)r.p[boff + bytepos] << (8 * (i & 7)); }
+    Bits256 bf;  // bf bit i ↔ child i; big-endian byte string, right aligned
+    bf.clear();
+    if (!r.err) for (uint32_t i = 0; i < blen; i++) bf.or_byte(i, r.p[boff + (blen - 1 - i)]);
     uint32_t np = rd_array(r);
-    uint32_t pc = (uint32_t)(__popcll(bf[0]) + __popcll(bf[1]) + __popcll(bf[2]) + __popcll(bf[3]));
+    uint32_t pc = bf.popc();
     bool present = bm_test(bf, idx);
     uint32_t want = present ? bm_rank(bf, idx) : 0xffffffffu;
     for (uint32_t k = 0; k < np && !r.err; k++) {

@@ -124,6 +124,10 @@ static bool parse_prefix(const uint8_t* p, uint64_t key[4]) {
     return pos == 6 && key[3] == 32;
 }
 
+static void upload_view(Store* s) {
+    if (!s->view_dev.p) s->view_dev.alloc(1);
+    IPCFP_CUDA(cudaMemcpyAsync(s->view_dev.p, &s->view, sizeof(StoreView), cudaMemcpyHostToDevice, s->stream));
+}
 static void fill_view(Store* s) {
     StoreView& v = s->view;
     v.blob = s->arena.p + 16;
@@ -251,6 +255,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
         IPCFP_CUDA(cudaStreamSynchronize(st));
         s->first_bad = s->host_words.p[0];  // reported by the C ABI as IPCFP_ERR_CID_MISMATCH (handle stays valid)
     }
+    upload_view(s.get());
     IPCFP_CUDA(cudaStreamSynchronize(st));
     return s.release();
 }
