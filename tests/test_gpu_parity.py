@@ -144,3 +144,229 @@ def test_bundle_parity(api, oracle_mod, ts3_small):
     for g, e in zip(got.events, exp.events):
         assert_event_results_equal(g, e)
     assert_witness_equal(got.witness, exp.witness)
+
+
+# ------------------------------------------------------------------ golden fixtures (independent Python oracle)
+def test_engine_matches_golden(api):
+    from tests import golden_util
+    z, ts, s = golden_util.load()
+    r = api.BlockStore.from_tipset(ts, verify_cids=True).generate_event_proof(ts, A.make_event_spec(ts.event_signature, ts.topic1, None))
+    golden_util.check_event_result(z, r)
+    specs = [(int(a), z["s_slot"][k].tobytes()) for k, a in enumerate(z["s_actor"])]
+    golden_util.check_storage_result(z, api.BlockStore.from_tipset(s, verify_cids=True).generate_storage_proofs(s, specs))
+    off = 0
+    msgs = []
+    for n in z["kat_lens"]:
+        msgs.append(z["kat_msgs"][off:off + int(n)].tobytes())
+        off += int(n)
+    assert api.blake2b256_batch(msgs) == [x.tobytes() for x in z["kat_blake2b"]]
+    assert api.sha256_batch(msgs) == [x.tobytes() for x in z["kat_sha256"]]
+    assert api.keccak256_batch(msgs) == [x.tobytes() for x in z["kat_keccak"]]
+
+
+# ------------------------------------------------------------------ reference semantics / error parity
+def _both(api, oracle_mod, ts, spec, flags=0):
+    """Runs oracle and engine; returns ('ok', result) or ('err', status, index) for each."""
+    out = []
+    for mk in (lambda: oracle_mod.Store.from_tipset(ts), lambda: api.BlockStore.from_tipset(ts)):
+        try:
+            out.append(("ok", mk().generate_event_proof(ts, spec, flags)))
+        except A.IpcfpError as e:
+            out.append(("err", e.status, e.index))
+    return out
+
+
+def test_extract_evm_log_traps_gpu(api, oracle_mod, synth_mod):
+    from tests.test_oracle_cpu import _custom_events_tipset
+    from oracle import pyoracle as P
+    t0 = P.keccak256(b"NewTopDownMessage(bytes32,uint256)")
+    t1 = P.ascii_to_bytes32("calib-subnet-1")
+    other = bytes(32)
+    E = lambda k, v, fl=3, codec=0x55: [fl, k, codec, v]  # noqa: E731
+    events = [
+        [1001, [E("t1", other), E("t2", t1), E("t1", t0)]],
+        [1001, [E("t1", t0), E("t1", other), E("t2", t1)]],
+        [1001, [E("topics", t0 + t1), E("t1", other), E("data", b"xy")]],
+        [1001, [E("topics", (t0 + t1)[:63]), E("t1", t0), E("t2", t1)]],
+        [1001, [E("t1", t0), E("t2", t1), E("t3", b"short")]],
+        [1001, [E("t1", t0), E("t2", t1), E("t4", b"short")]],
+        [1001, [E("t2", t1), E("d", b"")]],
+        [1001, [E("t1", t0)]],
+        [1002, [E("t1", t0), E("t2", t1)]],
+        [1001, [E("t1", t0), E("t2", t1), E("t3", other), E("t4", other), E("d", bytes(range(40)))]],
+        [1001, [E("t1", t0, fl=300), E("t2", t1, codec=0x71), E("d", bytes(300))]],                 # wide flags / other codec / 2-byte length
+        [2 ** 40 + 1001, [E("t1", t0), E("t2", t1)]],                                               # 8-byte emitter
+        [1001, [E("t1", t0), E("other-key-é", b"zz"), E("t2", t1), E("topic", b""), E("dat", b"")]],  # unknown / non-ASCII keys
+        [1001, []],
+        [1001, [E("topics", t0 + t1 + other * 5), E("data", bytes(70))]],                           # 7 topics (Case A may exceed 4)
+        [1001, [E("topics", b"")]],                                                                  # Case A, zero topics → Some but no match
+    ]
+    ts = _custom_events_tipset(synth_mod, events)
+    spec = A.make_event_spec("NewTopDownMessage(bytes32,uint256)", "calib-subnet-1", 1001)
+    o, g = _both(api, oracle_mod, ts, spec)
+    assert o[0] == g[0] == "ok"
+    assert_event_results_equal(g[1], o[1])
+    assert [p.event_index for p in g[1].proofs] == [0, 2, 5, 9, 10, 12, 14]
+    assert len(g[1].proofs[6].topics) == 7
+    # no actor filter: the wrong-emitter and huge-emitter events match too
+    spec2 = A.make_event_spec("NewTopDownMessage(bytes32,uint256)", "calib-subnet-1", None)
+    o, g = _both(api, oracle_mod, ts, spec2)
+    assert_event_results_equal(g[1], o[1])
+    assert [p.event_index for p in g[1].proofs] == [0, 2, 5, 8, 9, 10, 11, 12, 14]
+    assert g[1].proofs[6].emitter == 2 ** 40 + 1001
+
+
+def test_error_parity(api, oracle_mod, synth_mod, ts1):
+    import cbor2
+    from tests.test_oracle_cpu import _patched
+    from tests.util import EditedTipset
+    spec = spec_of(ts1)
+    d = ts1.as_dict()
+    cases = []
+    # receipts without events root are skipped
+    has = ts1.has_events_root.copy()
+    has[::3] = 0
+    cases.append(EditedTipset(ts1, has_events_root=has))
+    # missing events block / missing receipts-AMT leaf / missing message-AMT node / missing TxMeta / missing parent header
+    def without(cid):
+        keep = [i for i in range(ts1.n_blocks) if bytes(ts1.cids[i]) != bytes(cid)]
+        return EditedTipset(ts1, cids=ts1.cids[keep], offsets=ts1.offsets[keep], lengths=ts1.lengths[keep], n_blocks=len(keep))
+    cases.append(without(ts1.events_roots[5]))
+    rr = cbor2.loads(d[bytes(ts1.receipts_root)])
+    cases.append(without(rr[2][1][1].value[1:]))                      # a receipts-AMT leaf on some matching path or not
+    tm = cbor2.loads(d[bytes(ts1.parent_txmeta_cids[0])])
+    bls_root = cbor2.loads(d[tm[0].value[1:]])
+    cases.append(without(bls_root[2][1][0].value[1:]))                 # first child of the BLS message AMT
+    cases.append(without(ts1.parent_txmeta_cids[1]))
+    cases.append(without(ts1.parent_cids[0]))                          # base witness block missing → materialize error
+    cases.append(without(ts1.receipts_root))
+    # malformed blocks (same CID, different bytes: the engine does not re-hash unless IPCFP_STORE_VERIFY_CIDS is set)
+    ev = d[bytes(ts1.events_roots[9])]
+    for bad in (ev + b"\x00", ev[:-1], ev[:1] + b"\x06" + ev[2:], ev[:5] + b"\x45\xff\x00\x00\x00\x00" + ev[10:], b"\xa0", b"",
+                ev.replace(b"\x62t1", b"\x62t\xff", 1), ev.replace(b"\x18\x55\x58\x20", b"\x18\x17\x58\x20", 1),
+                ev.replace(b"\x19\x03", b"\x1a\x00\x00\x03", 1)):
+        cases.append(_patched(ts1, ts1.events_roots[9], bad))
+    leaf_cid = rr[2][1][0].value[1:]
+    leaf = d[leaf_cid]
+    cases.append(_patched(ts1, leaf_cid, leaf[:-1]))
+    cases.append(_patched(ts1, leaf_cid, leaf.replace(b"\x84\x00\x40", b"\x84\x20\x40", 1)))   # negative exit code
+    cases.append(_patched(ts1, ts1.parent_txmeta_cids[0], cbor2.dumps([tm[0]])))               # TxMeta with one element
+    # execution order shorter than the receipts list
+    cases.append(EditedTipset(ts1, parent_cids=ts1.parent_cids[:1], parent_txmeta_cids=ts1.parent_txmeta_cids[:1], n_parents=1))
+    seen_err = 0
+    for k, ts in enumerate(cases):
+        o, g = _both(api, oracle_mod, ts, spec)
+        assert o[0] == g[0], (k, o, g)
+        if o[0] == "ok":
+            assert_event_results_equal(g[1], o[1])
+        else:
+            seen_err += 1
+            assert o[1:] == g[1:], (k, o, g)
+    assert seen_err >= 15
+
+
+def test_receipt_missing_from_amt_is_skipped(api, oracle_mod, synth_mod):
+    """events/generator.rs:249-251: r_amt.get(i) == None ⇒ `continue` (no proof, no events recording)."""
+    import cbor2
+    from oracle import pyoracle as P
+    from tests.util import EditedTipset
+    ts = synth_mod.Tipset(synth_mod.default_params(seed=21, n_receipts=40, events_per_receipt=4, match_ppm=400000, n_parents=1, dup_msgs=0))
+    d = ts.as_dict()
+    height, count, node = cbor2.loads(d[bytes(ts.receipts_root)])
+    # drop the last leaf (receipts 32..39) from the receipts AMT root
+    bmap, links, vals = node
+    node2 = [bytes([bmap[0] & 0x0f]), links[:4], vals]
+    root_b = cbor2.dumps([height, count, node2])
+    new_root = P.cid_of(root_b)
+    hdr = cbor2.loads(d[bytes(ts.child_cid)])
+    hdr[9] = cbor2.CBORTag(42, b"\x00" + new_root)
+    hdr_b = cbor2.dumps(hdr)
+    blob = bytearray(ts.blob.tobytes())
+    offs, lens, cids = list(ts.offsets), list(ts.lengths), [ts.cids]
+    for c, b in ((new_root, root_b), (P.cid_of(hdr_b), hdr_b)):
+        while len(blob) % 16:
+            blob.append(0)
+        offs.append(len(blob)); lens.append(len(b)); blob += b
+        cids.append(np.frombuffer(c, dtype=np.uint8).reshape(1, 38))
+    blob += bytes(32)
+    e = EditedTipset(ts, cids=np.concatenate(cids), offsets=np.array(offs, dtype=np.uint64), lengths=np.array(lens, dtype=np.uint32),
+                     blob=np.frombuffer(bytes(blob), dtype=np.uint8), n_blocks=len(lens), receipts_root=np.frombuffer(new_root, dtype=np.uint8),
+                     child_cid=np.frombuffer(P.cid_of(hdr_b), dtype=np.uint8))
+    o, g = _both(api, oracle_mod, e, spec_of(ts))
+    assert o[0] == g[0] == "ok"
+    assert any(i >= 32 for i in o[1].matching.tolist()) and all(p.exec_index < 32 for p in o[1].proofs)
+    assert g[1].matching.tolist() == o[1].matching.tolist()
+    assert [p.key() for p in g[1].proofs] == [p.key() for p in o[1].proofs]
+    assert np.array_equal(g[1].witness.cids, o[1].witness.cids)
+
+
+def test_storage_error_parity(api, oracle_mod, ts3_small):
+    from tests.util import EditedTipset
+    ts = ts3_small
+    slot = api.calculate_storage_slot("calib-subnet-1", 0)
+
+    def run(t, specs):
+        out = []
+        for mk in (lambda: oracle_mod.Store.from_tipset(t), lambda: api.BlockStore.from_tipset(t)):
+            try:
+                r = mk().generate_storage_proofs(t, specs)
+                out.append(("ok", [vars(p) for p in r.proofs]))
+            except A.IpcfpError as e:
+                out.append(("err", e.status, e.index))
+        return out
+    o, g = run(ts, [(1001, slot), (424242, slot)])
+    assert o == g == [("err", A.ERR_ACTOR_NOT_FOUND, 1)] * 2 or (o == g and o[0] == "err")
+    wrong = EditedTipset(ts, parent_state_root=ts.child_cid)
+    o, g = run(wrong, [(1001, slot)])
+    assert o == g and o[0] == "err" and o[1] == A.ERR_STATE_ROOT_MISMATCH
+    keep = [i for i in range(ts.n_blocks) if bytes(ts.cids[i]) != bytes(ts.storage_root)]
+    e = EditedTipset(ts, cids=ts.cids[keep], offsets=ts.offsets[keep], lengths=ts.lengths[keep], n_blocks=len(keep))
+    o, g = run(e, [(1003, slot), (1001, slot)])
+    assert o == g and o[0] == "err" and o[1:] == (A.ERR_MISSING_BLOCK, 1)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+def test_full_size_config4(api, oracle_mod, synth_mod):
+    """1 M receipts x 8 events, 0.1 % match, AMT bit widths 3/5: bit-exact vs the oracle + size-independent properties."""
+    ts = synth_mod.Tipset(synth_mod.config_params(4))
+    spec = spec_of(ts)
+    store = api.BlockStore.from_tipset(ts, verify_cids=True)
+    d, keep = A.make_tipset_desc(ts)
+    got = store.generate_event_proof(ts, spec)
+    assert got.matching.tolist() == ts.selected.tolist()                # ground truth by construction
+    assert got.n_exec == ts.n_receipts
+    # witness: sorted, unique, every block hashes to its CID, union contains every recorded kind of block
+    w = got.witness
+    digs = [bytes(c[6:]) for c in w.cids]
+    assert digs == sorted(set(digs))
+    for i in np.random.default_rng(0).integers(0, w.n_blocks, 2000):
+        assert hashlib.blake2b(w.block(int(i)), digest_size=32).digest() == digs[int(i)]
+    # closed loop: the witness verifies every proof (restated events/verifier.rs)
+    assert all(oracle_mod.verify_event_proofs(w, ts, got, spec))
+    # bit-exact against the CPU oracle (pass 1 on 8 threads)
+    exp = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec, threads=8)
+    assert got.matching.tolist() == exp.matching.tolist()
+    assert [p.key() for p in got.proofs] == [p.key() for p in exp.proofs]
+    assert np.array_equal(w.cids, exp.witness.cids) and np.array_equal(w.lengths, exp.witness.lengths)
+    sample = np.random.default_rng(1).integers(0, w.n_blocks, 3000)
+    assert all(w.block(int(i)) == exp.witness.block(int(i)) for i in sample)
+    # idempotence: a second scan of the resident store gives the same answer
+    again = store.generate_event_proof(ts, spec)
+    assert np.array_equal(again.witness.cids, w.cids) and [p.key() for p in again.proofs] == [p.key() for p in got.proofs]
+
+
+def test_full_size_config3(api, oracle_mod, synth_mod):
+    """1 M-slot storage HAMT, 1 k lookups (900 present + 100 absent)."""
+    ts = synth_mod.Tipset(synth_mod.config_params(3))
+    n = int(ts.params.hamt_entries)
+    ks = np.random.default_rng(9).integers(0, n, 900).tolist()
+    keys = [ts.storage_entry(k)[0] for k in ks] + [ts.storage_absent_key(k) for k in range(100)]
+    slots = np.frombuffer(b"".join(api.compute_mapping_slots(keys, [0] * len(keys))), dtype=np.uint8)
+    got = api.BlockStore.from_tipset(ts, verify_cids=True).read_storage_slots(ts.storage_root, slots)
+    exp = oracle_mod.Store.from_tipset(ts).read_storage_slots(ts.storage_root, slots)
+    assert np.array_equal(got.found, exp.found) and np.array_equal(got.raw_len, exp.raw_len) and np.array_equal(got.values, exp.values)
+    assert_witness_equal(got.witness, exp.witness)
+    assert got.found[:900].all() and not got.found[900:].any()
+    for i, k in enumerate(ks):
+        v = ts.storage_entry(k)[1]
+        assert bytes(got.values[i][32 - len(v):]) == v

@@ -1,0 +1,319 @@
+"""CPU tests: the oracle against golden vectors / the independent Python oracle / the restated verifiers,
+host logic, and the C-ABI library surface (no GPU compute)."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import cbor2
+import numpy as np
+import pytest
+
+from ipc_filecoin_proofs_b200 import _abi as A
+from tests import golden_util
+from tests.util import EditedTipset, ShuffledTipset, assert_event_results_equal, dict_of, spec_of
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ hashes
+def test_hash_known_answers(oracle_mod, synth_mod):
+    from oracle import pyoracle as P
+    assert oracle_mod.blake2b256(b"").hex() == "0e5751c026e543b2e8ab2eb06099daa1d1e5df47778f7787faab45cdf12fe3a8"
+    assert oracle_mod.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert oracle_mod.keccak256(b"Transfer(address,address,uint256)").hex() == "ddf252ad1be2c89b69c2b068fc378daa952ba7f163c4a11628f55a4df523b3ef"
+    assert oracle_mod.sha256(b"").hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 55, 56, 63, 64, 65, 111, 112, 127, 128, 129, 135, 136, 137, 255, 256, 257, 1028, 4096]:
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle_mod.blake2b256(m) == hashlib.blake2b(m, digest_size=32).digest() == synth_mod.blake2b256(m)
+        assert oracle_mod.sha256(m) == hashlib.sha256(m).digest() == synth_mod.sha256(m)
+        assert oracle_mod.keccak256(m) == P.keccak256(m) == synth_mod.keccak256(m)
+
+
+def test_golden_kats(oracle_mod):
+    z, _, _ = golden_util.load()
+    off = 0
+    for k, n in enumerate(z["kat_lens"]):
+        m = z["kat_msgs"][off:off + int(n)].tobytes()
+        off += int(n)
+        assert oracle_mod.blake2b256(m) == z["kat_blake2b"][k].tobytes()
+        assert oracle_mod.sha256(m) == z["kat_sha256"][k].tobytes()
+        assert oracle_mod.keccak256(m) == z["kat_keccak"][k].tobytes()
+
+
+def test_topic_constants(oracle_mod):
+    # the reference's demo spec (src/main.rs:60-64,38): NewTopDownMessage(bytes32,uint256), "calib-subnet-1", slot index 0
+    t0 = oracle_mod.keccak256(b"NewTopDownMessage(bytes32,uint256)")
+    assert len(t0) == 32
+    key = b"calib-subnet-1" + bytes(18)
+    assert oracle_mod.compute_mapping_slot(key, 0) == oracle_mod.keccak256(key + bytes(32))
+    assert oracle_mod.compute_mapping_slot(key, 7) == oracle_mod.keccak256(key + (7).to_bytes(32, "big"))
+
+
+# ------------------------------------------------------------------ synthetic data is well-formed DAG-CBOR with valid CIDs
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_synth_blocks_roundtrip_cbor2(synth_mod, cfg):
+    ts = synth_mod.Tipset(synth_mod.config_params(cfg))
+    for i in range(ts.n_blocks):
+        b = ts.block(i)
+        assert cbor2.dumps(cbor2.loads(b)) == b                       # minimal, definite-length encoding
+        assert hashlib.blake2b(b, digest_size=32).digest() == bytes(ts.cids[i][6:])
+        assert bytes(ts.cids[i][:6]) == bytes([0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20])
+        assert int(ts.offsets[i]) % 16 == 0
+    # shapes from SURVEY.md §8(a)
+    import collections
+    d = ts.as_dict()
+    lens = collections.Counter(len(d[bytes(ts.events_roots[i])]) for i in range(int(ts.n_receipts)))
+    assert lens.most_common(1)[0][0] == 1028   # events-AMT v3 bw5 root with 8 x 127-byte StampedEvents
+    assert oracle_mod_verify(ts)
+
+
+def oracle_mod_verify(ts):
+    import oracle
+    return oracle.Store.from_tipset(ts).verify_cids(threads=2) is None
+
+
+# ------------------------------------------------------------------ oracle vs golden (independent Python oracle)
+def test_oracle_matches_golden_events(oracle_mod):
+    z, ts, _ = golden_util.load()
+    st = oracle_mod.Store.from_tipset(ts)
+    r = st.generate_event_proof(ts, A.make_event_spec(ts.event_signature, ts.topic1, None))
+    golden_util.check_event_result(z, r)
+
+
+def test_oracle_matches_golden_storage(oracle_mod):
+    z, _, s = golden_util.load()
+    st = oracle_mod.Store.from_tipset(s)
+    specs = [(int(a), z["s_slot"][k].tobytes()) for k, a in enumerate(z["s_actor"])]
+    golden_util.check_storage_result(z, st.generate_storage_proofs(s, specs))
+
+
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_oracle_vs_python_oracle(oracle_mod, synth_mod, cfg):
+    from oracle import pyoracle as P
+    ts = synth_mod.Tipset(synth_mod.config_params(cfg))
+    r = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec_of(ts))
+    pr = P.generate_event_proof(ts.as_dict(), ts, ts.event_signature, ts.topic1, ts.actor_filter)
+    assert pr["matching"] == r.matching.tolist() == ts.selected.tolist()
+    assert [bytes(c) for c in r.witness.cids] == pr["witness"]
+    assert [(p.exec_index, p.event_index, p.emitter, tuple(p.topics), p.data, p.message_cid) for p in r.proofs] == pr["proofs"]
+    assert r.n_exec == len(pr["exec_order"])
+
+
+def test_oracle_threads_and_order_independent(oracle_mod, ts2):
+    st = oracle_mod.Store.from_tipset(ts2)
+    a = st.generate_event_proof(ts2, spec_of(ts2), threads=1)
+    b = st.generate_event_proof(ts2, spec_of(ts2), threads=4)
+    assert_event_results_equal(a, b)
+    sh = ShuffledTipset(ts2, seed=11, misalign=True)
+    c = oracle_mod.Store.from_tipset(sh).generate_event_proof(sh, spec_of(sh))
+    assert_event_results_equal(a, c)
+
+
+# ------------------------------------------------------------------ generate → verify closed loop, minimality
+def test_verify_and_minimality(oracle_mod, ts1):
+    st = oracle_mod.Store.from_tipset(ts1)
+    spec = spec_of(ts1)
+    r = st.generate_event_proof(ts1, spec)
+    assert len(r.proofs) > 0 and all(oracle_mod.verify_event_proofs(r.witness, ts1, r, spec))
+    # dropping ANY witness block must break verification of at least one proof (or raise "missing")
+    w = r.witness
+    for drop in range(w.n_blocks):
+        keep = [i for i in range(w.n_blocks) if i != drop]
+        w2 = A.WitnessPy(w.cids[keep], w.offsets[keep], w.lengths[keep], w.blob)
+        try:
+            ok = oracle_mod.verify_event_proofs(w2, ts1, r, spec)
+        except A.IpcfpError:
+            continue
+        assert not all(ok), f"witness block {drop} is not needed"
+    # a tampered claim must fail
+    r.raw_proofs = r.raw_proofs.copy()
+    r.raw_proofs[8] ^= 1  # event_index of proof 0
+    assert not oracle_mod.verify_event_proofs(w, ts1, r, spec)[0]
+
+
+def test_storage_verify(oracle_mod, ts3_small):
+    ts = ts3_small
+    st = oracle_mod.Store.from_tipset(ts)
+    n = int(ts.params.hamt_entries)
+    slots = [oracle_mod.compute_mapping_slot(ts.storage_entry(k)[0], 0) for k in (0, 5, n)] + [oracle_mod.compute_mapping_slot(ts.storage_absent_key(3), 0)]
+    specs = [(a, s) for a in (1001, 1002, 1003, 1004, 1005, 1006) for s in slots]
+    r = st.generate_storage_proofs(ts, specs)
+    assert all(oracle_mod.verify_storage_proofs(r.witness, ts, r))
+    v = ts.storage_entry(5)[1]
+    assert r.proofs[1].found and r.proofs[1].value == bytes(32 - len(v)) + v
+    assert not r.proofs[3].found and r.proofs[3].value == bytes(32)
+    assert r.proofs[2].value == bytes(31) + b"\x0f"       # the calib-subnet-1 nonce entry
+    # inline small maps only hold entries 0..2: entry 5 is absent there
+    assert not r.proofs[2 * 4 + 1].found
+    with pytest.raises(A.IpcfpError) as ei:
+        st.generate_storage_proofs(ts, [(999999, slots[0])])
+    assert ei.value.status == A.ERR_ACTOR_NOT_FOUND
+
+
+# ------------------------------------------------------------------ reference semantics (SURVEY Appendix B traps)
+def _patched(ts, cid, new_bytes):
+    """Tipset whose block `cid` is replaced by new_bytes (same CID: the engine does not re-hash unless asked)."""
+    idx = [i for i in range(ts.n_blocks) if bytes(ts.cids[i]) == bytes(cid)][0]
+    blob = np.concatenate([ts.blob, np.frombuffer(bytes(new_bytes) + bytes(32), dtype=np.uint8)])
+    offs = ts.offsets.copy()
+    lens = ts.lengths.copy()
+    offs[idx] = len(ts.blob)
+    lens[idx] = len(new_bytes)
+    return EditedTipset(ts, blob=blob, offsets=offs, lengths=lens)
+
+
+def test_error_semantics(oracle_mod, ts1):
+    spec = spec_of(ts1)
+    base = oracle_mod.Store.from_tipset(ts1).generate_event_proof(ts1, spec)
+    # B-1: a receipt without events root is skipped entirely
+    has = ts1.has_events_root.copy()
+    victim = int(base.matching[0])
+    has[victim] = 0
+    r = oracle_mod.Store.from_tipset(ts1).generate_event_proof(EditedTipset(ts1, has_events_root=has), spec)
+    assert victim not in r.matching.tolist() and len(r.matching) == len(base.matching) - 1
+    # missing events-AMT block → MISSING_BLOCK at that receipt
+    keep = [i for i in range(ts1.n_blocks) if bytes(ts1.cids[i]) != bytes(ts1.events_roots[5])]
+    e = EditedTipset(ts1, cids=ts1.cids[keep], offsets=ts1.offsets[keep], lengths=ts1.lengths[keep], n_blocks=len(keep))
+    with pytest.raises(A.IpcfpError) as ei:
+        oracle_mod.Store.from_tipset(e).generate_event_proof(e, spec)
+    assert (ei.value.status, ei.value.index) == (A.ERR_MISSING_BLOCK, 5)
+    # trailing byte after a node → DECODE at that receipt (strict decoder)
+    blk = ts1.as_dict()[bytes(ts1.events_roots[9])]
+    p = _patched(ts1, ts1.events_roots[9], blk + b"\x00")
+    with pytest.raises(A.IpcfpError) as ei:
+        oracle_mod.Store.from_tipset(p).generate_event_proof(p, spec)
+    assert (ei.value.status, ei.value.index) == (A.ERR_DECODE, 9)
+    # B-4: execution order shorter than a matching index → MISSING_EXEC (checked before the receipt get)
+    # (drop the last parent block's TxMeta from the descriptor: fewer messages than receipts)
+    e2 = EditedTipset(ts1, parent_cids=ts1.parent_cids[:1], parent_txmeta_cids=ts1.parent_txmeta_cids[:1], n_parents=1)
+    with pytest.raises(A.IpcfpError) as ei:
+        oracle_mod.Store.from_tipset(e2).generate_event_proof(e2, spec)
+    assert ei.value.status == A.ERR_MISSING_EXEC and ei.value.index >= 32
+
+
+def test_extract_evm_log_traps(oracle_mod, synth_mod):
+    """Appendix B-6: duplicate keys (last wins), `topics` beats t1, bad tK length voids the log, gaps stop the walk."""
+    from oracle import pyoracle as P
+    t0 = P.keccak256(b"NewTopDownMessage(bytes32,uint256)")
+    t1 = P.ascii_to_bytes32("calib-subnet-1")
+    other = bytes(32)
+    E = lambda k, v: [3, k, 0x55, v]  # noqa: E731
+    events = [
+        [1001, [E("t1", other), E("t2", t1), E("t1", t0)]],                 # 0 duplicate t1: last wins → match
+        [1001, [E("t1", t0), E("t1", other), E("t2", t1)]],                 # 1 last t1 is wrong → no match
+        [1001, [E("topics", t0 + t1), E("t1", other), E("data", b"xy")]],    # 2 Case A wins → match
+        [1001, [E("topics", (t0 + t1)[:63]), E("t1", t0), E("t2", t1)]],     # 3 Case A bad length → None
+        [1001, [E("t1", t0), E("t2", t1), E("t3", b"short")]],               # 4 bad t3 voids the whole log
+        [1001, [E("t1", t0), E("t2", t1), E("t4", b"short")]],               # 5 t3 missing → t4 ignored → match
+        [1001, [E("t2", t1), E("d", b"")]],                                   # 6 no t1 → None
+        [1001, [E("t1", t0)]],                                                # 7 one topic only → no match
+        [1002, [E("t1", t0), E("t2", t1)]],                                   # 8 wrong emitter
+        [1001, [E("t1", t0), E("t2", t1), E("t3", other), E("t4", other), E("d", bytes(range(40)))]],  # 9 four topics + data → match
+    ]
+    ts = _custom_events_tipset(synth_mod, events)
+    r = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, A.make_event_spec("NewTopDownMessage(bytes32,uint256)", "calib-subnet-1", 1001))
+    assert [p.event_index for p in r.proofs] == [0, 2, 5, 9]
+    assert r.proofs[1].data == b"xy" and len(r.proofs[3].topics) == 4 and r.proofs[3].data == bytes(range(40))
+    pr = P.generate_event_proof(dict_of(ts), ts, "NewTopDownMessage(bytes32,uint256)", "calib-subnet-1", 1001)
+    assert [(p.exec_index, p.event_index, p.emitter, tuple(p.topics), p.data, p.message_cid) for p in r.proofs] == pr["proofs"]
+
+
+def _custom_events_tipset(synth_mod, events, n_receipts=9, target=4):
+    """A small synthetic tipset whose receipt `target` gets a hand-made events AMT (bit width 5, one node)."""
+    from oracle import pyoracle as P
+    ts = synth_mod.Tipset(synth_mod.default_params(seed=5, n_receipts=n_receipts, events_per_receipt=2, match_ppm=0, n_parents=1, dup_msgs=0))
+    n = len(events)
+    bmap = bytearray(4)
+    for i in range(n):
+        bmap[i // 8] |= 1 << (i % 8)
+    root = cbor2.dumps([5, 0, n, [bytes(bmap), [], events]])
+    cid = P.cid_of(root)
+    # new events root for `target` → the receipts AMT leaf must change too; rebuild leaf + root by hand
+    d = ts.as_dict()
+    rr = cbor2.loads(d[bytes(ts.receipts_root)])
+    height, count, node = rr
+    assert height == 1 and count == n_receipts
+    leaf_links = node[1]
+    leaf0 = cbor2.loads(d[P._link(leaf_links[target // 8])])
+    leaf0[2][target % 8][3] = cbor2.CBORTag(42, b"\x00" + cid)
+    leaf0_b = cbor2.dumps(leaf0)
+    leaf_links[target // 8] = cbor2.CBORTag(42, b"\x00" + P.cid_of(leaf0_b))
+    root_b = cbor2.dumps([height, count, node])
+    new_root_cid = P.cid_of(root_b)
+    # child header points at the receipts root: patch field 9 and re-hash the header
+    hdr = cbor2.loads(d[bytes(ts.child_cid)])
+    hdr[9] = cbor2.CBORTag(42, b"\x00" + new_root_cid)
+    hdr_b = cbor2.dumps(hdr)
+    extra = [(cid, root), (P.cid_of(leaf0_b), leaf0_b), (new_root_cid, root_b), (P.cid_of(hdr_b), hdr_b)]
+    blob = bytearray(ts.blob.tobytes())
+    cids, offs, lens = [ts.cids], list(ts.offsets), list(ts.lengths)
+    for c, b in extra:
+        while len(blob) % 16:
+            blob.append(0)
+        offs.append(len(blob))
+        lens.append(len(b))
+        blob += b
+        cids.append(np.frombuffer(c, dtype=np.uint8).reshape(1, 38))
+    blob += bytes(32)
+    roots = ts.events_roots.copy()
+    roots[target] = np.frombuffer(cid, dtype=np.uint8)
+    return EditedTipset(ts, cids=np.concatenate(cids), offsets=np.array(offs, dtype=np.uint64), lengths=np.array(lens, dtype=np.uint32),
+                        blob=np.frombuffer(bytes(blob), dtype=np.uint8), n_blocks=len(lens), events_roots=roots,
+                        receipts_root=np.frombuffer(new_root_cid, dtype=np.uint8), child_cid=np.frombuffer(P.cid_of(hdr_b), dtype=np.uint8))
+
+
+def test_cid_ordering(oracle_mod):
+    from oracle import pyoracle as P
+    rng = np.random.default_rng(3)
+    cids = []
+    for k in range(200):
+        prefix = [bytes([1, 0x71, 0xa0, 0xe4, 2, 0x20]), bytes([1, 0x55, 0xa0, 0xe4, 2, 0x20]), bytes([1, 0x71, 0x92, 0xe4, 2, 0x20])][k % 3]
+        cids.append(prefix + rng.integers(0, 256, 32, dtype=np.uint8).tobytes())
+    cids += cids[:10]
+    got = oracle_mod.sort_unique_cids(np.frombuffer(b"".join(cids), dtype=np.uint8))
+    exp = sorted(set(cids), key=P.cid_sort_key)
+    assert [bytes(c) for c in got] == exp
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def test_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "ipcfp.h")).read()
+    declared = set(re.findall(r"\b(ipcfp_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ipcfp_store", "ipcfp_tipset"}
+    from ipc_filecoin_proofs_b200 import api
+    L = api.lib()
+    missing = [name for name in sorted(declared) if not hasattr(L, name)]
+    assert not missing, missing
+    assert set(api.EXPORTS) <= declared
+
+
+def test_no_cpu_fallback(api, ts1):
+    """Without a CUDA device every compute entry point fails loudly (IPCFP_ERR_NO_DEVICE)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(A.IpcfpError) as ei:
+        api.BlockStore.from_tipset(ts1)
+    assert ei.value.status == A.ERR_NO_DEVICE
+    with pytest.raises(A.IpcfpError) as ei:
+        api.keccak256_batch([b"abc"])
+    assert ei.value.status == A.ERR_NO_DEVICE
+    assert api.lib().ipcfp_version().decode().startswith("ipcfp-b200")
+
+
+def test_product_does_not_link_oracle():
+    """The product library and package never reference oracle/ or synth/."""
+    import subprocess
+    from ipc_filecoin_proofs_b200 import api
+    out = subprocess.run(["ldd", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "synth" not in out
+    syms = subprocess.run(["nm", "-D", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in syms and "synth_" not in syms
+    pkg = os.path.join(ROOT, "ipc_filecoin_proofs_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/__init__.py", ""), f

@@ -67,3 +67,12 @@ class EditedTipset:
 
     def __getattr__(self, name):
         return getattr(self._ts, name)
+
+
+def dict_of(ts):
+    """cid -> bytes of any tipset-like object, from its flat arrays (first occurrence wins)."""
+    d = {}
+    for i in range(int(ts.n_blocks)):
+        o = int(ts.offsets[i])
+        d.setdefault(bytes(ts.cids[i]), bytes(ts.blob[o:o + int(ts.lengths[i])]))
+    return d
