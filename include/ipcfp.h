@@ -172,6 +172,13 @@ typedef struct ipcfp_event_result {
     float ms_total, ms_pass1, ms_pass2, ms_txamt, ms_witness;
     uint64_t pass1_bytes;             /* algorithmic bytes read by the pass-1 scan kernel       */
     uint64_t pass1_nodes;
+    /* shard mode only (ipcfp_generate_event_proof_shard): this shard's slice of the concatenated message list,
+     * in order, as 40-byte records {digest[32], prefix[6], 0, 0} in DEVICE memory (valid until the result is
+     * freed; free results before destroying the store). proofs[].message_cid is left zero and n_exec is 0:
+     * the execution order spans shards and is resolved by the caller (ipcfp_exec_* helpers). */
+    const void* shard_exec_dev;
+    uint64_t shard_exec_count;
+    uint64_t shard_raw_total;         /* total length of the concatenated message list (all shards) */
 } ipcfp_event_result;
 
 typedef struct ipcfp_storage_proof {
@@ -262,6 +269,22 @@ void ipcfp_bundle_free(ipcfp_bundle* b);
 ipcfp_status ipcfp_generate_event_proof_shard(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_spec* spec,
                                               uint64_t lo, uint64_t hi, uint32_t world_size, uint32_t rank,
                                               uint32_t flags, ipcfp_event_result** out);
+/* Cross-shard execution order (events/utils.rs:56-91, "first seen wins" over ALL message AMTs): a distributed
+ * hash join whose collectives the caller runs between these device helpers. All pointers *_dev are device
+ * memory; an "exec entry" is 48 bytes {record[40], global position u64}.
+ *   1. pos0 = sum of shard_exec_count of lower ranks (all-gather); ipcfp_exec_bucketize routes every record of
+ *      the rank's slice to owner = hash(cid) % world: send_dev = world segments of `cap` entries, counts[world].
+ *   2. all-to-all of counts and segments; ipcfp_exec_dedup returns the global positions that are NOT the first
+ *      occurrence of their CID (any order).
+ *   3. all-gather of the duplicate lists → sorted D on every rank: exec index i ↔ raw position p with
+ *      p = i + |{d ∈ D : d ≤ p}|; n_exec = shard_raw_total − |D|.
+ *   4. ipcfp_exec_fetch writes the records at the requested global positions this rank holds (others untouched). */
+ipcfp_status ipcfp_exec_bucketize(int device, const void* seg_dev, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap,
+                                  void* send_dev, uint64_t* counts /* host, world */);
+ipcfp_status ipcfp_exec_dedup(int device, const void* recv_dev, const uint64_t* counts /* host, world */, uint32_t world, uint64_t cap,
+                              uint64_t* dup_pos_dev, uint64_t cap_out, uint64_t* n_dup);
+ipcfp_status ipcfp_exec_fetch(int device, const void* seg_dev, uint64_t nseg, uint64_t pos0, const uint64_t* req_pos_dev, uint64_t n_req,
+                              void* out_dev /* n_req*40 */);
 /* Device-resident copy of a result's sorted witness CIDs (n*38 bytes) for the collective. */
 ipcfp_status ipcfp_witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap_cids, uint64_t* n);
 /* Merge all-gathered CID lists on the device: gathered = world*cap*38 bytes, counts[world];

@@ -98,6 +98,9 @@ class EventResultC(C.Structure):
         ("ms_witness", C.c_float),
         ("pass1_bytes", C.c_uint64),
         ("pass1_nodes", C.c_uint64),
+        ("shard_exec_dev", C.c_void_p),
+        ("shard_exec_count", C.c_uint64),
+        ("shard_raw_total", C.c_uint64),
     ]
 
 

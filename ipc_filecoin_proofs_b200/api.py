@@ -39,6 +39,8 @@ EXPORTS = [
     "ipcfp_compute_mapping_slots", "ipcfp_generate_event_proof", "ipcfp_event_result_free", "ipcfp_read_storage_slots",
     "ipcfp_slot_result_free", "ipcfp_generate_storage_proofs", "ipcfp_storage_result_free", "ipcfp_generate_proof_bundle",
     "ipcfp_bundle_free", "ipcfp_generate_event_proof_shard", "ipcfp_witness_cids_to_device", "ipcfp_merge_witness_cids",
+    "ipcfp_tipset_upload", "ipcfp_tipset_free", "ipcfp_generate_event_proof_resident", "ipcfp_generate_event_proof_shard_resident",
+    "ipcfp_store_stream", "ipcfp_exec_bucketize", "ipcfp_exec_dedup", "ipcfp_exec_fetch",
 ]
 
 
@@ -92,6 +94,23 @@ def lib():
         L.ipcfp_generate_proof_bundle.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                   C.POINTER(C.POINTER(A.BundleC))]
         L.ipcfp_bundle_free.argtypes = [C.POINTER(A.BundleC)]
+        L.ipcfp_tipset_upload.restype = C.c_int32
+        L.ipcfp_tipset_upload.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.POINTER(C.c_void_p)]
+        L.ipcfp_tipset_free.argtypes = [C.c_void_p]
+        L.ipcfp_generate_event_proof_resident.restype = C.c_int32
+        L.ipcfp_generate_event_proof_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.EventSpec), C.c_uint32,
+                                                          C.POINTER(C.POINTER(A.EventResultC))]
+        L.ipcfp_generate_event_proof_shard_resident.restype = C.c_int32
+        L.ipcfp_generate_event_proof_shard_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.EventSpec), C.c_uint64, C.c_uint64,
+                                                                C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(A.EventResultC))]
+        L.ipcfp_store_stream.restype = C.c_void_p
+        L.ipcfp_store_stream.argtypes = [C.c_void_p]
+        L.ipcfp_exec_bucketize.restype = C.c_int32
+        L.ipcfp_exec_bucketize.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ipcfp_exec_dedup.restype = C.c_int32
+        L.ipcfp_exec_dedup.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.ipcfp_exec_fetch.restype = C.c_int32
+        L.ipcfp_exec_fetch.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ipcfp_witness_cids_to_device.restype = C.c_int32
         L.ipcfp_witness_cids_to_device.argtypes = [C.POINTER(A.EventResultC), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ipcfp_merge_witness_cids.restype = C.c_int32

@@ -314,6 +314,27 @@ void ipcfp_bundle_free(ipcfp_bundle* b) {
     delete box;
 }
 
+ipcfp_status ipcfp_exec_bucketize(int device, const void* seg_dev, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send_dev,
+                                  uint64_t* counts) {
+    return guard([&] {
+        if ((nseg && !seg_dev) || !send_dev || !counts) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        exec_bucketize(device, seg_dev, nseg, pos0, world, cap, send_dev, counts);
+    });
+}
+ipcfp_status ipcfp_exec_dedup(int device, const void* recv_dev, const uint64_t* counts, uint32_t world, uint64_t cap, uint64_t* dup_pos_dev,
+                              uint64_t cap_out, uint64_t* n_dup) {
+    return guard([&] {
+        if (!recv_dev || !counts || !dup_pos_dev || !n_dup) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        exec_dedup(device, recv_dev, counts, world, cap, dup_pos_dev, cap_out, n_dup);
+    });
+}
+ipcfp_status ipcfp_exec_fetch(int device, const void* seg_dev, uint64_t nseg, uint64_t pos0, const uint64_t* req_pos_dev, uint64_t n_req,
+                              void* out_dev) {
+    return guard([&] {
+        if ((nseg && !seg_dev) || (n_req && (!req_pos_dev || !out_dev))) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        exec_fetch(device, seg_dev, nseg, pos0, req_pos_dev, n_req, out_dev);
+    });
+}
 ipcfp_status ipcfp_witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap_cids, uint64_t* n) {
     return guard([&] {
         if (!r || !dev_ptr || !n) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");

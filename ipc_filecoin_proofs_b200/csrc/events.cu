@@ -18,14 +18,14 @@
 #include "hashes.cuh"
 #include "ipld.cuh"
 #include "prims.cuh"
+#include "rawcid.cuh"
 
 namespace ipcfp {
 
 // ------------------------------------------------------------------------------------------ events AMT walk
 enum WalkMode { WALK_ANY = 0, WALK_COUNT = 1, WALK_EMIT = 2 };
 
-// A CID value of a message AMT as five aligned words: w[0..3] digest bytes, w[4] low 48 bits = CID prefix bytes 0..5
-struct RawCid { uint64_t w[5]; };
+
 
 struct EmitCtx {
     ipcfp_event_proof* proofs;   // base for this match
@@ -248,6 +248,7 @@ struct Pass2Args {
     ipcfp_event_proof* proofs;
     uint8_t* blob;
     uint32_t* any_skip;            // set when a matching receipt is absent from the receipts AMT
+    uint32_t resolve_msg;          // 0 in shard mode: execution order is resolved across ranks afterwards
 };
 
 // One thread per matching receipt (events/generator.rs:242-301): exec.get(i), r_amt.get(i) with path
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     uint32_t rel = a.match_rel[t];
     uint64_t i = a.lo + rel;
     // exec.get(i) comes first (:244-246)
-    if (i >= *a.n_exec) { report_error(a.err, ST_PASS2, i, DC_MISSING_EXEC, 0); return; }
+    if (a.resolve_msg && i >= *a.n_exec) { report_error(a.err, ST_PASS2, i, DC_MISSING_EXEC, 0); return; }
     uint32_t detail = 0;
     int got = receipts_get(a.store, a.receipts_root_blk, i, a.wbits, &detail);
     if (got < 0) { report_error(a.err, ST_PASS2, i, (uint32_t)(-got), detail); return; }
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     ec.blob = a.blob;
     ec.blob_off = a.byte_base[rel];
     ec.exec_index = i;
-    ec.msg_cid = a.exec_cids[a.exec_idx[i]];
+    if (a.resolve_msg) ec.msg_cid = a.exec_cids[a.exec_idx[i]]; else ec.msg_cid = RawCid{};
     uint32_t rc = walk_events<WALK_EMIT>(a.store_dev, (uint32_t)root, a.m_dev, a.wbits, wo, &ec, &detail);
     if (rc) report_error(a.err, ST_PASS2, i, rc, detail);
 }
@@ -385,9 +386,24 @@ __global__ void k_setup(SetupArgs a) {
 
 struct Frontier { uint32_t* blk; uint32_t* meta; uint64_t* base; };
 
-__device__ __forceinline__ uint32_t amt_item_count(const StoreView& s, uint32_t blk, uint32_t meta, uint32_t round, uint32_t last_round) {
+// slots (children, or values at level 0) of a node at `base` whose index range intersects [rlo, rhi):
+// the share of the message AMTs a shard walks (all ones when not sharded)
+__device__ __forceinline__ uint32_t slot_mask(uint64_t base, uint32_t level, uint64_t rlo, uint64_t rhi) {
+    uint64_t sub = pow_sat(3, level);
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t sl = 0; sl < 8; sl++) {
+        uint64_t off = sub == ~0ull ? (sl ? ~0ull : 0) : sub * sl;
+        uint64_t cb = base + off < base ? ~0ull : base + off;
+        uint64_t ce = cb + sub < cb ? ~0ull : cb + sub;
+        if (cb < rhi && ce > rlo) m |= 1u << sl;
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t amt_item_count(const StoreView& s, uint32_t blk, uint32_t meta, uint64_t base, uint32_t round, uint32_t last_round,
+                                                   const uint64_t* rlo, const uint64_t* rhi) {
     if (meta == AMT_SENTINEL) return 0;
-    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1;
+    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
     if (level == 0 && round < last_round) return 1;  // parked
     uint32_t len;
     const uint8_t* p = store_block(s, blk, len);
@@ -397,7 +413,7 @@ __device__ __forceinline__ uint32_t amt_item_count(const StoreView& s, uint32_t 
     uint32_t bl;
     uint32_t bo = rd_bytes(r, bl);
     if (r.err || bl != 1) return 0;  // reported by the expand pass
-    if (level != 0 || round == last_round) return (uint32_t)__popc((uint32_t)p[bo]);
+    if (level != 0 || round == last_round) return (uint32_t)__popc((uint32_t)p[bo] & slot_mask(base, level, rlo[amt], rhi[amt]));
     return 0;
 }
 
@@ -412,6 +428,8 @@ struct ExpandArgs {
     Frontier out;              // rounds < last_round
     RawCid* vals;              // last round
     uint32_t cap;
+    const uint64_t* rlo;       // per message AMT: index range this call walks
+    const uint64_t* rhi;
 };
 __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t, uint32_t blk, uint32_t meta, uint64_t base, uint32_t expect) {
     if (meta == AMT_SENTINEL) return;
@@ -433,12 +451,14 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
     amt_node_finish(r, h, nv, level);
     uint64_t eidx = 3ull * (amt >> 1) + 1 + (amt & 1);
     uint32_t produced = 0;
+    const uint32_t smask = slot_mask(base, level, a.rlo[amt], a.rhi[amt]);
     if (r.err) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err);
     else if (h.nl) {
-        for (uint32_t k = 0; k < h.nl && k < expect; k++) {
+        for (uint32_t k = 0; k < h.nl && produced < expect; k++) {
             uint32_t slot = bm_select(h.bm, k);
+            if (!((smask >> slot) & 1)) continue;
             int32_t child = store_lookup(a.store, p + h.links_off + 43 * k + 5);
-            uint64_t d = o + k;
+            uint64_t d = o + produced;
             if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
             else {
                 if (a.record) witness_mark(a.wbits, (uint32_t)child);
@@ -447,13 +467,14 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
             produced++;
         }
     } else if (a.round == a.last_round) {
-        for (uint32_t v = 0; v < nv && v < expect; v++) {
+        for (uint32_t v = 0; v < nv && produced < expect; v++) {
+            if (!((smask >> bm_select(h.bm, v)) & 1)) continue;
             const uint8_t* src = p + vals_off + 43 * v + 5;
             RawCid c;
             c.w[4] = load_u64_any(src) & 0xffffffffffffull;
             Digest dg = load_digest(src + 6);
             c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
-            a.vals[o + v] = c;
+            a.vals[o + produced] = c;
             produced++;
         }
     }
@@ -463,12 +484,12 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
 }
 
 __global__ void __launch_bounds__(128) k_amt_count(StoreView store, Frontier in, const unsigned long long* in_count, uint32_t round, uint32_t last_round,
-                                                   uint32_t cap, uint32_t* counts) {
+                                                   uint32_t cap, uint32_t* counts, const uint64_t* rlo, const uint64_t* rhi) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t cnt = *in_count;
     if (cnt > cap) cnt = cap;
     if (t >= cnt) { counts[t] = 0; return; }   // the grid covers exactly the scanned range
-    counts[t] = amt_item_count(store, in.blk[t], in.meta[t], round, last_round);
+    counts[t] = amt_item_count(store, in.blk[t], in.meta[t], in.base[t], round, last_round, rlo, rhi);
 }
 __global__ void __launch_bounds__(128) k_amt_expand(ExpandArgs a, const uint32_t* counts, unsigned long long* out_count, const unsigned long long* total) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,7 +518,7 @@ __global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier pin
         uint32_t round = first_round + rr;
         uint64_t cnt = *count_io;
         if (cnt > TOP_CAP) cnt = TOP_CAP;
-        uint32_t c = t < cnt ? amt_item_count(a0.store, cur.blk[t], cur.meta[t], round, a0.last_round) : 0;
+        uint32_t c = t < cnt ? amt_item_count(a0.store, cur.blk[t], cur.meta[t], cur.base[t], round, a0.last_round, a0.rlo, a0.rhi) : 0;
         // block exclusive scan of c
         uint32_t x = c;
 #pragma unroll
@@ -533,10 +554,6 @@ __global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier pin
 
 // first-seen dedup of the raw execution list (events/utils.rs:56-91): hash set keyed by the full
 // CID holding the smallest position; an entry survives iff it holds its own position.
-__device__ __forceinline__ bool rawcid_eq(const RawCid& x, const RawCid& y) {
-    return x.w[0] == y.w[0] && x.w[1] == y.w[1] && x.w[2] == y.w[2] && x.w[3] == y.w[3] && x.w[4] == y.w[4];
-}
-__device__ __forceinline__ uint64_t rawcid_hash(const RawCid& c) { return mix64(c.w[0] ^ (c.w[2] * 0x9E3779B97F4A7C15ULL) ^ c.w[4]); }
 __global__ void k_dedup_insert(const RawCid* __restrict__ raw, uint64_t n, unsigned long long* table, uint64_t mask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -578,6 +595,7 @@ struct EventResultBox {
     ipcfp_event_result r;  // must stay first
     PinnedArray matching, proofs, blob;
     WitnessOut wit;
+    AsyncBuf<RawCid> shard_exec;  // shard mode: this shard's slice of the raw execution list, kept on the device
 };
 
 static void throw_device_error(uint64_t key) {
@@ -709,6 +727,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     sa.amt_count = amt_count.p;
     k_setup<<<1, 32, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();
     IPCFP_CUDA(cudaMemcpyAsync(hw + 24, misc.p, (64 + 2 * IPCFP_MAX_PARENTS) * 4, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 128, amt_count.p, 2 * IPCFP_MAX_PARENTS * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
@@ -722,6 +741,33 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
 
     // ---- message AMT BFS (recording + raw execution list)
     IPCFP_CUDA(cudaEventRecord(s->ev[1], st));
+    // share of the concatenated ("raw") message list this call walks: everything, or — sharded —
+    // [Nraw*lo/N, Nraw*hi/N) expressed as one index range per AMT
+    std::vector<uint64_t> h_rng(4 * IPCFP_MAX_PARENTS, 0);
+    uint64_t nraw_total = 0;
+    {
+        const uint64_t* cnts = (const uint64_t*)(hw + 128);
+        std::vector<uint64_t> rawbase(namt + 1, 0);
+        for (uint32_t k = 0; k < namt; k++) rawbase[k + 1] = rawbase[k] + cnts[k];
+        nraw_total = rawbase[namt];
+        uint64_t glo = 0, ghi = UINT64_MAX;
+        if (sharded) {
+            glo = td.n_receipts ? (uint64_t)((__uint128_t)nraw_total * lo / td.n_receipts) : 0;
+            ghi = td.n_receipts ? (uint64_t)((__uint128_t)nraw_total * hi / td.n_receipts) : 0;
+        }
+        for (uint32_t k = 0; k < namt; k++) {
+            uint64_t A0 = rawbase[k], A1 = rawbase[k + 1];
+            uint64_t l = glo > A0 ? glo - A0 : 0, h = ghi > A0 ? ghi - A0 : 0;
+            if (!sharded) { l = 0; h = UINT64_MAX; }
+            else if (glo >= A1 && !(A1 == A0 && glo == A0)) { l = h = 0; }          // nothing of this AMT
+            else if (ghi >= A1) h = UINT64_MAX;                                      // reaches the tail: also owns indices ≥ count
+            if (h < l) h = l;
+            h_rng[k] = l; h_rng[2 * IPCFP_MAX_PARENTS + k] = h;
+        }
+    }
+    AsyncBuf<uint64_t> d_rng(4 * IPCFP_MAX_PARENTS, st);
+    IPCFP_CUDA(cudaMemcpyAsync(d_rng.p, h_rng.data(), h_rng.size() * 8, cudaMemcpyHostToDevice, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
     AsyncBuf<uint32_t> counts(cap + 1024, st);
     AsyncBuf<uint64_t> out_off(cap + 1024, st), scratch(scan_scratch_elems(std::max<uint64_t>(cap, N) + 64) + 64, st);
     Frontier fcur{fA_blk.p, fA_meta.p, fA_base.p}, fnxt{fB_blk.p, fB_meta.p, fB_base.p};
@@ -729,6 +775,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     ExpandArgs ea;
     ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw;
     ea.vals = nullptr; ea.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
+    ea.rlo = d_rng.p; ea.rhi = d_rng.p + 2 * IPCFP_MAX_PARENTS;
     // static frontier bound per round: namt * 8^round
     auto bound_of = [&](uint32_t round) { uint64_t b = namt; for (uint32_t k = 0; k < round && b <= cap; k++) b *= 8; return std::min<uint64_t>(b, cap); };
     AsyncBuf<RawCid> exec_raw;
@@ -754,7 +801,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         uint64_t items = bound_of(round);
         if (round == last_round) alloc_vals();
         unsigned grid = div_up(std::max<uint64_t>(items, 1), 128);
-        k_amt_count<<<grid, 128, 0, st>>>(s->view, fcur, ccount, round, last_round, ea.cap, counts.p); IPCFP_LAUNCH_CHECK();
+        k_amt_count<<<grid, 128, 0, st>>>(s->view, fcur, ccount, round, last_round, ea.cap, counts.p, ea.rlo, ea.rhi); IPCFP_LAUNCH_CHECK();
         exclusive_scan_u32(counts.p, out_off.p, (uint64_t)grid * 128, (uint64_t*)total_dev, scratch.p, st);
         ExpandArgs a = ea;
         a.in = fcur; a.in_count = ccount; a.out = fnxt; a.round = round; a.out_off = out_off.p;
@@ -777,7 +824,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     wbuild.start_copy(hw[8]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
-    if (nraw) {
+    if (sharded) IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));   // execution order is resolved across ranks by the caller
+    else if (nraw) {
         uint64_t slots = 64;
         while (slots < 2 * nraw) slots <<= 1;
         AsyncBuf<unsigned long long> dtab(slots, st);
@@ -821,7 +869,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         p2.store = s->view; p2.store_dev = s->view_dev.p; p2.m_dev = d_matcher; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
         p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
         p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
-        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev;
+        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = sharded ? 0 : 1;
         k_pass2<<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
@@ -872,6 +920,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[3], s->ev[4])); r.ms_pass2 = ms;
     IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[4], s->ev[5])); r.ms_witness = ms;
     r.pass1_bytes = pass1_bytes; r.pass1_nodes = pass1_nodes;
+    r.shard_raw_total = nraw_total;
+    if (sharded) { r.n_exec = 0; r.shard_exec_count = nraw; box->shard_exec = std::move(exec_raw); r.shard_exec_dev = box->shard_exec.p; }
     return &box.release()->r;
 }
 

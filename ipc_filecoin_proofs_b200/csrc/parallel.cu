@@ -1,0 +1,139 @@
+// parallel.cu — device helpers for the cross-shard part of the path (one process per GPU; the
+// collectives themselves belong to the caller: torch.distributed / NCCL).
+//
+// The reference builds the execution order by walking every message AMT and dropping repeated CIDs
+// "first seen wins" (events/utils.rs:56-91). With the message list sharded over ranks, duplicates can
+// span shards, so the dedup is a distributed hash join:
+//   ipcfp_exec_bucketize   every rank routes (cid, global position) of its slice to owner = hash(cid) % world
+//   [all-to-all]
+//   ipcfp_exec_dedup       every owner finds, per distinct CID, the smallest position; all other positions
+//                          of that CID are duplicates → returned as a list
+//   [all-gather of the (tiny) duplicate lists]  →  exec index i ↔ raw position p(i) on the host
+//   ipcfp_exec_fetch       CIDs at requested raw positions (for EventProof.message_cid)
+#include <algorithm>
+#include <vector>
+
+#include "engine.cuh"
+#include "rawcid.cuh"
+
+namespace ipcfp {
+
+struct ExecEntry { RawCid c; uint64_t pos; };  // 48 bytes
+
+__global__ void k_exec_bucketize(const RawCid* __restrict__ seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, ExecEntry* send,
+                                 unsigned long long* counts) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    RawCid c = seg[i];
+    uint32_t owner = (uint32_t)((rawcid_hash(c) >> 32) % world);
+    unsigned long long slot = atomicAdd(&counts[owner], 1ull);
+    if (slot < cap) { ExecEntry e; e.c = c; e.pos = pos0 + i; send[(uint64_t)owner * cap + slot] = e; }
+}
+
+// entry k of the received buffer (world segments of `cap`, counts[r] valid in segment r)
+__device__ __forceinline__ const ExecEntry* recv_entry(const ExecEntry* recv, const uint64_t* seg_off, uint32_t world, uint64_t cap, uint64_t k) {
+    uint32_t r = 0;
+    while (r + 1 < world && k >= seg_off[r + 1]) r++;
+    return recv + (uint64_t)r * cap + (k - seg_off[r]);
+}
+// pass 1: one canonical slot per distinct CID (value = fingerprint << 32 | smallest entry ordinal + 1)
+__global__ void k_exec_claim(const ExecEntry* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap, uint64_t total,
+                             unsigned long long* table, uint64_t mask) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
+    uint64_t h = rawcid_hash(e->c);
+    uint32_t fp = (uint32_t)h | 1u;
+    unsigned long long mine = ((unsigned long long)fp << 32) | (unsigned long long)(k + 1);
+    uint64_t slot = (h >> 20) & mask;
+    for (;;) {
+        unsigned long long v = table[slot];
+        if (v == 0) { v = atomicCAS(&table[slot], 0ull, mine); if (v == 0) return; }
+        if ((uint32_t)(v >> 32) == fp && rawcid_eq(recv_entry(recv, seg_off, world, cap, (uint32_t)v - 1)->c, e->c)) { atomicMin(&table[slot], mine); return; }
+        slot = (slot + 1) & mask;
+    }
+}
+__device__ __forceinline__ uint64_t exec_find_slot(const ExecEntry* recv, const uint64_t* seg_off, uint32_t world, uint64_t cap, const ExecEntry* e,
+                                                   const unsigned long long* table, uint64_t mask) {
+    uint64_t h = rawcid_hash(e->c);
+    uint32_t fp = (uint32_t)h | 1u;
+    uint64_t slot = (h >> 20) & mask;
+    for (;;) {
+        unsigned long long v = table[slot];
+        if ((uint32_t)(v >> 32) == fp && rawcid_eq(recv_entry(recv, seg_off, world, cap, (uint32_t)v - 1)->c, e->c)) return slot;
+        slot = (slot + 1) & mask;
+    }
+}
+// pass 2: smallest global position per CID
+__global__ void k_exec_minpos(const ExecEntry* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap, uint64_t total,
+                              const unsigned long long* table, uint64_t mask, unsigned long long* minpos) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
+    atomicMin(&minpos[exec_find_slot(recv, seg_off, world, cap, e, table, mask)], (unsigned long long)e->pos);
+}
+// pass 3: every position that is not its CID's smallest is a duplicate
+__global__ void k_exec_dups(const ExecEntry* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap, uint64_t total,
+                            const unsigned long long* table, uint64_t mask, const unsigned long long* minpos, uint64_t* dup, uint64_t cap_out,
+                            unsigned long long* n_dup) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
+    if (minpos[exec_find_slot(recv, seg_off, world, cap, e, table, mask)] != e->pos) {
+        unsigned long long j = atomicAdd(n_dup, 1ull);
+        if (j < cap_out) dup[j] = e->pos;
+    }
+}
+__global__ void k_exec_fetch(const RawCid* __restrict__ seg, uint64_t nseg, uint64_t pos0, const uint64_t* __restrict__ req, uint64_t n, RawCid* out) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t p = req[j];
+    if (p >= pos0 && p - pos0 < nseg) out[j] = seg[p - pos0];
+}
+
+void exec_bucketize(int device, const void* seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send, uint64_t* counts_host) {
+    check_device(device);
+    if (!world) throw Error(IPCFP_ERR_INVALID_ARG, "world == 0");
+    cudaStream_t st = nullptr;
+    AsyncBuf<unsigned long long> cnt(world, st);
+    cnt.zero();
+    if (nseg) { k_exec_bucketize<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, nseg, pos0, world, cap, (ExecEntry*)send, cnt.p); IPCFP_LAUNCH_CHECK(); }
+    IPCFP_CUDA(cudaMemcpyAsync(counts_host, cnt.p, world * 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t r = 0; r < world; r++) if (counts_host[r] > cap) throw Error(IPCFP_ERR_INVALID_ARG, "bucket capacity too small", counts_host[r]);
+}
+void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t world, uint64_t cap, uint64_t* dup_dev, uint64_t cap_out, uint64_t* n_dup) {
+    check_device(device);
+    cudaStream_t st = nullptr;
+    std::vector<uint64_t> seg(world + 1, 0);
+    for (uint32_t r = 0; r < world; r++) { if (counts[r] > cap) throw Error(IPCFP_ERR_INVALID_ARG, "count exceeds bucket capacity"); seg[r + 1] = seg[r] + counts[r]; }
+    uint64_t total = seg[world];
+    *n_dup = 0;
+    if (!total) return;
+    if (total >= 0xffffffffull) throw Error(IPCFP_ERR_UNSUPPORTED, "more than 2^32 messages per owner");
+    uint64_t slots = 64;
+    while (slots < 2 * total) slots <<= 1;
+    AsyncBuf<uint64_t> d_seg(world + 1, st);
+    AsyncBuf<unsigned long long> table(slots, st), minpos(slots, st), nd(1, st);
+    table.zero(); nd.zero();
+    IPCFP_CUDA(cudaMemsetAsync(minpos.p, 0xff, slots * 8, st));
+    IPCFP_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), (world + 1) * 8, cudaMemcpyHostToDevice, st));
+    unsigned g = div_up(total, 256);
+    const ExecEntry* e = (const ExecEntry*)recv;
+    k_exec_claim<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1); IPCFP_LAUNCH_CHECK();
+    k_exec_minpos<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1, minpos.p); IPCFP_LAUNCH_CHECK();
+    k_exec_dups<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1, minpos.p, dup_dev, cap_out, nd.p); IPCFP_LAUNCH_CHECK();
+    unsigned long long n = 0;
+    IPCFP_CUDA(cudaMemcpyAsync(&n, nd.p, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (n > cap_out) throw Error(IPCFP_ERR_INVALID_ARG, "duplicate list capacity too small", n);
+    *n_dup = n;
+}
+void exec_fetch(int device, const void* seg, uint64_t nseg, uint64_t pos0, const uint64_t* req_dev, uint64_t n, void* out_dev) {
+    check_device(device);
+    if (!n) return;
+    k_exec_fetch<<<div_up(n, 256), 256>>>((const RawCid*)seg, nseg, pos0, req_dev, n, (RawCid*)out_dev); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+}  // namespace ipcfp

@@ -847,7 +847,7 @@ static EventGenOut generate_event_proof(const Blockstore& net, const TipsetIn& t
         for (auto& c : ts.txmeta) collector.add_cid(c);
         // record_transaction_amts (:148-177)
         // sharded: a rank records TxMeta, AMT roots and the nodes intersecting its share
-        // [Nraw*rank/world, Nraw*(rank+1)/world) of the concatenated (raw) message list.
+        // [Nraw*lo/N, Nraw*hi/N) of the concatenated (raw) message list.
         uint64_t nraw = 0;
         std::vector<uint64_t> bases;
         if (sharded) {
@@ -868,7 +868,8 @@ static EventGenOut generate_event_proof(const Blockstore& net, const TipsetIn& t
                 auto amt = Amt<Cid>::load(*r, *rec, 0);
                 if (!sharded) amt.for_each([](uint64_t, const Cid&) {});
                 else {
-                    uint64_t glo = (uint64_t)((__uint128_t)nraw * rank / world), ghi = (uint64_t)((__uint128_t)nraw * (rank + 1) / world);
+                    uint64_t glo = ts.n_receipts ? (uint64_t)((__uint128_t)nraw * lo / ts.n_receipts) : 0, ghi = ts.n_receipts ? (uint64_t)((__uint128_t)nraw * hi / ts.n_receipts) : 0;
+                    (void)rank; (void)world;
                     uint64_t base = bases[ai];
                     uint64_t l = glo > base ? glo - base : 0, h = ghi > base ? ghi - base : 0;
                     if (h > l) amt.for_each_range_node(amt.root, amt.height, 0, l, h, [](uint64_t, const Cid&) {});

@@ -491,6 +491,11 @@ synth_tipset* synth_build(const synth_params* pp) {
         return cid_of(buf, 16);
     };
     uint64_t bls0 = 0;  // size of block 0's BLS list
+    uint64_t nraw_total = N, raw_base = 0;
+    {
+        uint64_t b0 = (N * 1 / P - N * 0 / P) * 3 / 4;
+        for (uint32_t b = 1; b < P; b++) nraw_total += std::min<uint64_t>(p.dup_msgs, b0);
+    }
     for (uint32_t b = 0; b < P; b++) {
         uint64_t lo = N * b / P, hi = N * (b + 1) / P;
         uint64_t nbls = (hi - lo) * 3 / 4, nsecp = (hi - lo) - nbls;
@@ -506,19 +511,22 @@ synth_tipset* synth_build(const synth_params* pp) {
             Cid c = msg_cid(lo + nbls + i);
             cb_cid(o, c.b);
         };
-        // sharding of message AMTs: rank owns index range [cnt*lo_frac, cnt*hi_frac) of every AMT
-        auto mk_keep = [&](uint64_t cnt) {
+        // sharding of message AMTs: a shard keeps the nodes that intersect its share
+        // [Nraw*slo/N, Nraw*shi/N) of the concatenated ("raw") message list of all AMTs
+        auto mk_keep = [&](uint64_t amt_base) {
             return [=](int level, uint64_t k) {
                 if (!sharded) return true;
-                uint64_t olo = (uint64_t)((__uint128_t)cnt * slo / N), ohi = (uint64_t)((__uint128_t)cnt * shi / N);
+                uint64_t glo = (uint64_t)((__uint128_t)nraw_total * slo / N), ghi = (uint64_t)((__uint128_t)nraw_total * shi / N);
                 unsigned sh = 3u * (unsigned)(level + 1);
-                uint64_t a = sh >= 64 ? 0 : (k << sh);
-                uint64_t bb = sh >= 64 ? ~0ull : ((k + 1) << sh);
-                return a < ohi && bb > olo;
+                uint64_t a = amt_base + (sh >= 64 ? 0 : (k << sh));
+                uint64_t bb = sh >= 64 ? ~0ull : amt_base + ((k + 1) << sh);
+                return a < ghi && bb > glo;
             };
         };
-        Cid bls_root = build_amt(nbls + dup, 3, 0, bls_v, mk_keep(nbls + dup), &T->bs, threads);
-        Cid secp_root = build_amt(nsecp, 3, 0, secp_v, mk_keep(nsecp), &T->bs, threads);
+        uint64_t base_bls = raw_base, base_secp = raw_base + nbls + dup;
+        raw_base += nbls + dup + nsecp;
+        Cid bls_root = build_amt(nbls + dup, 3, 0, bls_v, mk_keep(base_bls), &T->bs, threads);
+        Cid secp_root = build_amt(nsecp, 3, 0, secp_v, mk_keep(base_secp), &T->bs, threads);
         Bytes tm;
         cb_array(tm, 2); cb_cid(tm, bls_root.b); cb_cid(tm, secp_root.b);
         txmeta[b] = T->bs.add(tm);

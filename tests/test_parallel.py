@@ -1,0 +1,26 @@
+"""World-size-2 tests of the cross-shard path (execution-order resolution + witness merge)."""
+import numpy as np
+import pytest
+
+from tests import dist_worker
+
+
+def test_raw_position_arithmetic():
+    from ipc_filecoin_proofs_b200.parallel import raw_position_of
+    raw = list(range(30))
+    D = [3, 4, 10, 29]
+    kept = [p for p in raw if p not in D]
+    for i, p in enumerate(kept):
+        assert raw_position_of(i, D) == p
+    assert raw_position_of(0, []) == 0 and raw_position_of(5, [0, 1, 2]) == 8
+
+
+def test_cross_shard_protocol_gloo_cpu():
+    """2 processes, gloo, no GPU: oracle per rank + host restatement of the device helpers."""
+    dist_worker.run(dist_worker.cpu_worker, world=2)
+
+
+@pytest.mark.gpu
+def test_cross_shard_engine_two_ranks_one_gpu():
+    """2 processes sharing cuda:0 over gloo: the CUDA engine on sharded stores + ipcfp_exec_* helpers."""
+    dist_worker.run(dist_worker.gpu_worker, world=2)
