@@ -216,59 +216,35 @@ def run_engine(args, world, rank, local):
 
     # ---- resident-state objects
     store = store_create(A.STORE_VERIFY_CIDS)
-    L.ipcfp_tipset_upload.restype = C.c_int32
-    L.ipcfp_tipset_upload.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.POINTER(C.c_void_p)]
-    L.ipcfp_tipset_free.argtypes = [C.c_void_p]
-    L.ipcfp_generate_event_proof_shard_resident.restype = C.c_int32
-    L.ipcfp_generate_event_proof_shard_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.EventSpec), C.c_uint64, C.c_uint64, C.c_uint32,
-                                                            C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(A.EventResultC))]
-    L.ipcfp_store_stream.restype = C.c_void_p
-    L.ipcfp_store_stream.argtypes = [C.c_void_p]
     tip = C.c_void_p()
     assert L.ipcfp_tipset_upload(store, C.byref(d), C.byref(tip)) == 0, L.ipcfp_last_error()
     ext_stream = torch.cuda.ExternalStream(L.ipcfp_store_stream(store), device=torch.device("cuda", local))
 
-    cap = None
-    gathered = None
+    coll = ops = None
+    if world > 1:
+        from ipc_filecoin_proofs_b200 import parallel as PL
+        coll = PL.Collectives(dist, torch.device("cuda", local))
+        ops = PL.CudaShardOps(L, local)
 
-    def collective(res):
-        """all-gather of the per-shard witness CID sets + merge (only for N > 1)."""
-        nonlocal cap, gathered
+    def run_shard(store_h, tip_h):
+        """One step on this rank: local shard scan + (N > 1) cross-shard execution order and witness-CID union."""
         if world == 1:
-            return int(res.contents.witness.n_blocks)
-        m = int(res.contents.witness.n_blocks)
-        cnt = torch.tensor([m], dtype=torch.int64, device="cuda")
-        counts = torch.empty(world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(counts, cnt)
-        counts_h = counts.cpu().numpy().astype(np.uint64)
-        cap_now = int(counts_h.max())
-        if cap is None or cap_now > cap:
-            cap = cap_now + cap_now // 8 + 1024
-            gathered = None
-        mine = torch.empty(cap * 38, dtype=torch.uint8, device="cuda")
-        n = C.c_uint64()
-        assert L.ipcfp_witness_cids_to_device(res, C.c_void_p(mine.data_ptr()), cap, C.byref(n)) == 0, L.ipcfp_last_error()
-        if gathered is None:
-            gathered = torch.empty(world * cap * 38, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(gathered, mine)
-        out = torch.empty(int(counts_h.sum()) * 38 + 38, dtype=torch.uint8, device="cuda")
-        n_out = C.c_uint64()
-        torch.cuda.synchronize()
-        counts_c = np.ascontiguousarray(counts_h)
-        assert L.ipcfp_merge_witness_cids(local, C.c_void_p(gathered.data_ptr()), counts_c.ctypes.data, world, cap, C.c_void_p(out.data_ptr()),
-                                          int(counts_h.sum()) + 1, C.byref(n_out)) == 0, L.ipcfp_last_error()
-        return int(n_out.value)
+            out = C.POINTER(A.EventResultC)()
+            rc = L.ipcfp_generate_event_proof_resident(store_h, tip_h, C.byref(spec), 0, C.byref(out))
+            assert rc == 0, L.ipcfp_last_error()
+            return out, int(out.contents.n_exec), int(out.contents.witness.n_blocks)
+        out, n_exec, merged = PL.generate_event_proof_distributed(L, store_h, tip_h, spec, lo, hi, coll, ops)
+        return out, n_exec, int(merged.numel() // 38)
 
     stats = {}
 
     def step_resident():
-        out = C.POINTER(A.EventResultC)()
-        rc = L.ipcfp_generate_event_proof_shard_resident(store, tip, C.byref(spec), lo, hi, world, rank, 0, C.byref(out))
-        assert rc == 0, L.ipcfp_last_error()
+        out, n_exec, merged = run_shard(store, tip)
         r = out.contents
-        merged = collective(out)
-        stats.update(n_matching=int(r.n_matching), n_proofs=int(r.n_proofs), witness_blocks=int(r.witness.n_blocks),
-                     witness_bytes=int(r.witness.blob_size), merged_witness_cids=merged, n_exec=int(r.n_exec),
+        m = int(r.witness.n_blocks)
+        wbytes = int(np.frombuffer((C.c_uint32 * m).from_address(r.witness.lengths), dtype=np.uint32).sum(dtype=np.uint64)) if m else 0
+        stats.update(n_matching=int(r.n_matching), n_proofs=int(r.n_proofs), witness_blocks=m,
+                     witness_bytes=wbytes, merged_witness_cids=merged, n_exec=n_exec,
                      ms=dict(total=r.ms_total, txamt=r.ms_txamt, pass1=r.ms_pass1, pass2=r.ms_pass2, witness=r.ms_witness),
                      pass1_bytes=int(r.pass1_bytes), pass1_nodes=int(r.pass1_nodes),
                      d2h_bytes=int(r.n_matching) * 4 + int(r.n_proofs) * C.sizeof(A.EventProofC) + int(r.data_blob_size) +
@@ -303,7 +279,7 @@ def run_engine(args, world, rank, local):
     barrier()
     t_wall1 = time.time()
     launches = api.kernel_launch_count() - launches0
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = ev0.elapsed_time(ev1) if world == 1 else (t_wall1 - t_wall0) * 1e3
     t_local = torch.tensor([dev_ms, (t_wall1 - t_wall0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -322,12 +298,12 @@ def run_engine(args, world, rank, local):
         t0 = time.time()
         h = store_create(A.STORE_VERIFY_CIDS)
         t1 = time.time()
-        out = C.POINTER(A.EventResultC)()
-        rc = L.ipcfp_generate_event_proof_shard(h, C.byref(d), C.byref(spec), lo, hi, world, rank, 0, C.byref(out))
-        assert rc == 0, L.ipcfp_last_error()
-        collective(out)
+        tp = C.c_void_p()
+        assert L.ipcfp_tipset_upload(h, C.byref(d), C.byref(tp)) == 0, L.ipcfp_last_error()
+        out, _, _ = run_shard(h, tp)
         t2 = time.time()
         L.ipcfp_event_result_free(out)
+        L.ipcfp_tipset_free(tp)
         L.ipcfp_store_destroy(h)
         t3 = time.time()
         e2e_parts.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
@@ -377,7 +353,7 @@ def run_engine(args, world, rank, local):
             "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[3] per GPU: 1M receipts x 8 events, 0.1% match, events-AMT bit-widths 3/5; "
                                    "generate_event_proof (message-AMT walk + exec order, pass 1, pass 2, witness sort+gather, results to host)"
-                                   + ("" if world == 1 else f"; N={world}: {world}M-receipt tipset sharded by index range + NCCL all-gather of witness CID sets"),
+                                   + ("" if world == 1 else f"; N={world}: one {world}M-receipt tipset sharded by index range; NCCL all-to-all (distributed first-seen dedup of the execution order) + all-gather of witness CID sets"),
                        "receipts_per_gpu": N_local, "receipts_total": n_total, "store_blocks_per_gpu": int(ts.n_blocks),
                        "store_bytes_per_gpu": int(len(ts.blob)), "l2": "inputs (1.15 GB/GPU) exceed the 126 MB L2; no flush needed",
                        "matching": stats["n_matching"], "proofs": stats["n_proofs"], "witness_blocks": stats["witness_blocks"],
