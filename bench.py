@@ -271,13 +271,17 @@ def run_engine(args, world, rank, local):
     pass1_ms, step_ms = [], []
     t_wall0 = time.time()
     ev0.record(ext_stream)
+    step_wall = []
     for _ in range(args.steps):
+        _t = time.perf_counter()
         step_resident()
+        step_wall.append(1e3 * (time.perf_counter() - _t))
         pass1_ms.append(stats["ms"]["pass1"])
         step_ms.append(stats["ms"]["total"])
     ev1.record(ext_stream)
-    barrier()
+    torch.cuda.synchronize()
     t_wall1 = time.time()
+    barrier()
     launches = api.kernel_launch_count() - launches0
     dev_ms = ev0.elapsed_time(ev1) if world == 1 else (t_wall1 - t_wall0) * 1e3
     t_local = torch.tensor([dev_ms, (t_wall1 - t_wall0) * 1e3], dtype=torch.float64, device="cuda")
@@ -287,6 +291,9 @@ def run_engine(args, world, rank, local):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     log(f"resident timing done: {dev_ms_max / args.steps:.3f} ms/step")
+    if world > 1 and PL.PROFILE is not None and rank == 0:
+        log("parallel phases (ms, median/max over calls): " + ", ".join(f"{k}={np.median(v):.2f}/{np.max(v):.1f}" for k, v in PL.PROFILE.items()))
+        log("per-step wall ms: " + ", ".join(f"{x:.1f}" for x in step_wall))
     # ---- end-to-end timing (host buffers → results on the host), every step re-ingests the block set
     L.ipcfp_tipset_free(tip)
     L.ipcfp_store_destroy(store)

@@ -110,6 +110,7 @@ void storage_result_free(ipcfp_storage_result* r);
 struct WitnessOut {
     PinnedArray cids, offsets, lengths, blob;
     PinnedArray sorted_idx;       // host copy of the block indices in Cid order (u32[n])
+    AsyncBuf<uint8_t> cids_dev;   // the same sorted CIDs in device memory (n*38), for the multi-GPU union
     uint64_t n = 0, blob_size = 0;
     void fill(ipcfp_witness& w) const {
         w.n_blocks = n; w.cids = cids.as<uint8_t>(); w.offsets = offsets.as<uint64_t>(); w.lengths = lengths.as<uint32_t>();

@@ -930,7 +930,11 @@ void event_result_free(ipcfp_event_result* r) { delete reinterpret_cast<EventRes
 void witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap, uint64_t* n) {
     uint64_t m = r->witness.n_blocks;
     if (m > cap) throw Error(IPCFP_ERR_INVALID_ARG, "device buffer too small for the witness CID list");
-    if (m) IPCFP_CUDA(cudaMemcpy(dev_ptr, r->witness.cids, m * 38, cudaMemcpyHostToDevice));
+    const EventResultBox* box = reinterpret_cast<const EventResultBox*>(r);
+    if (m) {
+        if (box->wit.cids_dev.p) IPCFP_CUDA(cudaMemcpy(dev_ptr, box->wit.cids_dev.p, m * 38, cudaMemcpyDeviceToDevice));
+        else IPCFP_CUDA(cudaMemcpy(dev_ptr, r->witness.cids, m * 38, cudaMemcpyHostToDevice));
+    }
     *n = m;
 }
 

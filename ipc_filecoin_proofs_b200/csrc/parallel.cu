@@ -26,7 +26,14 @@ __global__ void k_exec_bucketize(const RawCid* __restrict__ seg, uint64_t nseg, 
     if (i >= nseg) return;
     RawCid c = seg[i];
     uint32_t owner = (uint32_t)((rawcid_hash(c) >> 32) % world);
-    unsigned long long slot = atomicAdd(&counts[owner], 1ull);
+    // warp-aggregated slot claim: one atomic per distinct owner per warp
+    unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, owner);
+    int leader = __ffs((int)peers) - 1;
+    unsigned long long base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&counts[owner], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    unsigned long long slot = base + (unsigned long long)__popc(peers & ((1u << (threadIdx.x & 31)) - 1));
     if (slot < cap) { ExecEntry e; e.c = c; e.pos = pos0 + i; send[(uint64_t)owner * cap + slot] = e; }
 }
 
@@ -91,20 +98,34 @@ __global__ void k_exec_fetch(const RawCid* __restrict__ seg, uint64_t nseg, uint
     if (p >= pos0 && p - pos0 < nseg) out[j] = seg[p - pos0];
 }
 
+// grow-only scratch + a private non-blocking stream per device for the helpers (no allocation in steady state)
+struct HelperCtx {
+    cudaStream_t st = nullptr;
+    DevBuf<unsigned long long> table, minpos, small;
+};
+static HelperCtx& helper_ctx(int device) {
+    static HelperCtx ctx[16];
+    HelperCtx& c = ctx[device & 15];
+    if (!c.st) { IPCFP_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking)); c.small.alloc(1024); }
+    return c;
+}
+
 void exec_bucketize(int device, const void* seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send, uint64_t* counts_host) {
     check_device(device);
-    if (!world) throw Error(IPCFP_ERR_INVALID_ARG, "world == 0");
-    cudaStream_t st = nullptr;
-    AsyncBuf<unsigned long long> cnt(world, st);
-    cnt.zero();
-    if (nseg) { k_exec_bucketize<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, nseg, pos0, world, cap, (ExecEntry*)send, cnt.p); IPCFP_LAUNCH_CHECK(); }
-    IPCFP_CUDA(cudaMemcpyAsync(counts_host, cnt.p, world * 8, cudaMemcpyDeviceToHost, st));
+    if (!world || world > 1000) throw Error(IPCFP_ERR_INVALID_ARG, "bad world size");
+    HelperCtx& hc = helper_ctx(device);
+    cudaStream_t st = hc.st;
+    unsigned long long* cnt = hc.small.p;
+    IPCFP_CUDA(cudaMemsetAsync(cnt, 0, world * 8, st));
+    if (nseg) { k_exec_bucketize<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, nseg, pos0, world, cap, (ExecEntry*)send, cnt); IPCFP_LAUNCH_CHECK(); }
+    IPCFP_CUDA(cudaMemcpyAsync(counts_host, cnt, world * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     for (uint32_t r = 0; r < world; r++) if (counts_host[r] > cap) throw Error(IPCFP_ERR_INVALID_ARG, "bucket capacity too small", counts_host[r]);
 }
 void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t world, uint64_t cap, uint64_t* dup_dev, uint64_t cap_out, uint64_t* n_dup) {
     check_device(device);
-    cudaStream_t st = nullptr;
+    HelperCtx& hc = helper_ctx(device);
+    cudaStream_t st = hc.st;
     std::vector<uint64_t> seg(world + 1, 0);
     for (uint32_t r = 0; r < world; r++) { if (counts[r] > cap) throw Error(IPCFP_ERR_INVALID_ARG, "count exceeds bucket capacity"); seg[r + 1] = seg[r] + counts[r]; }
     uint64_t total = seg[world];
@@ -113,18 +134,22 @@ void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t w
     if (total >= 0xffffffffull) throw Error(IPCFP_ERR_UNSUPPORTED, "more than 2^32 messages per owner");
     uint64_t slots = 64;
     while (slots < 2 * total) slots <<= 1;
-    AsyncBuf<uint64_t> d_seg(world + 1, st);
-    AsyncBuf<unsigned long long> table(slots, st), minpos(slots, st), nd(1, st);
-    table.zero(); nd.zero();
-    IPCFP_CUDA(cudaMemsetAsync(minpos.p, 0xff, slots * 8, st));
-    IPCFP_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), (world + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (world + 2 > 1000) throw Error(IPCFP_ERR_UNSUPPORTED, "world too large");
+    hc.table.ensure(slots);
+    hc.minpos.ensure(slots);
+    uint64_t* d_seg = (uint64_t*)hc.small.p;             // [0, world]
+    unsigned long long* nd = hc.small.p + 1023;
+    IPCFP_CUDA(cudaMemsetAsync(hc.table.p, 0, slots * 8, st));
+    IPCFP_CUDA(cudaMemsetAsync(hc.minpos.p, 0xff, slots * 8, st));
+    IPCFP_CUDA(cudaMemsetAsync(nd, 0, 8, st));
+    IPCFP_CUDA(cudaMemcpyAsync(d_seg, seg.data(), (world + 1) * 8, cudaMemcpyHostToDevice, st));
     unsigned g = div_up(total, 256);
     const ExecEntry* e = (const ExecEntry*)recv;
-    k_exec_claim<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1); IPCFP_LAUNCH_CHECK();
-    k_exec_minpos<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1, minpos.p); IPCFP_LAUNCH_CHECK();
-    k_exec_dups<<<g, 256, 0, st>>>(e, d_seg.p, world, cap, total, table.p, slots - 1, minpos.p, dup_dev, cap_out, nd.p); IPCFP_LAUNCH_CHECK();
+    k_exec_claim<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1); IPCFP_LAUNCH_CHECK();
+    k_exec_minpos<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1, hc.minpos.p); IPCFP_LAUNCH_CHECK();
+    k_exec_dups<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1, hc.minpos.p, dup_dev, cap_out, nd); IPCFP_LAUNCH_CHECK();
     unsigned long long n = 0;
-    IPCFP_CUDA(cudaMemcpyAsync(&n, nd.p, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(&n, nd, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (n > cap_out) throw Error(IPCFP_ERR_INVALID_ARG, "duplicate list capacity too small", n);
     *n_dup = n;

@@ -228,6 +228,7 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
         IPCFP_CUDA(cudaMemcpyAsync(out.lengths.p, d_lens.p, m * 4, cudaMemcpyDeviceToHost, st));
         IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, d_idx.p, m * 4, cudaMemcpyDeviceToHost, st));
     }
+    out.cids_dev = std::move(d_cids);
     IPCFP_CUDA(cudaStreamWaitEvent(st, s->ev[7], 0));  // the big copy on the side stream
     IPCFP_CUDA(cudaStreamSynchronize(st));
     IPCFP_CUDA(cudaStreamSynchronize(st2));

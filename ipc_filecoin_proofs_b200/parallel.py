@@ -24,6 +24,26 @@ from . import _abi as A
 ENTRY = 48   # exec entry: 40-byte CID record + u64 global position
 REC = 40
 
+import os
+import time
+
+PROFILE = {} if os.environ.get("IPCFP_PARALLEL_PROFILE") else None
+
+
+class _Phase:
+    """Wall-clock phase timer (only when IPCFP_PARALLEL_PROFILE is set)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.t = time.perf_counter()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            PROFILE.setdefault(self.name, []).append(1e3 * (time.perf_counter() - self.t))
+
 
 class Collectives:
     """Thin wrapper over torch.distributed that works for nccl (device tensors) and gloo (host staging)."""
@@ -152,6 +172,16 @@ class CudaShardOps:
     def upload(self, a):
         return self.torch.as_tensor(np.ascontiguousarray(a)).to(self.tdev)
 
+    def witness_cids_device(self, res_ptr, cap):
+        """The result's sorted witness CIDs as a zero-padded device tensor of cap*38 bytes (device-to-device copy)."""
+        t = self.torch.zeros(cap * 38, dtype=self.torch.uint8, device=self.tdev)
+        n = C.c_uint64()
+        self.torch.cuda.synchronize(self.tdev)
+        st = self.L.ipcfp_witness_cids_to_device(res_ptr, C.c_void_p(t.data_ptr()), cap, C.byref(n))
+        if st != A.OK:
+            raise A.IpcfpError(st, self.L.ipcfp_last_error().decode(), self.L.ipcfp_last_error_index())
+        return t
+
 
 def raw_position_of(exec_index, dups_sorted):
     """exec index i ↔ position p in the concatenated message list, given the sorted duplicate positions D:
@@ -165,35 +195,66 @@ def raw_position_of(exec_index, dups_sorted):
         p = q
 
 
-def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices):
+def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices, seg_counts=None):
     """Runs the distributed first-seen dedup and returns (n_exec, {exec_index: 40-byte record}).
 
     seg_ptr/nseg: this rank's slice of the raw message list (device pointer for CudaShardOps);
     matching: the rank's matching receipt indices (for the MISSING_EXEC check, events/generator.rs:244-246);
-    proof_exec_indices: exec indices whose message CID the rank's proofs need."""
+    proof_exec_indices: exec indices whose message CID the rank's proofs need;
+    seg_counts: per-rank slice lengths if the caller already gathered them."""
     world, rank = coll.world, coll.rank
-    counts = coll.all_gather_i64([nseg])[:, 0]
+    if seg_counts is None:
+        with _Phase("x.counts"):
+            seg_counts = coll.all_gather_i64([nseg])[:, 0]
+    counts = np.asarray(seg_counts, dtype=np.int64)
     pos0 = int(counts[:rank].sum())
     nraw = int(counts.sum())
     cap = int(counts.max()) // world + int(counts.max()) // (4 * world) + 1024
-    send, cnt = ops.bucketize(seg_ptr, nseg, pos0, world, cap)
-    cnt_matrix = coll.all_gather_i64(cnt.view(np.int64))          # [sender, owner]
+    with _Phase("x.bucketize"):
+        send, cnt = ops.bucketize(seg_ptr, nseg, pos0, world, cap)
+    with _Phase("x.count_matrix"):
+        cnt_matrix = coll.all_gather_i64(cnt.view(np.int64))          # [sender, owner]
     recv_counts = cnt_matrix[:, rank].astype(np.uint64)
-    recv = coll.all_to_all_bytes(send, cap * ENTRY)
-    dups_local = ops.dedup(recv, recv_counts, world, cap)
-    dups, _ = coll.all_gather_var_u64(dups_local)
+    with _Phase("x.all_to_all"):
+        recv = coll.all_to_all_bytes(send, cap * ENTRY)
+    with _Phase("x.dedup"):
+        dups_local = ops.dedup(recv, recv_counts, world, cap)
+    # one fixed-size all-gather carries the duplicate positions of every owner ([count, positions…]);
+    # the rare overflow falls back to the variable-length path
+    DUP_CAP = 1023
+    with _Phase("x.dups_gather"):
+        pad = np.zeros(DUP_CAP + 1, dtype=np.int64)
+        pad[0] = len(dups_local)
+        k = min(len(dups_local), DUP_CAP)
+        pad[1:1 + k] = dups_local[:k].view(np.int64)
+        allp = coll.all_gather_i64(pad)
+        if int(allp[:, 0].max()) > DUP_CAP:
+            dups, _ = coll.all_gather_var_u64(dups_local)
+        else:
+            dups = np.concatenate([allp[r, 1:1 + int(allp[r, 0])] for r in range(world)]).view(np.uint64)
     D = np.sort(dups).tolist()
     n_exec = nraw - len(D)
-    # exec.get(i) must exist for every matching receipt (checked in ascending order by the reference)
+    # exec.get(i) must exist for every matching receipt (checked in ascending order by the reference);
+    # the verdict travels with the position requests
     bad = [int(i) for i in matching if int(i) >= n_exec]
-    first_bad = coll.all_reduce_min_i64(min(bad) if bad else np.iinfo(np.int64).max)
-    if first_bad != np.iinfo(np.int64).max:
-        raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
+    my_bad = min(bad) if bad else np.iinfo(np.int64).max
     need = sorted(set(int(i) for i in proof_exec_indices))
-    pos = np.array([raw_position_of(i, D) for i in need], dtype=np.uint64)
-    req_all, req_counts = coll.all_gather_var_u64(pos)
-    ans = ops.fetch(seg_ptr, nseg, pos0, req_all)                # zeros where another rank owns the position
-    ans = coll.all_reduce_sum_i64(ans.reshape(-1).view(np.int64)).view(np.uint8).reshape(-1, REC)
+    pos = np.array([raw_position_of(i, D) if i < n_exec else 0 for i in need], dtype=np.uint64)
+    with _Phase("x.req_gather"):
+        hdr = coll.all_gather_i64([len(pos), my_bad])
+        req_counts = hdr[:, 0]
+        first_bad = int(hdr[:, 1].min())
+        if first_bad != np.iinfo(np.int64).max:
+            raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
+        capq = int(req_counts.max()) if len(req_counts) else 0
+        padq = np.zeros(max(capq, 1), dtype=np.int64)
+        padq[:len(pos)] = pos.view(np.int64)
+        allq = coll.all_gather_i64(padq)
+        req_all = np.concatenate([allq[r, :int(req_counts[r])] for r in range(world)]).view(np.uint64) if capq else np.zeros(0, np.uint64)
+    with _Phase("x.fetch"):
+        ans = ops.fetch(seg_ptr, nseg, pos0, req_all)                # zeros where another rank owns the position
+    with _Phase("x.ans_reduce"):
+        ans = coll.all_reduce_sum_i64(ans.reshape(-1).view(np.int64)).view(np.uint8).reshape(-1, REC)
     start = int(req_counts[:rank].sum())
     mine = ans[start:start + len(need)]
     return n_exec, {i: bytes(mine[k]) for k, i in enumerate(need)}
@@ -204,24 +265,46 @@ def record_to_cid(rec40):
     return bytes(rec40[32:38]) + bytes(rec40[:32])
 
 
+def _proofs_view(res_c):
+    """numpy view (n, sizeof(EventProofC)) over the result's proof records (host memory owned by the result)."""
+    n = int(res_c.n_proofs)
+    sz = C.sizeof(A.EventProofC)
+    if n == 0:
+        return np.zeros((0, sz), dtype=np.uint8)
+    addr = C.cast(res_c.proofs, C.c_void_p).value
+    return np.frombuffer((C.c_uint8 * (n * sz)).from_address(addr), dtype=np.uint8).reshape(n, sz)
+
+
 def patch_message_cids(res_c, msg_of):
     """Writes EventProof.message_cid of a shard result in place (res_c: EventResultC)."""
-    for k in range(int(res_c.n_proofs)):
-        p = res_c.proofs[k]
-        cid = record_to_cid(msg_of[int(p.exec_index)])
-        C.memmove(C.addressof(p.message_cid), cid, 38)
+    pv = _proofs_view(res_c)
+    if not len(pv):
+        return
+    off = A.EventProofC.message_cid.offset
+    exec_idx = pv[:, :8].copy().view(np.uint64).reshape(-1)
+    keys = sorted(msg_of)
+    table = np.frombuffer(b"".join(record_to_cid(msg_of[k]) for k in keys), dtype=np.uint8).reshape(-1, 38)
+    where = np.searchsorted(np.array(keys, dtype=np.uint64), exec_idx)
+    pv[:, off:off + 38] = table[where]
 
 
-def gather_witness_cids(ops, coll, local_sorted_cids):
-    """all-gather of the per-shard sorted witness CID lists + device merge → (m, 38) uint8 tensor/array of the union."""
-    local = np.ascontiguousarray(local_sorted_cids, dtype=np.uint8).reshape(-1, 38)
-    counts = coll.all_gather_i64([len(local)])[:, 0].astype(np.uint64)
+def gather_witness_cids(ops, coll, local_sorted_cids, counts=None, device_tensor=None):
+    """all-gather of the per-shard sorted witness CID lists + device merge → uint8 tensor (m*38) of the union.
+    device_tensor: the local list already on the device, padded to (max count + 1) * 38 bytes."""
+    if counts is None:
+        local = np.ascontiguousarray(local_sorted_cids, dtype=np.uint8).reshape(-1, 38)
+        counts = coll.all_gather_i64([len(local)])[:, 0]
+    counts = np.asarray(counts).astype(np.uint64)
     cap = int(counts.max()) + 1
-    buf = np.zeros((cap, 38), dtype=np.uint8)
-    buf[:len(local)] = local
-    mine = ops.upload(buf.reshape(-1))
-    gathered = coll.all_gather_bytes(mine)
-    merged = ops.merge_witness(gathered, counts, coll.world, cap)
+    if device_tensor is None:
+        local = np.ascontiguousarray(local_sorted_cids, dtype=np.uint8).reshape(-1, 38)
+        buf = np.zeros((cap, 38), dtype=np.uint8)
+        buf[:len(local)] = local
+        device_tensor = ops.upload(buf.reshape(-1))
+    with _Phase("w.all_gather"):
+        gathered = coll.all_gather_bytes(device_tensor)
+    with _Phase("w.merge"):
+        merged = ops.merge_witness(gathered, counts, coll.world, cap)
     return merged
 
 
@@ -229,19 +312,34 @@ def generate_event_proof_distributed(lib, store_handle, tipset_handle, spec_c, l
     """One rank's part of a sharded generate_event_proof + the cross-shard resolution.
     Returns (POINTER(EventResultC) with message CIDs patched — caller frees it, n_exec, merged witness CIDs)."""
     out = C.POINTER(A.EventResultC)()
-    st = lib.ipcfp_generate_event_proof_shard_resident(store_handle, tipset_handle, C.byref(spec_c), lo, hi, coll.world, coll.rank, flags, C.byref(out))
-    # a failing rank must not leave the others hanging in a collective: agree on the status first
-    worst = coll.all_reduce_min_i64(st)
+    with _Phase("local_shard_scan"):
+        st = lib.ipcfp_generate_event_proof_shard_resident(store_handle, tipset_handle, C.byref(spec_c), lo, hi, coll.world, coll.rank, flags,
+                                                           C.byref(out))
+    ok = st == A.OK
+    r = out.contents if ok else None
+    # one all-gather: status (a failing rank must not leave the others hanging), slice length, witness size
+    with _Phase("header_allgather"):
+        hdr = coll.all_gather_i64([st, int(r.shard_exec_count) if ok else 0, int(r.witness.n_blocks) if ok else 0])
+    worst = int(hdr[:, 0].min())
     if worst != A.OK:
-        if st != A.OK:
+        if not ok:
             raise A.IpcfpError(st, lib.ipcfp_last_error().decode(errors="replace"), lib.ipcfp_last_error_index())
+        lib.ipcfp_event_result_free(out)
         raise A.IpcfpError(worst, "another rank failed", 0xFFFFFFFFFFFFFFFF)
-    r = out.contents
     matching = np.frombuffer((C.c_uint64 * int(r.n_matching)).from_address(r.matching_indices), dtype=np.uint64) if r.n_matching else np.zeros(0, np.uint64)
-    need = [int(r.proofs[k].exec_index) for k in range(int(r.n_proofs))]
-    n_exec, msg_of = resolve_execution_order(ops, coll, r.shard_exec_dev, int(r.shard_exec_count), matching, need)
-    patch_message_cids(r, msg_of)
-    m = int(r.witness.n_blocks)
-    local_cids = np.frombuffer((C.c_uint8 * (m * 38)).from_address(r.witness.cids), dtype=np.uint8) if m else np.zeros(0, np.uint8)
-    merged = gather_witness_cids(ops, coll, local_cids)
+    need = _proofs_view(r)[:, :8].copy().view(np.uint64).reshape(-1) if r.n_proofs else np.zeros(0, np.uint64)
+    with _Phase("resolve_exec_total"):
+        n_exec, msg_of = resolve_execution_order(ops, coll, r.shard_exec_dev, int(r.shard_exec_count), matching, need, seg_counts=hdr[:, 1])
+    with _Phase("patch"):
+        patch_message_cids(r, msg_of)
+    with _Phase("witness_union"):
+        wcounts = hdr[:, 2]
+        dev_t = None
+        if hasattr(ops, "witness_cids_device"):
+            dev_t = ops.witness_cids_device(out, int(wcounts.max()) + 1)
+        m = int(r.witness.n_blocks)
+        local_cids = None
+        if dev_t is None:
+            local_cids = np.frombuffer((C.c_uint8 * (m * 38)).from_address(r.witness.cids), dtype=np.uint8) if m else np.zeros(0, np.uint8)
+        merged = gather_witness_cids(ops, coll, local_cids, counts=wcounts, device_tensor=dev_t)
     return out, n_exec, merged
