@@ -266,6 +266,7 @@ def run_engine(args, world, rank, local):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    barrier()   # every rank enters the timed region together (rank 0 just waited for the sampler)
     launches0 = api.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pass1_ms, step_ms = [], []
