@@ -274,7 +274,9 @@ ipcfp_status ipcfp_generate_event_proof_shard(ipcfp_store* s, const ipcfp_tipset
  * memory; an "exec entry" is 48 bytes {record[40], global position u64}.
  *   1. pos0 = sum of shard_exec_count of lower ranks (all-gather); ipcfp_exec_bucketize routes every record of
  *      the rank's slice to owner = hash(cid) % world: send_dev = world segments of `cap` entries, counts[world].
- *   2. all-to-all of counts and segments; ipcfp_exec_dedup returns the global positions that are NOT the first
+ *      Inside a segment the entries are in increasing position order.
+ *   2. all-to-all of counts and segments (segment r of the received buffer comes from rank r, so the buffer is
+ *      ordered by global position per CID); ipcfp_exec_dedup returns the global positions that are NOT the first
  *      occurrence of their CID (any order).
  *   3. all-gather of the duplicate lists → sorted D on every rank: exec index i ↔ raw position p with
  *      p = i + |{d ∈ D : d ≤ p}|; n_exec = shard_raw_total − |D|.

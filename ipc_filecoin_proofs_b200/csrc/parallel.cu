@@ -14,27 +14,34 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "prims.cuh"
 #include "rawcid.cuh"
 
 namespace ipcfp {
 
 struct ExecEntry { RawCid c; uint64_t pos; };  // 48 bytes
 
-__global__ void k_exec_bucketize(const RawCid* __restrict__ seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, ExecEntry* send,
-                                 unsigned long long* counts) {
+// owner of every record of the slice (key for the stable partition)
+__global__ void k_exec_owner(const RawCid* __restrict__ seg, uint64_t nseg, uint32_t world, uint32_t* keys, uint32_t* vals) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nseg) return;
-    RawCid c = seg[i];
-    uint32_t owner = (uint32_t)((rawcid_hash(c) >> 32) % world);
-    // warp-aggregated slot claim: one atomic per distinct owner per warp
-    unsigned active = __activemask();
-    unsigned peers = __match_any_sync(active, owner);
-    int leader = __ffs((int)peers) - 1;
-    unsigned long long base = 0;
-    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&counts[owner], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    unsigned long long slot = base + (unsigned long long)__popc(peers & ((1u << (threadIdx.x & 31)) - 1));
-    if (slot < cap) { ExecEntry e; e.c = c; e.pos = pos0 + i; send[(uint64_t)owner * cap + slot] = e; }
+    keys[i] = (uint32_t)((rawcid_hash(seg[i]) >> 32) % world);
+    vals[i] = (uint32_t)i;
+}
+// first sorted position of every owner
+__global__ void k_exec_starts(const uint32_t* __restrict__ keys, uint64_t nseg, unsigned long long* start) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nseg) return;
+    if (j == 0 || keys[j - 1] != keys[j]) start[keys[j]] = j;
+}
+// entries leave in (owner, position) order: within a bucket the global positions are increasing
+__global__ void k_exec_scatter(const RawCid* __restrict__ seg, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t nseg,
+                               uint64_t pos0, const unsigned long long* __restrict__ start, uint64_t cap, ExecEntry* send) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nseg) return;
+    uint32_t owner = keys[j], src = vals[j];
+    uint64_t slot = j - start[owner];
+    if (slot < cap) { ExecEntry e; e.c = seg[src]; e.pos = pos0 + src; send[(uint64_t)owner * cap + slot] = e; }
 }
 
 // entry k of the received buffer (world segments of `cap`, counts[r] valid in segment r)
@@ -71,22 +78,15 @@ __device__ __forceinline__ uint64_t exec_find_slot(const ExecEntry* recv, const 
         slot = (slot + 1) & mask;
     }
 }
-// pass 2: smallest global position per CID
-__global__ void k_exec_minpos(const ExecEntry* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap, uint64_t total,
-                              const unsigned long long* table, uint64_t mask, unsigned long long* minpos) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total) return;
-    const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
-    atomicMin(&minpos[exec_find_slot(recv, seg_off, world, cap, e, table, mask)], (unsigned long long)e->pos);
-}
-// pass 3: every position that is not its CID's smallest is a duplicate
+// pass 2: the received buffer is ordered by (sender rank, position), so the smallest entry ordinal of a CID is
+// its smallest global position: every other entry of that CID is a duplicate
 __global__ void k_exec_dups(const ExecEntry* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap, uint64_t total,
-                            const unsigned long long* table, uint64_t mask, const unsigned long long* minpos, uint64_t* dup, uint64_t cap_out,
-                            unsigned long long* n_dup) {
+                            const unsigned long long* table, uint64_t mask, uint64_t* dup, uint64_t cap_out, unsigned long long* n_dup) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total) return;
     const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
-    if (minpos[exec_find_slot(recv, seg_off, world, cap, e, table, mask)] != e->pos) {
+    uint64_t slot = exec_find_slot(recv, seg_off, world, cap, e, table, mask);
+    if ((uint32_t)table[slot] - 1 != (uint32_t)k) {
         unsigned long long j = atomicAdd(n_dup, 1ull);
         if (j < cap_out) dup[j] = e->pos;
     }
@@ -112,14 +112,31 @@ static HelperCtx& helper_ctx(int device) {
 
 void exec_bucketize(int device, const void* seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send, uint64_t* counts_host) {
     check_device(device);
-    if (!world || world > 1000) throw Error(IPCFP_ERR_INVALID_ARG, "bad world size");
+    if (!world || world > 256) throw Error(IPCFP_ERR_INVALID_ARG, "bad world size");
+    if (nseg >= 0xffffffffull) throw Error(IPCFP_ERR_UNSUPPORTED, "slice too long");
     HelperCtx& hc = helper_ctx(device);
     cudaStream_t st = hc.st;
-    unsigned long long* cnt = hc.small.p;
-    IPCFP_CUDA(cudaMemsetAsync(cnt, 0, world * 8, st));
-    if (nseg) { k_exec_bucketize<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, nseg, pos0, world, cap, (ExecEntry*)send, cnt); IPCFP_LAUNCH_CHECK(); }
-    IPCFP_CUDA(cudaMemcpyAsync(counts_host, cnt, world * 8, cudaMemcpyDeviceToHost, st));
+    for (uint32_t r = 0; r < world; r++) counts_host[r] = 0;
+    if (!nseg) return;
+    unsigned nb = radix_blocks(nseg);
+    AsyncBuf<uint32_t> keys(nseg, st), vals(nseg, st), ka(nseg, st), va(nseg, st), hist((size_t)256 * nb + 256, st);
+    AsyncBuf<uint64_t> scan_tmp((size_t)256 * nb + 256, st), scratch(scan_scratch_elems((uint64_t)256 * nb) + 8, st);
+    unsigned long long* start = hc.small.p;   // [0, world]
+    std::vector<unsigned long long> h_start(world + 1, nseg);
+    IPCFP_CUDA(cudaMemcpyAsync(start, h_start.data(), (world + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_exec_owner<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, nseg, world, keys.p, vals.p); IPCFP_LAUNCH_CHECK();
+    radix_sort_pairs(keys.p, vals.p, ka.p, va.p, nseg, 8, hist.p, scan_tmp.p, scratch.p, st);
+    k_exec_starts<<<div_up(nseg, 256), 256, 0, st>>>(keys.p, nseg, start); IPCFP_LAUNCH_CHECK();
+    k_exec_scatter<<<div_up(nseg, 256), 256, 0, st>>>((const RawCid*)seg, keys.p, vals.p, nseg, pos0, start, cap, (ExecEntry*)send); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaMemcpyAsync(h_start.data(), start, (world + 1) * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
+    // owners without entries keep start == nseg; counts from consecutive starts of present owners
+    uint64_t next = nseg;
+    for (int r = (int)world - 1; r >= 0; r--) {
+        if (h_start[r] == nseg) { counts_host[r] = 0; continue; }
+        counts_host[r] = next - h_start[r];
+        next = h_start[r];
+    }
     for (uint32_t r = 0; r < world; r++) if (counts_host[r] > cap) throw Error(IPCFP_ERR_INVALID_ARG, "bucket capacity too small", counts_host[r]);
 }
 void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t world, uint64_t cap, uint64_t* dup_dev, uint64_t cap_out, uint64_t* n_dup) {
@@ -136,18 +153,15 @@ void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t w
     while (slots < 2 * total) slots <<= 1;
     if (world + 2 > 1000) throw Error(IPCFP_ERR_UNSUPPORTED, "world too large");
     hc.table.ensure(slots);
-    hc.minpos.ensure(slots);
     uint64_t* d_seg = (uint64_t*)hc.small.p;             // [0, world]
     unsigned long long* nd = hc.small.p + 1023;
     IPCFP_CUDA(cudaMemsetAsync(hc.table.p, 0, slots * 8, st));
-    IPCFP_CUDA(cudaMemsetAsync(hc.minpos.p, 0xff, slots * 8, st));
     IPCFP_CUDA(cudaMemsetAsync(nd, 0, 8, st));
     IPCFP_CUDA(cudaMemcpyAsync(d_seg, seg.data(), (world + 1) * 8, cudaMemcpyHostToDevice, st));
     unsigned g = div_up(total, 256);
     const ExecEntry* e = (const ExecEntry*)recv;
     k_exec_claim<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1); IPCFP_LAUNCH_CHECK();
-    k_exec_minpos<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1, hc.minpos.p); IPCFP_LAUNCH_CHECK();
-    k_exec_dups<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1, hc.minpos.p, dup_dev, cap_out, nd); IPCFP_LAUNCH_CHECK();
+    k_exec_dups<<<g, 256, 0, st>>>(e, d_seg, world, cap, total, hc.table.p, slots - 1, dup_dev, cap_out, nd); IPCFP_LAUNCH_CHECK();
     unsigned long long n = 0;
     IPCFP_CUDA(cudaMemcpyAsync(&n, nd, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
