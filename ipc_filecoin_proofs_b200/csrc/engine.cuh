@@ -46,6 +46,7 @@ struct Store {
     DevBuf<Digest> digests;
     DevBuf<uint8_t> cls;
     DevBuf<uint64_t> table;
+    DevBuf<BlockRec> recs;
     StoreView view{};
     DevBuf<StoreView> view_dev;   // device copy, for out-of-line device functions (keeps kernel params off the stack)
     std::vector<std::array<uint8_t, 6>> class_prefix;  // distinct CID prefixes in this store

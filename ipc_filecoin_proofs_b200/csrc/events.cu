@@ -12,6 +12,7 @@
 //                      events-AMT walk, witness bits, EventProof records
 //   materialize_witness (witness.cu)   WitnessCollector::materialize (:104)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.cuh"
@@ -141,7 +142,7 @@ struct Pass1Args {
 // One thread per receipt: resolve its events root CID, decode the root node of its events AMT,
 // test every StampedEvent. The common single-node AMT (≤ 2^bw events) never leaves this
 // function; taller AMTs fall through to the generic walker.
-__global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
+__device__ __forceinline__ void pass1_body(const Pass1Args& a) {
     uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool matched = false;
     uint32_t bytes = 0, nodes = 0, np_ = 0, nb_ = 0;
@@ -190,6 +191,11 @@ __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) {
     for (int o = 16; o; o >>= 1) { bytes += __shfl_xor_sync(0xffffffffu, bytes, o); nodes += __shfl_xor_sync(0xffffffffu, nodes, o); }
     if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(a.stats, (unsigned long long)nodes); atomicAdd(a.stats + 1, (unsigned long long)bytes); }
 }
+// the same kernel at three register budgets (resident CTAs per SM: 6 → 80 regs, 8 → 64, 10 → 48);
+// IPCFP_PASS1_MINB selects one at run time for tuning, 6 is the measured default
+__global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) { pass1_body(a); }
+__global__ void __launch_bounds__(128, 8) k_pass1_occ8(Pass1Args a) { pass1_body(a); }
+__global__ void __launch_bounds__(128, 10) k_pass1_occ10(Pass1Args a) { pass1_body(a); }
 
 // ------------------------------------------------------------------------------------------ receipts AMT
 // Amtv0<Receipt>::get(i) with recording (events/generator.rs:249). 1 = Some, 0 = None, <0 = -DevCode.
@@ -843,7 +849,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     Pass1Args p1;
     p1.store = s->view; p1.store_dev = s->view_dev.p; p1.m_dev = d_matcher; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
     p1.match_bits = match_bits.p; p1.cnt = cnt.p; p1.nbytes = nby.p; p1.err = dw; p1.stats = dw + 4;
-    if (N) { k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1); IPCFP_LAUNCH_CHECK(); }
+    if (N) {
+        static const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 6;
+        if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
+        else if (minb >= 8) k_pass1_occ8<<<div_up(N, 128), 128, 0, st>>>(p1);
+        else k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1);
+        IPCFP_LAUNCH_CHECK();
+    }
     IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
     AsyncBuf<uint32_t> match_rel(N + 32, st);
     AsyncBuf<uint64_t> wp3((N + 31) / 32 + 8, st);

@@ -90,6 +90,15 @@ __global__ void k_build_index(uint32_t n, const Digest* __restrict__ digests, co
     }
 }
 
+__global__ void k_build_recs(uint32_t n, const Digest* __restrict__ digests, const uint8_t* __restrict__ cls, const uint64_t* __restrict__ offsets,
+                             const uint32_t* __restrict__ lengths, BlockRec* recs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    BlockRec r;
+    r.d = digests[i]; r.off = offsets[i]; r.len = lengths[i]; r.cls = cls[i]; r.pad[0] = r.pad[1] = 0;
+    recs[i] = r;
+}
+
 // K1: Blake2b-256 of every block compared with the digest in its CID (class must be a
 // blake2b-256 multihash: code 0xb220; other classes are skipped).
 __global__ void __launch_bounds__(128) k_verify_cids(StoreView v, uint32_t lo, uint32_t hi, uint32_t b2b_class_mask, unsigned long long* first_bad) {
@@ -132,6 +141,7 @@ static void fill_view(Store* s) {
     StoreView& v = s->view;
     v.blob = s->arena.p + 16;
     v.offsets = s->offsets.p; v.lengths = s->lengths.p; v.digests = s->digests.p; v.cls = s->cls.p; v.table = s->table.p;
+    v.recs = s->recs.p;
     v.mask = s->table.n - 1;
     v.n = (uint32_t)s->n;
     v.n_classes = (uint32_t)s->class_prefix.size();
@@ -185,6 +195,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     s->lengths.alloc(n + 1);
     s->digests.alloc(n + 1);
     s->cls.alloc(n + 1);
+    s->recs.alloc(n + 1);
     uint64_t slots = 64;
     while (slots < 2 * n) slots <<= 1;
     s->table.alloc(slots);
@@ -233,6 +244,8 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     }
     if (!n) { fill_view(s.get()); }
     if (n) {
+        k_build_recs<<<div_up(n, 256), 256, 0, st>>>((uint32_t)n, s->digests.p, s->cls.p, s->offsets.p, s->lengths.p, s->recs.p);
+        IPCFP_LAUNCH_CHECK();
         k_build_index<<<div_up(n, 256), 256, 0, st>>>((uint32_t)n, s->digests.p, s->cls.p, (unsigned long long*)s->table.p, s->table.n - 1);
         IPCFP_LAUNCH_CHECK();
     }

@@ -17,8 +17,13 @@ namespace ipcfp {
 
 #define IPCFP_MAX_CID_CLASSES 8
 
+// everything a Blockstore::get needs about one block in ONE 64-byte line: the probe compares the digest,
+// the hit continues with offset/length from the same line (instead of four scattered arrays)
+struct __align__(64) BlockRec { Digest d; uint64_t off; uint32_t len; uint32_t cls; uint64_t pad[2]; };
+
 struct StoreView {
     const uint8_t* blob;      // arena + 16
+    const BlockRec* recs;     // n records (hot lookup path)
     const uint64_t* offsets;
     const uint32_t* lengths;
     const Digest* digests;
@@ -51,10 +56,9 @@ __device__ __forceinline__ int32_t store_find(const StoreView& s, uint32_t cls, 
         if (e == 0) return -1;
         if ((uint32_t)(e >> 32) == fp) {
             uint32_t idx = (uint32_t)e - 1;
-            const Digest* q = s.digests + idx;
-            Digest o;
-            o.w[0] = __ldg(&q->w[0]); o.w[1] = __ldg(&q->w[1]); o.w[2] = __ldg(&q->w[2]); o.w[3] = __ldg(&q->w[3]);
-            if (digest_eq(o, d) && __ldg(s.cls + idx) == cls) return (int32_t)idx;
+            const BlockRec* q = s.recs + idx;
+            const ulonglong2 w0 = __ldg((const ulonglong2*)&q->d), w1 = __ldg((const ulonglong2*)&q->d + 1);   // 2 x 16-byte loads, one sector
+            if (w0.x == d.w[0] && w0.y == d.w[1] && w1.x == d.w[2] && w1.y == d.w[3] && __ldg(&q->cls) == cls) return (int32_t)idx;
         }
         slot = (slot + 1) & s.mask;
     }
@@ -67,8 +71,9 @@ __device__ __forceinline__ int32_t store_lookup(const StoreView& s, const uint8_
     return store_find(s, (uint32_t)c, d);
 }
 __device__ __forceinline__ const uint8_t* store_block(const StoreView& s, uint32_t idx, uint32_t& len) {
-    len = __ldg(s.lengths + idx);
-    return s.blob + __ldg(s.offsets + idx);
+    const BlockRec* q = s.recs + idx;
+    len = __ldg(&q->len);
+    return s.blob + __ldg(&q->off);
 }
 // RecordingBlockStore::get side effect: one bit per block
 __device__ __forceinline__ void witness_mark(uint32_t* wbits, uint32_t idx) {
