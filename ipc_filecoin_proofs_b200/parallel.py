@@ -195,8 +195,22 @@ def raw_position_of(exec_index, dups_sorted):
         p = q
 
 
-def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices, seg_counts=None):
-    """Runs the distributed first-seen dedup and returns (n_exec, {exec_index: 40-byte record}).
+def raw_positions_of(exec_indices, dups_sorted):
+    """Vectorised raw_position_of for a sorted array of exec indices."""
+    i = np.asarray(exec_indices, dtype=np.uint64)
+    if len(dups_sorted) == 0 or len(i) == 0:
+        return i.copy()
+    D = np.asarray(dups_sorted, dtype=np.uint64)
+    p = i.copy()
+    while True:
+        q = i + np.searchsorted(D, p, side="right").astype(np.uint64)
+        if np.array_equal(q, p):
+            return p
+        p = q
+
+
+def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices, seg_counts=None, need_counts=None):
+    """Runs the distributed first-seen dedup and returns (n_exec, (sorted exec indices, their 40-byte records)).
 
     seg_ptr/nseg: this rank's slice of the raw message list (device pointer for CudaShardOps);
     matching: the rank's matching receipt indices (for the MISSING_EXEC check, events/generator.rs:244-246);
@@ -232,32 +246,35 @@ def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indic
             dups, _ = coll.all_gather_var_u64(dups_local)
         else:
             dups = np.concatenate([allp[r, 1:1 + int(allp[r, 0])] for r in range(world)]).view(np.uint64)
-    D = np.sort(dups).tolist()
+    D = np.sort(dups)
     n_exec = nraw - len(D)
     # exec.get(i) must exist for every matching receipt (checked in ascending order by the reference);
     # the verdict travels with the position requests
-    bad = [int(i) for i in matching if int(i) >= n_exec]
-    my_bad = min(bad) if bad else np.iinfo(np.int64).max
-    need = sorted(set(int(i) for i in proof_exec_indices))
-    pos = np.array([raw_position_of(i, D) if i < n_exec else 0 for i in need], dtype=np.uint64)
+    matching = np.asarray(matching, dtype=np.uint64)
+    bad = matching[matching >= np.uint64(n_exec)]
+    my_bad = int(bad.min()) if len(bad) else np.iinfo(np.int64).max
+    need = np.unique(np.asarray(proof_exec_indices, dtype=np.uint64))
+    pos = raw_positions_of(np.minimum(need, np.uint64(max(n_exec, 1) - 1)), D)
     with _Phase("x.req_gather"):
-        hdr = coll.all_gather_i64([len(pos), my_bad])
-        req_counts = hdr[:, 0]
-        first_bad = int(hdr[:, 1].min())
+        if need_counts is None:
+            need_counts = coll.all_gather_i64([len(need)])[:, 0]
+        req_counts = np.asarray(need_counts, dtype=np.int64)
+        capq = int(req_counts.max()) if len(req_counts) else 0
+        padq = np.zeros(capq + 1, dtype=np.int64)      # [MISSING_EXEC verdict, positions…]
+        padq[0] = my_bad
+        padq[1:1 + len(pos)] = pos.view(np.int64)
+        allq = coll.all_gather_i64(padq)
+        first_bad = int(allq[:, 0].min())
         if first_bad != np.iinfo(np.int64).max:
             raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
-        capq = int(req_counts.max()) if len(req_counts) else 0
-        padq = np.zeros(max(capq, 1), dtype=np.int64)
-        padq[:len(pos)] = pos.view(np.int64)
-        allq = coll.all_gather_i64(padq)
-        req_all = np.concatenate([allq[r, :int(req_counts[r])] for r in range(world)]).view(np.uint64) if capq else np.zeros(0, np.uint64)
+        req_all = np.concatenate([allq[r, 1:1 + int(req_counts[r])] for r in range(world)]).view(np.uint64) if capq else np.zeros(0, np.uint64)
     with _Phase("x.fetch"):
         ans = ops.fetch(seg_ptr, nseg, pos0, req_all)                # zeros where another rank owns the position
     with _Phase("x.ans_reduce"):
         ans = coll.all_reduce_sum_i64(ans.reshape(-1).view(np.int64)).view(np.uint8).reshape(-1, REC)
     start = int(req_counts[:rank].sum())
     mine = ans[start:start + len(need)]
-    return n_exec, {i: bytes(mine[k]) for k, i in enumerate(need)}
+    return n_exec, (need, mine)
 
 
 def record_to_cid(rec40):
@@ -275,17 +292,23 @@ def _proofs_view(res_c):
     return np.frombuffer((C.c_uint8 * (n * sz)).from_address(addr), dtype=np.uint8).reshape(n, sz)
 
 
+def records_to_cids(recs):
+    """(k, 40) records → (k, 38) CIDs."""
+    recs = np.asarray(recs, dtype=np.uint8).reshape(-1, REC)
+    return np.concatenate([recs[:, 32:38], recs[:, :32]], axis=1)
+
+
 def patch_message_cids(res_c, msg_of):
-    """Writes EventProof.message_cid of a shard result in place (res_c: EventResultC)."""
+    """Writes EventProof.message_cid of a shard result in place (res_c: EventResultC).
+    msg_of = (sorted exec indices, (k, 40) records)."""
     pv = _proofs_view(res_c)
     if not len(pv):
         return
+    keys, recs = msg_of
     off = A.EventProofC.message_cid.offset
     exec_idx = pv[:, :8].copy().view(np.uint64).reshape(-1)
-    keys = sorted(msg_of)
-    table = np.frombuffer(b"".join(record_to_cid(msg_of[k]) for k in keys), dtype=np.uint8).reshape(-1, 38)
-    where = np.searchsorted(np.array(keys, dtype=np.uint64), exec_idx)
-    pv[:, off:off + 38] = table[where]
+    where = np.searchsorted(np.asarray(keys, dtype=np.uint64), exec_idx)
+    pv[:, off:off + 38] = records_to_cids(recs)[where]
 
 
 def gather_witness_cids(ops, coll, local_sorted_cids, counts=None, device_tensor=None):
@@ -319,7 +342,8 @@ def generate_event_proof_distributed(lib, store_handle, tipset_handle, spec_c, l
     r = out.contents if ok else None
     # one all-gather: status (a failing rank must not leave the others hanging), slice length, witness size
     with _Phase("header_allgather"):
-        hdr = coll.all_gather_i64([st, int(r.shard_exec_count) if ok else 0, int(r.witness.n_blocks) if ok else 0])
+        need = np.unique(_proofs_view(r)[:, :8].copy().view(np.uint64).reshape(-1)) if ok and r.n_proofs else np.zeros(0, np.uint64)
+        hdr = coll.all_gather_i64([st, int(r.shard_exec_count) if ok else 0, int(r.witness.n_blocks) if ok else 0, len(need)])
     worst = int(hdr[:, 0].min())
     if worst != A.OK:
         if not ok:
@@ -327,9 +351,9 @@ def generate_event_proof_distributed(lib, store_handle, tipset_handle, spec_c, l
         lib.ipcfp_event_result_free(out)
         raise A.IpcfpError(worst, "another rank failed", 0xFFFFFFFFFFFFFFFF)
     matching = np.frombuffer((C.c_uint64 * int(r.n_matching)).from_address(r.matching_indices), dtype=np.uint64) if r.n_matching else np.zeros(0, np.uint64)
-    need = _proofs_view(r)[:, :8].copy().view(np.uint64).reshape(-1) if r.n_proofs else np.zeros(0, np.uint64)
     with _Phase("resolve_exec_total"):
-        n_exec, msg_of = resolve_execution_order(ops, coll, r.shard_exec_dev, int(r.shard_exec_count), matching, need, seg_counts=hdr[:, 1])
+        n_exec, msg_of = resolve_execution_order(ops, coll, r.shard_exec_dev, int(r.shard_exec_count), matching, need, seg_counts=hdr[:, 1],
+                                                 need_counts=hdr[:, 3])
     with _Phase("patch"):
         patch_message_cids(r, msg_of)
     with _Phase("witness_union"):

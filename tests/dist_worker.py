@@ -106,8 +106,11 @@ def cpu_worker(rank, world, port, q):
         ops = NumpyShardOps()
         n_exec, msg_of = PL.resolve_execution_order(ops, coll, seg, len(seg), res.matching, [p.exec_index for p in res.proofs])
         assert n_exec == exp.n_exec, (n_exec, exp.n_exec)
+        keys, recs = msg_of
+        cids = PL.records_to_cids(recs)
         for p in res.proofs:
-            assert PL.record_to_cid(msg_of[p.exec_index]) == p.message_cid
+            k = int(np.searchsorted(keys, np.uint64(p.exec_index)))
+            assert int(keys[k]) == p.exec_index and cids[k].tobytes() == p.message_cid
         merged = PL.gather_witness_cids(ops, coll, res.witness.cids)
         assert np.array_equal(np.asarray(merged).reshape(-1, 38), exp.witness.cids)
         # MISSING_EXEC agreement: pretend a receipt index beyond the execution order matched on rank 1

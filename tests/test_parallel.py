@@ -13,6 +13,9 @@ def test_raw_position_arithmetic():
     for i, p in enumerate(kept):
         assert raw_position_of(i, D) == p
     assert raw_position_of(0, []) == 0 and raw_position_of(5, [0, 1, 2]) == 8
+    from ipc_filecoin_proofs_b200.parallel import raw_positions_of
+    assert raw_positions_of(np.arange(len(kept), dtype=np.uint64), np.array(D, dtype=np.uint64)).tolist() == kept
+    assert raw_positions_of(np.array([5], dtype=np.uint64), np.array([0, 1, 2], dtype=np.uint64)).tolist() == [8]
 
 
 def test_cross_shard_protocol_gloo_cpu():
