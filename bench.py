@@ -386,6 +386,10 @@ def run_engine(args, world, rank, local):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else a library prints (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
