@@ -57,9 +57,9 @@ __global__ void k_exec_claim(const ExecEntry* __restrict__ recv, const uint64_t*
     if (k >= total) return;
     const ExecEntry* e = recv_entry(recv, seg_off, world, cap, k);
     uint64_t h = rawcid_hash(e->c);
-    uint32_t fp = (uint32_t)h | 1u;
+    uint32_t fp = (uint32_t)(h >> 40) | 1u;   // bits 40..63: independent of the slot bits
     unsigned long long mine = ((unsigned long long)fp << 32) | (unsigned long long)(k + 1);
-    uint64_t slot = (h >> 20) & mask;
+    uint64_t slot = h & mask;   // low bits: independent of the owner choice ((h >> 32) % world)
     for (;;) {
         unsigned long long v = table[slot];
         if (v == 0) { v = atomicCAS(&table[slot], 0ull, mine); if (v == 0) return; }
@@ -70,8 +70,8 @@ __global__ void k_exec_claim(const ExecEntry* __restrict__ recv, const uint64_t*
 __device__ __forceinline__ uint64_t exec_find_slot(const ExecEntry* recv, const uint64_t* seg_off, uint32_t world, uint64_t cap, const ExecEntry* e,
                                                    const unsigned long long* table, uint64_t mask) {
     uint64_t h = rawcid_hash(e->c);
-    uint32_t fp = (uint32_t)h | 1u;
-    uint64_t slot = (h >> 20) & mask;
+    uint32_t fp = (uint32_t)(h >> 40) | 1u;   // bits 40..63: independent of the slot bits
+    uint64_t slot = h & mask;   // low bits: independent of the owner choice ((h >> 32) % world)
     for (;;) {
         unsigned long long v = table[slot];
         if ((uint32_t)(v >> 32) == fp && rawcid_eq(recv_entry(recv, seg_off, world, cap, (uint32_t)v - 1)->c, e->c)) return slot;
