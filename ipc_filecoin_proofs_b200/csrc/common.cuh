@@ -79,13 +79,21 @@ template <class T> struct AsyncBuf {
 // pinned host scratch for small read-backs (counters, error words)
 template <class T> struct PinnedBuf {
     T* p = nullptr;
+    T* dev = nullptr;   // device-side alias of the same (mapped) host memory
     size_t n = 0;
     PinnedBuf() {}
     explicit PinnedBuf(size_t count) { alloc(count); }
     PinnedBuf(const PinnedBuf&) = delete;
     PinnedBuf& operator=(const PinnedBuf&) = delete;
     ~PinnedBuf() { if (p) cudaFreeHost(p); }
-    void alloc(size_t count) { if (p) cudaFreeHost(p); p = nullptr; n = count; if (count) IPCFP_CUDA(cudaMallocHost((void**)&p, count * sizeof(T))); }
+    void alloc(size_t count) {
+        if (p) cudaFreeHost(p);
+        p = nullptr; dev = nullptr; n = count;
+        if (count) {
+            IPCFP_CUDA(cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocMapped));
+            IPCFP_CUDA(cudaHostGetDevicePointer((void**)&dev, p, 0));
+        }
+    }
     void ensure(size_t count) { if (count > n) alloc(count); }
 };
 

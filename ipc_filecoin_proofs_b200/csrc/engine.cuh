@@ -86,6 +86,10 @@ void hash_batch(int which, const uint8_t* blob, uint64_t blob_size, const uint64
                 uint8_t* out);
 void mapping_slots(const uint8_t* keys32, const uint64_t* slot_indices, uint64_t n, int device, uint8_t* out);
 void check_device(int device);
+// counters dev_words[first, first+count) → host_words (same indices) through mapped host memory: a tiny kernel
+// instead of a D2H copy, so the read-back never queues behind a large copy on the copy engine
+void publish_words(Store* s, uint32_t first, uint32_t count);
+void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint32_t n_words);
 
 // events.cu
 void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td);

@@ -820,13 +820,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
     wbuild.snapshot(wbits.p);
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 2, ccount, 8, cudaMemcpyDeviceToHost, st));
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 8, dw + 8, 8, cudaMemcpyDeviceToHost, st));
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
+    publish_words(s, 0, 16);   // dw[1]/dw[2] hold the frontier counters: ccount is one of them
+    const uint32_t ccount_idx = (uint32_t)(ccount - dw);
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
-    uint64_t nraw = std::min<uint64_t>(hw[2], raw_cap);
+    uint64_t nraw = std::min<uint64_t>(hw[ccount_idx], raw_cap);
     wbuild.start_copy(hw[8]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
@@ -863,7 +862,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     bitmap_to_indices(match_bits.p, (N + 31) / 32 * 32, match_rel.p, (uint64_t*)n_match_dev, wp3.p, scratch.p, st);
     exclusive_scan_u32(cnt.p, pbase.p, N, (uint64_t*)(dw + 7), scratch.p, st);
     exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 14 * 8, cudaMemcpyDeviceToHost, st));
+    publish_words(s, 0, 16);
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     const uint64_t n_exec = hw[3], M = hw[6];
@@ -886,12 +885,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
     wbuild.finish_enqueue(wbits.p);
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 14 * 8, cudaMemcpyDeviceToHost, st));
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 20, any_skip_dev, 4, cudaMemcpyDeviceToHost, st));
+    publish_words(s, 0, 16);
+    publish_words_from(s, misc.p, 20, 2);   // misc[2] = any_skip (32-bit words 0..3 land in hw[20..21])
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     const uint64_t mB = hw[10];
-    const bool any_skip = (*(const uint32_t*)(hw + 20)) != 0;
+    const bool any_skip = ((const uint32_t*)(hw + 20))[2] != 0;
     IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
 
     // ---- results to the host

@@ -113,6 +113,20 @@ __global__ void __launch_bounds__(128) k_verify_cids(StoreView v, uint32_t lo, u
     if (!digest_eq(d, v.digests[i])) atomicMin(first_bad, (unsigned long long)i);
 }
 
+__global__ void k_publish(const unsigned long long* __restrict__ src, unsigned long long* dst, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    __threadfence_system();
+}
+void publish_words(Store* s, uint32_t first, uint32_t count) {
+    k_publish<<<div_up(count, 64), 64, 0, s->stream>>>(s->dev_words.p + first, (unsigned long long*)s->host_words.dev + first, count);
+    IPCFP_LAUNCH_CHECK();
+}
+void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint32_t n_words) {
+    k_publish<<<div_up(n_words, 64), 64, 0, s->stream>>>((const unsigned long long*)src_dev, (unsigned long long*)s->host_words.dev + dst_first, n_words);
+    IPCFP_LAUNCH_CHECK();
+}
+
 __global__ void k_lookup_one(StoreView v, const uint8_t* cid, int32_t* out) { out[0] = store_lookup(v, cid); }
 
 // ------------------------------------------------------------------------------------------ host side

@@ -161,7 +161,7 @@ void WitnessBuilder::start_copy(uint64_t mA_) {
     unsigned long long* dw = s->dev_words.p;
     if (mA) { k_padded_lengths<<<div_up(mA, 256), 256, 0, st>>>(idx.p, mA, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
     exclusive_scan_u32(plen.p, offs.p, mA, (uint64_t*)(dw + 9), scratch.p, st);
-    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 9, dw + 9, 8, cudaMemcpyDeviceToHost, st));
+    publish_words(s, 9, 1);
     IPCFP_CUDA(cudaStreamSynchronize(st));
     bytesA = s->host_words.p[9];
     host_cap = bytesA + bytesA / 8 + (8u << 20);
@@ -191,7 +191,7 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
     if (mB) {
         k_padded_lengths<<<div_up(mB, 256), 256, 0, st>>>(idx.p + mA, mB, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK();
         exclusive_scan_u32(plen.p, offs.p + mA, mB, (uint64_t*)(dw + 11), scratch.p, st);
-        IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 11, dw + 11, 8, cudaMemcpyDeviceToHost, st));
+        publish_words(s, 11, 1);
         IPCFP_CUDA(cudaStreamSynchronize(st));
         bytesB = s->host_words.p[11];
     }
@@ -239,7 +239,7 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
 void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out) {
     WitnessBuilder wb(s);
     wb.snapshot(wbits_dev);
-    IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p + 8, s->dev_words.p + 8, 8, cudaMemcpyDeviceToHost, s->stream));
+    publish_words(s, 8, 1);
     IPCFP_CUDA(cudaStreamSynchronize(s->stream));
     wb.start_copy(s->host_words.p[8]);
     wb.finish(0, out);
