@@ -147,14 +147,17 @@ __device__ __forceinline__ uint64_t load_u64_any(const uint8_t* q) {
     uint64_t x0 = b[0], x1 = b[1];
     return (x0 >> s) | ((x1 << 1) << (63 - s));
 }
-// 16 bytes at any alignment with three aligned 8-byte loads
+// 16 bytes at any alignment with three aligned 8-byte loads; the byte shift is one word select
+// (shift >= 32 bits) plus four 32-bit funnel shifts (shf.r.wrap takes the shift mod 32)
 __device__ __forceinline__ void win_load(const uint8_t* q, uint64_t& w0, uint64_t& w1) {
     uintptr_t a = (uintptr_t)q;
-    const uint64_t* b = (const uint64_t*)(a & ~(uintptr_t)7);
+    const uint2* b = (const uint2*)(a & ~(uintptr_t)7);
     uint32_t s = (uint32_t)(a & 7) * 8;
-    uint64_t x0 = b[0], x1 = b[1], x2 = b[2];
-    w0 = (x0 >> s) | ((x1 << 1) << (63 - s));
-    w1 = (x1 >> s) | ((x2 << 1) << (63 - s));
+    uint2 x0 = b[0], x1 = b[1], x2 = b[2];
+    bool up = (s & 32) != 0;
+    uint32_t c0 = up ? x0.y : x0.x, c1 = up ? x1.x : x0.y, c2 = up ? x1.y : x1.x, c3 = up ? x2.x : x1.y, c4 = up ? x2.y : x2.x;
+    w0 = (uint64_t)__funnelshift_r(c0, c1, s) | ((uint64_t)__funnelshift_r(c1, c2, s) << 32);
+    w1 = (uint64_t)__funnelshift_r(c2, c3, s) | ((uint64_t)__funnelshift_r(c3, c4, s) << 32);
 }
 __device__ __forceinline__ Digest load_digest(const uint8_t* p) {
     uintptr_t a = (uintptr_t)p;
@@ -167,6 +170,7 @@ __device__ __forceinline__ Digest load_digest(const uint8_t* p) {
     return d;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 }  // namespace ipcfp

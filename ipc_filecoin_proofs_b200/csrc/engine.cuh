@@ -56,6 +56,7 @@ struct Store {
     // small persistent scratch
     DevBuf<unsigned long long> dev_words;  // [0] error word, [1..] counters
     PinnedBuf<uint64_t> host_words;
+    PinnedBuf<uint8_t> stage;              // pinned staging for small per-call uploads (spec, tipset CIDs, walk tables): no host sync needed
     cudaEvent_t ev[8] = {};
     ~Store();
     void use() const { IPCFP_CUDA(cudaSetDevice(device)); }
@@ -134,7 +135,7 @@ struct WitnessBuilder {
     PinnedArray host_blob;
     explicit WitnessBuilder(Store* store);
     void snapshot(const uint32_t* wbits);        // enqueue; count → dev_words[8]
-    void start_copy(uint64_t mA);                // gather + D2H of the snapshot on the side stream
+    void start_copy(uint64_t mA, uint64_t bytesA);  // host knows the counts: gather + D2H on the side stream
     void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10]
     void finish(uint64_t mB, WitnessOut& out);   // late blocks, Cid-order index arrays, join
 };

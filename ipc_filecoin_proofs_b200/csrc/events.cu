@@ -64,9 +64,13 @@ __device__ __forceinline__ void emit_proof(const uint8_t* p, const EvLog& ev, ui
 // Decodes the values of one events-AMT node. Returns false on a decode error (r.err set).
 template <int MODE>
 __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNodeHdr& h, uint32_t nv, uint64_t base, const Matcher& m,
-                                            WalkOut& wo, EmitCtx* ec) {
+                                            WalkOut& wo, EmitCtx* ec, uint32_t tune = 0) {
     for (uint32_t v = 0; v < nv && !r.err; v++) {
-        if (r.pos + 384 < r.n) prefetch_l2(r.p + r.pos + 384);  // rolling prefetch: ~3 lines ahead of the dependent walk
+        // rolling prefetch: 2 lines ahead of the dependent walk — measured best of 0/2/3/4/6 (profiles/r1_pass1_prefetch_sweep.txt);
+        // IPCFP_PASS1_TUNE: bits 4..7 = other distance in lines, bit 1 = off
+        const uint32_t ahead = (tune >> 4) & 15u ? 128u * ((tune >> 4) & 15u) : 256u;
+        if (!(tune & 2) && r.pos + ahead < r.n) prefetch_l2(r.p + r.pos + ahead);
+        if ((tune & 1) && r.pos + 128 < r.n) prefetch_l1(r.p + r.pos + 128);  // experiment: next line into L1
         EvLog ev;
         decode_stamped_event(r, ev);
         if (r.err) break;
@@ -137,6 +141,7 @@ struct Pass1Args {
     uint32_t* nbytes;              // [i - lo] topics+data bytes of those events
     unsigned long long* err;
     unsigned long long* stats;     // [0] nodes scanned, [1] bytes scanned
+    uint32_t tune;                 // experiment bits (env IPCFP_PASS1_TUNE), 0 = default
 };
 
 // One thread per receipt: resolve its events root CID, decode the root node of its events AMT,
@@ -158,7 +163,8 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
     const uint8_t* p = nullptr;
     if (blk >= 0) {
         p = store_block(a.store, (uint32_t)blk, len);
-        for (uint32_t o = 0; o < len && o < 512; o += 128) prefetch_l2(p + o);  // first lines in flight before the dependent walk
+        const uint32_t first = (a.tune & 4) ? 2048u : ((a.tune & 8) ? 256u : 512u);
+        for (uint32_t o = 0; o < len && o < first; o += 128) prefetch_l2(p + o);  // first lines in flight before the dependent walk
     }
     __syncwarp();
     // phase 2: decode the root node, test every event
@@ -172,7 +178,7 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
         amt_node_begin(r, bw, h);
         uint32_t nv = rd_array(r);
         WalkOut wo{0, 0, false};
-        node_events<WALK_COUNT>(r, p, h, nv, 0, a.m, wo, nullptr);
+        node_events<WALK_COUNT>(r, p, h, nv, 0, a.m, wo, nullptr, a.tune);
         amt_node_finish(r, h, nv, height);
         if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
         else if (h.nl) {
@@ -192,7 +198,7 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
     if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(a.stats, (unsigned long long)nodes); atomicAdd(a.stats + 1, (unsigned long long)bytes); }
 }
 // the same kernel at three register budgets (resident CTAs per SM: 6 → 80 regs, 8 → 64, 10 → 48);
-// IPCFP_PASS1_MINB selects one at run time for tuning, 6 is the measured default
+// IPCFP_PASS1_MINB selects one at run time for tuning, 8 is the measured default
 __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 8) k_pass1_occ8(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 10) k_pass1_occ10(Pass1Args a) { pass1_body(a); }
@@ -310,30 +316,38 @@ struct SetupArgs {
     uint32_t* amt_height;   // per AMT
     uint64_t* amt_count;    // per AMT (root.count)
     uint32_t* missing_base; // flag: a base-witness CID is not in the store (→ materialize error)
+    const uint8_t* sig;     // event signature bytes (zero padded to a multiple of 8) and the Matcher whose t0 this kernel fills
+    uint32_t sig_len;
+    Matcher* matcher;
 };
 // meta of a frontier item: amt ordinal << 16 | is_root << 8 | level
 __device__ __forceinline__ uint32_t make_meta(uint32_t amt, uint32_t is_root, uint32_t level) { return (amt << 16) | (is_root << 8) | level; }
 
-// Single-thread prologue: marks the base witness, decodes each parent's TxMeta, loads (and
-// validates) the receipts-AMT root and the BLS/SECP AMT roots, seeds the BFS frontier.
-__global__ void k_setup(SetupArgs a) {
-    if (threadIdx.x || blockIdx.x) return;
+// One-CTA prologue, the independent pieces on different warps so their dependent lookups overlap:
+//   thread 0        Amtv0::<MessageReceipt>::load(&receipts_root) (events/generator.rs:195-196), root validated
+//   threads 32..95  one parent each: TxMeta → BLS / SECP AMT roots (seeds the walk frontier, AMT ordinal 2b + k)
+//   thread 96       keccak256(event_signature) → Matcher.t0 (EventMatcher::new, events/generator.rs:30-35)
+//   threads 128..   base witness marks (parent headers, child header, receipts root, TxMeta blocks)
+// Errors go through the atomicMin error word, so the one reported is the one the sequential order meets first.
+__global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
     const StoreView& s = a.store;
-    uint32_t namt = 0;
-    if (!a.skip_tx) {
-        auto base = [&](const uint8_t* cid) {
+    const uint32_t t = threadIdx.x, P = a.n_parents;
+    if (t >= 128 && !a.skip_tx) {
+        for (uint32_t i = t - 128; i < 2 * P + 2; i += 128) {
+            const uint8_t* cid = i < P ? a.parent_cids + 38 * i : (i == P ? a.child_cid : (i == P + 1 ? a.receipts_root : a.txmeta_cids + 38 * (i - P - 2)));
             int32_t b = store_lookup(s, cid);
             if (b < 0) *a.missing_base = 1; else witness_mark(a.wbits, (uint32_t)b);
-        };
-        for (uint32_t b = 0; b < a.n_parents; b++) base(a.parent_cids + 38 * b);
-        base(a.child_cid);
-        base(a.receipts_root);
-        for (uint32_t b = 0; b < a.n_parents; b++) base(a.txmeta_cids + 38 * b);
+        }
+    }
+    if (t == 96) {
+        Digest d;
+        keccak256(a.sig, a.sig_len, d);
+        a.matcher->t0[0] = d.w[0]; a.matcher->t0[1] = d.w[1]; a.matcher->t0[2] = d.w[2]; a.matcher->t0[3] = d.w[3];
     }
     // TxMeta + message AMT roots (needed for the execution order even when skip_tx)
-    for (uint32_t b = 0; b < a.n_parents; b++) {
+    if (t >= 32 && t < 96) for (uint32_t b = t - 32; b < P; b += 64) {
         int32_t tb = store_lookup(s, a.txmeta_cids + 38 * b);
-        if (tb < 0) { report_error(a.err, ST_TXMETA, 3 * b, DC_MISSING, 0); return; }
+        if (tb < 0) { report_error(a.err, ST_TXMETA, 3 * b, DC_MISSING, 0); continue; }
         if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)tb);
         uint32_t len;
         const uint8_t* p = store_block(s, (uint32_t)tb, len);
@@ -341,10 +355,10 @@ __global__ void k_setup(SetupArgs a) {
         rd_array_exact(r, 2);
         uint32_t c0 = rd_cid(r), c1 = rd_cid(r);
         rd_end(r);
-        if (r.err) { report_error(a.err, ST_TXMETA, 3 * b, DC_DECODE, r.err); return; }
+        if (r.err) { report_error(a.err, ST_TXMETA, 3 * b, DC_DECODE, r.err); continue; }
         for (uint32_t k = 0; k < 2; k++) {
             int32_t rb = store_lookup(s, p + (k ? c1 : c0));
-            if (rb < 0) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_MISSING, 0); return; }
+            if (rb < 0) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_MISSING, 0); break; }
             if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)rb);
             uint32_t rl;
             const uint8_t* rp = store_block(s, (uint32_t)rb, rl);
@@ -352,16 +366,17 @@ __global__ void k_setup(SetupArgs a) {
             uint32_t bw, h;
             uint64_t cnt;
             amt_root_begin(rr, 0, bw, h, cnt);
-            if (rr.err) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_DECODE, rr.err); return; }
-            a.f_blk[namt] = (uint32_t)rb;
-            a.f_meta[namt] = make_meta(namt, 1, h);
-            a.f_base[namt] = 0;
-            a.amt_height[namt] = h;
-            a.amt_count[namt] = cnt;
-            namt++;
+            if (rr.err) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_DECODE, rr.err); break; }
+            const uint32_t amt = 2 * b + k;
+            a.f_blk[amt] = (uint32_t)rb;
+            a.f_meta[amt] = make_meta(amt, 1, h);
+            a.f_base[amt] = 0;
+            a.amt_height[amt] = h;
+            a.amt_count[amt] = cnt;
         }
     }
-    *a.f_count = namt;
+    if (t != 0) return;
+    *a.f_count = 2 * P;
     // Amtv0::<MessageReceipt>::load(&receipts_root, &rec_receipts) (events/generator.rs:195-196)
     int32_t rb = store_lookup(s, a.receipts_root);
     if (rb < 0) { report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_MISSING, 0); return; }
@@ -437,12 +452,16 @@ struct ExpandArgs {
     const uint64_t* rlo;       // per message AMT: index range this call walks
     const uint64_t* rhi;
 };
-__device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t, uint32_t blk, uint32_t meta, uint64_t base, uint32_t expect) {
+// Eight lanes per frontier item (a bw-3 node has ≤ 8 links or values). Every lane runs the same strict decode of
+// the node (same bytes → one memory transaction per group; the decode is a few hundred instructions), then lane j
+// resolves link j (hash probe + witness mark) or copies value j — the eight dependent store lookups of a node
+// proceed in parallel instead of back to back. No lane depends on another, so there is no intra-group sync.
+__device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t, uint32_t j, uint32_t blk, uint32_t meta, uint64_t base, uint32_t expect) {
     if (meta == AMT_SENTINEL) return;
     uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
     uint64_t o = a.out_off[t];
     if (level == 0 && a.round < a.last_round) {  // park
-        if (o < a.cap) { a.out.blk[o] = blk; a.out.meta[o] = meta; a.out.base[o] = base; }
+        if (j == 0 && o < a.cap) { a.out.blk[o] = blk; a.out.meta[o] = meta; a.out.base[o] = base; }
         return;
     }
     uint32_t len;
@@ -456,37 +475,40 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
     for (uint32_t v = 0; v < nv && !r.err; v++) (void)rd_cid(r);
     amt_node_finish(r, h, nv, level);
     uint64_t eidx = 3ull * (amt >> 1) + 1 + (amt & 1);
-    uint32_t produced = 0;
     const uint32_t smask = slot_mask(base, level, a.rlo[amt], a.rhi[amt]);
-    if (r.err) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err);
-    else if (h.nl) {
-        for (uint32_t k = 0; k < h.nl && produced < expect; k++) {
-            uint32_t slot = bm_select(h.bm, k);
-            if (!((smask >> slot) & 1)) continue;
-            int32_t child = store_lookup(a.store, p + h.links_off + 43 * k + 5);
-            uint64_t d = o + produced;
-            if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
-            else {
-                if (a.record) witness_mark(a.wbits, (uint32_t)child);
-                if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
+    const uint32_t bm8 = (uint32_t)h.bm.b0 & 0xffu;
+    uint32_t produced = 0;   // outputs of the whole node (same value in every lane)
+    if (r.err) { if (j == 0) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err); }
+    else if (h.nl || a.round == a.last_round) {
+        produced = (uint32_t)__popc(bm8 & smask);
+        if (produced > expect) produced = expect;
+        const uint32_t n_items = h.nl ? h.nl : nv;                 // == popc(bm8) after amt_node_finish
+        if (j < n_items) {
+            uint32_t slot = bm_select(h.bm, j);
+            uint32_t rank = (uint32_t)__popc(bm8 & smask & ((1u << slot) - 1u));   // selected items before this one
+            if (((smask >> slot) & 1) && rank < expect) {
+                uint64_t d = o + rank;
+                if (h.nl) {
+                    int32_t child = store_lookup(a.store, p + h.links_off + 43 * j + 5);
+                    if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
+                    else {
+                        if (a.record) witness_mark(a.wbits, (uint32_t)child);
+                        if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
+                    }
+                } else {
+                    const uint8_t* src = p + vals_off + 43 * j + 5;
+                    RawCid c;
+                    c.w[4] = load_u64_any(src) & 0xffffffffffffull;
+                    Digest dg = load_digest(src + 6);
+                    c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
+                    a.vals[d] = c;
+                }
             }
-            produced++;
-        }
-    } else if (a.round == a.last_round) {
-        for (uint32_t v = 0; v < nv && produced < expect; v++) {
-            if (!((smask >> bm_select(h.bm, v)) & 1)) continue;
-            const uint8_t* src = p + vals_off + 43 * v + 5;
-            RawCid c;
-            c.w[4] = load_u64_any(src) & 0xffffffffffffull;
-            Digest dg = load_digest(src + 6);
-            c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
-            a.vals[o + produced] = c;
-            produced++;
         }
     }
     // slots promised by the count pass but not produced (malformed node): neutralise them
-    if (a.round < a.last_round) for (uint32_t k = produced; k < expect; k++) if (o + k < a.cap) a.out.meta[o + k] = AMT_SENTINEL;
-    if (a.round == a.last_round) for (uint32_t k = produced; k < expect; k++) { RawCid z{}; a.vals[o + k] = z; }
+    if (a.round < a.last_round) for (uint32_t k = produced + j; k < expect; k += 8) if (o + k < a.cap) a.out.meta[o + k] = AMT_SENTINEL;
+    if (a.round == a.last_round) for (uint32_t k = produced + j; k < expect; k += 8) { RawCid z{}; a.vals[o + k] = z; }
 }
 
 __global__ void __launch_bounds__(128) k_amt_count(StoreView store, Frontier in, const unsigned long long* in_count, uint32_t round, uint32_t last_round,
@@ -498,16 +520,18 @@ __global__ void __launch_bounds__(128) k_amt_count(StoreView store, Frontier in,
     counts[t] = amt_item_count(store, in.blk[t], in.meta[t], in.base[t], round, last_round, rlo, rhi);
 }
 __global__ void __launch_bounds__(128) k_amt_expand(ExpandArgs a, const uint32_t* counts, unsigned long long* out_count, const unsigned long long* total) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = g >> 3;          // frontier item
+    const uint32_t j = (uint32_t)g & 7; // lane of the item
     uint64_t cnt = *a.in_count;
     if (cnt > a.cap) cnt = a.cap;
-    if (t == 0) {
+    if (g == 0) {
         unsigned long long n = *total;
         if (a.round < a.last_round && n > a.cap) { report_error(a.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = a.cap; }
         *out_count = n;
     }
     if (t >= cnt) return;
-    amt_item_expand(a, t, a.in.blk[t], a.in.meta[t], a.in.base[t], counts[t]);
+    amt_item_expand(a, t, j, a.in.blk[t], a.in.meta[t], a.in.base[t], counts[t]);
 }
 
 // Rounds whose frontier is guaranteed to fit one CTA (≤ 1024 items) run fused in a single launch:
@@ -545,7 +569,7 @@ __global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier pin
         __syncthreads();
         ExpandArgs a = a0;
         a.in = cur; a.out = nxt; a.round = round; a.out_off = scan_tmp;
-        if (t < cnt) amt_item_expand(a, t, cur.blk[t], cur.meta[t], cur.base[t], s_cnt[t]);
+        for (uint32_t it = t >> 3; it < cnt; it += TOP_CAP / 8) amt_item_expand(a, it, t & 7, cur.blk[it], cur.meta[it], cur.base[it], s_cnt[it]);
         __syncthreads();
         if (t == 0) {
             unsigned long long n = s_total;
@@ -555,6 +579,92 @@ __global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier pin
         __threadfence();
         __syncthreads();
         Frontier tmp = cur; cur = nxt; nxt = tmp;
+    }
+}
+
+// ---- dense message-AMT walk ---------------------------------------------------------------------------------
+// Message AMTs are built from arrays: index i of an AMT with `count` values exists iff i < count. While every
+// node's bitmap agrees with that (checked node by node), the position of a node inside its level and of a value
+// inside the execution list is plain index arithmetic, so a level is ONE launch — no count pass, no scan — and
+// the number of raw entries is known to the host up front. Any surprise (a bitmap that differs, a decode error,
+// a missing block) only raises `fail`: the host then re-walks with the general count → scan → expand kernels
+// above, which handle sparse AMTs and produce the error the reference's sequential walk would report.
+struct DenseArgs {
+    StoreView store;
+    Frontier ping, pong;     // round r reads (r even ? ping : pong) and writes the other
+    RawCid* vals;
+    const uint32_t* fofs;    // [(rounds) * namt] first frontier position of each AMT in each round
+    const uint32_t* ftot;    // [rounds] frontier items per round
+    const uint64_t* vbase;   // per AMT: position of its first owned value in vals
+    const uint64_t* cnt;     // per AMT: root.count
+    const uint64_t* lo;      // per AMT: owned index range [lo, hi) ⊆ [0, count)
+    const uint64_t* hi;
+    uint32_t namt, record;
+    uint32_t* wbits;
+    uint32_t* fail;
+};
+// Eight lanes per node. The walk only has to DETECT anything unusual, not name it, so instead of the sequential
+// strict decoder the node is matched against the one byte layout a bw-3 node the strict decoder accepts can have:
+//     83  41 <bitmap>  8<nl> <nl × 43-byte link>  8<nv> <nv × 43-byte link>  <end>     (root: 83 <height> <count> first)
+// with every link  d8 2a 58 27 00 01 …  — all lanes check the frame, lane j checks (and then resolves or copies) item j.
+// Whatever this accepts the strict decoder accepts with the same meaning; whatever it rejects goes to the general walk.
+__device__ __forceinline__ void amt_item_dense(const DenseArgs& a, const Frontier& in, const Frontier& out, uint32_t round, uint32_t it, uint32_t j) {
+    const uint32_t blk = in.blk[it], meta = in.meta[it];
+    const uint64_t base = in.base[it];
+    const uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    uint32_t len;
+    const uint8_t* p = store_block(a.store, blk, len);
+    uint32_t q0 = 0;                                    // offset of the node inside the block
+    if (is_root) {
+        Rd r(p, len);
+        uint32_t bw, h; uint64_t c;
+        amt_root_begin(r, 0, bw, h, c);
+        if (r.err) { *a.fail = 1; return; }
+        q0 = r.pos;
+    }
+    if (len < q0 + 5) { *a.fail = 1; return; }
+    const uint8_t* q = p + q0;
+    const uint32_t nlen = len - q0;
+    const uint32_t w = (uint32_t)load_u64_any(q);       // 83 41 bm 8n
+    const uint32_t bm8 = (w >> 16) & 0xffu, nl = (w >> 24) - 0x80u;
+    if ((w & 0xffffu) != 0x4183u || nl > 8u || 4u + 43u * nl >= nlen) { *a.fail = 1; return; }
+    const uint32_t nv = (uint32_t)q[4 + 43 * nl] - 0x80u;
+    if (nv > 8u || nlen != 5u + 43u * (nl + nv) || (nl && nv) || (nl && level == 0) || (nv && level != 0) || (uint32_t)__popc(bm8) != nl + nv) { *a.fail = 1; return; }
+    const uint64_t cnt = a.cnt[amt], lo = a.lo[amt], hi = a.hi[amt];
+    const uint32_t sh = 3 * level;                      // a child (a value at level 0) spans 2^sh indices; the host admits sh ≤ 60 only
+    uint32_t n_exp = 0;                                 // slots a dense AMT has under this node
+    if (cnt > base) { uint64_t n = ((cnt - base - 1) >> sh) + 1; n_exp = n > 8 ? 8u : (uint32_t)n; }
+    if (bm8 != (1u << n_exp) - 1u || (level ? nl : nv) != n_exp) { *a.fail = 1; return; }
+    if (j >= n_exp) return;
+    const uint8_t* item = q + (level ? 4u : 5u) + 43u * j;   // link j (nv == 0) or value j (nl == 0)
+    if ((load_u64_any(item) & 0xffffffffffffull) != 0x010027582ad8ull) { *a.fail = 1; return; }   // d8 2a 58 27 00 01
+    const uint64_t cb = base + ((uint64_t)j << sh), ce = cb + (1ull << sh);   // indices under slot j
+    if (!(cb < hi && ce > lo)) return;                  // not in this call's share
+    if (level) {
+        int32_t child = store_lookup(a.store, item + 5);
+        if (child < 0) { *a.fail = 1; return; }
+        if (a.record) witness_mark(a.wbits, (uint32_t)child);
+        const uint64_t d = (uint64_t)a.fofs[(round + 1) * a.namt + amt] + ((cb >> sh) - (lo >> sh));
+        out.blk[d] = (uint32_t)child; out.meta[d] = make_meta(amt, 0, level - 1); out.base[d] = cb;
+    } else {
+        const uint8_t* src = item + 5;
+        RawCid c;
+        c.w[4] = load_u64_any(src) & 0xffffffffffffull;
+        Digest dg = load_digest(src + 6);
+        c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
+        a.vals[a.vbase[amt] + (cb - lo)] = c;
+    }
+}
+// n_rounds == 1: any grid. n_rounds > 1: ONE CTA walks several small levels back to back (barrier between levels).
+__global__ void __launch_bounds__(1024) k_amt_dense(DenseArgs a, uint32_t first_round, uint32_t n_rounds) {
+    for (uint32_t rr = 0; rr < n_rounds; rr++) {
+        const uint32_t round = first_round + rr;
+        if (*(volatile uint32_t*)a.fail) return;        // same value in every thread: written before the previous barrier / launch
+        const Frontier in = (round & 1) ? a.pong : a.ping, out = (round & 1) ? a.ping : a.pong;
+        const uint64_t n8 = (uint64_t)a.ftot[round] * 8;
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (uint64_t)gridDim.x * blockDim.x)
+            amt_item_dense(a, in, out, round, (uint32_t)(g >> 3), (uint32_t)g & 7);
+        if (n_rounds > 1) { __threadfence(); __syncthreads(); }
     }
 }
 
@@ -655,13 +765,6 @@ void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
     }
 }
 
-// keccak256(event_signature) on the device (EventMatcher::new, events/generator.rs:30-35)
-__global__ void k_make_matcher(const uint8_t* sig, uint32_t len, Matcher* out) {
-    Digest d;
-    keccak256(sig, len, d);
-    out->t0[0] = d.w[0]; out->t0[1] = d.w[1]; out->t0[2] = d.w[2]; out->t0[3] = d.w[3];
-}
-
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*/, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
                                          bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/) {
     s->use();
@@ -691,27 +794,32 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         mh.actor = spec->actor_id_filter;
         mh.has_actor = spec->has_actor_id_filter ? 1 : 0;
     }
-    size_t siglen = strlen(spec->event_signature);
-    AsyncBuf<uint8_t> small(4096 + siglen + 38ull * (2 * td.n_parents + 2), st);
+    // spec + tipset CIDs go up in ONE copy from the store's pinned staging block (no host sync):
+    //   [0,1024) Matcher (t0 is filled in on the device) | signature, zero padded | parent, TxMeta, child, receipts-root CIDs
+    const size_t siglen = strlen(spec->event_signature);
+    const size_t sig_cap = (siglen + 64) & ~(size_t)63;
+    const size_t cids_bytes = 38ull * (2 * td.n_parents + 2);
+    const size_t small_bytes = 1024 + sig_cap + cids_bytes + 64;
+    static_assert(sizeof(Matcher) <= 1024, "Matcher must fit its staging slot");
+    const size_t STAGE_TABLES = 32768;                    // second half of the staging block: dense-walk tables
+    const size_t tables_off = std::max<size_t>(STAGE_TABLES, (small_bytes + 63) & ~(size_t)63);
+    s->stage.ensure(tables_off + STAGE_TABLES);
+    AsyncBuf<uint8_t> small(small_bytes, st);
     uint8_t* d_sig = small.p + 1024;                       // 8-byte aligned
-    uint8_t* d_cids = small.p + 1024 + ((siglen + 64) & ~(size_t)63);
+    uint8_t* d_cids = small.p + 1024 + sig_cap;
     Matcher* d_matcher = (Matcher*)small.p;
     {
-        std::vector<uint8_t> hb(siglen + 16, 0);
-        memcpy(hb.data(), spec->event_signature, siglen);
-        IPCFP_CUDA(cudaMemcpyAsync(d_sig, hb.data(), siglen + 16, cudaMemcpyHostToDevice, st));
-        std::vector<uint8_t> cb;
-        cb.insert(cb.end(), td.parent_cids.begin(), td.parent_cids.end());
-        cb.insert(cb.end(), td.txmeta_cids.begin(), td.txmeta_cids.end());
-        cb.insert(cb.end(), td.child_cid, td.child_cid + 38);
-        cb.insert(cb.end(), td.receipts_root, td.receipts_root + 38);
-        IPCFP_CUDA(cudaMemcpyAsync(d_cids, cb.data(), cb.size(), cudaMemcpyHostToDevice, st));
-        IPCFP_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
+        uint8_t* hs = s->stage.p;
+        memset(hs, 0, small_bytes);
+        memcpy(hs, &mh, sizeof(Matcher));
+        memcpy(hs + 1024, spec->event_signature, siglen);
+        uint8_t* hc = hs + 1024 + sig_cap;
+        memcpy(hc, td.parent_cids.data(), td.parent_cids.size()); hc += td.parent_cids.size();
+        memcpy(hc, td.txmeta_cids.data(), td.txmeta_cids.size()); hc += td.txmeta_cids.size();
+        memcpy(hc, td.child_cid, 38); hc += 38;
+        memcpy(hc, td.receipts_root, 38);
+        IPCFP_CUDA(cudaMemcpyAsync(small.p, hs, small_bytes, cudaMemcpyHostToDevice, st));
     }
-    IPCFP_CUDA(cudaMemcpyAsync(d_matcher, &mh, sizeof(Matcher), cudaMemcpyHostToDevice, st));
-    IPCFP_CUDA(cudaStreamSynchronize(st));
-    k_make_matcher<<<1, 1, 0, st>>>(d_sig, (uint32_t)siglen, d_matcher); IPCFP_LAUNCH_CHECK();
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 16, d_matcher, 32, cudaMemcpyDeviceToHost, st));
 
     // ---- witness bitmap + setup
     AsyncBuf<uint32_t> wbits((nblk + 31) / 32 + 8, st);
@@ -731,7 +839,9 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     sa.receipts_root_blk = misc.p; sa.missing_base = misc.p + 1; sa.amt_height = misc.p + 64;
     sa.f_blk = fA_blk.p; sa.f_meta = fA_meta.p; sa.f_base = fA_base.p; sa.f_count = dw + 1;
     sa.amt_count = amt_count.p;
-    k_setup<<<1, 32, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();
+    sa.sig = d_sig; sa.sig_len = (uint32_t)siglen; sa.matcher = d_matcher;
+    k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 16, d_matcher, 32, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw + 24, misc.p, (64 + 2 * IPCFP_MAX_PARENTS) * 4, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw + 128, amt_count.p, 2 * IPCFP_MAX_PARENTS * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16, cudaMemcpyDeviceToHost, st));
@@ -771,62 +881,146 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
             h_rng[k] = l; h_rng[2 * IPCFP_MAX_PARENTS + k] = h;
         }
     }
-    AsyncBuf<uint64_t> d_rng(4 * IPCFP_MAX_PARENTS, st);
-    IPCFP_CUDA(cudaMemcpyAsync(d_rng.p, h_rng.data(), h_rng.size() * 8, cudaMemcpyHostToDevice, st));
-    IPCFP_CUDA(cudaStreamSynchronize(st));
     AsyncBuf<uint32_t> counts(cap + 1024, st);
     AsyncBuf<uint64_t> out_off(cap + 1024, st), scratch(scan_scratch_elems(std::max<uint64_t>(cap, N) + 64) + 64, st);
-    Frontier fcur{fA_blk.p, fA_meta.p, fA_base.p}, fnxt{fB_blk.p, fB_meta.p, fB_base.p};
     unsigned long long *ccount = dw + 1, *ncount = dw + 2, *total_dev = dw + 13;
-    ExpandArgs ea;
-    ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw;
-    ea.vals = nullptr; ea.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
-    ea.rlo = d_rng.p; ea.rhi = d_rng.p + 2 * IPCFP_MAX_PARENTS;
-    // static frontier bound per round: namt * 8^round
-    auto bound_of = [&](uint32_t round) { uint64_t b = namt; for (uint32_t k = 0; k < round && b <= cap; k++) b *= 8; return std::min<uint64_t>(b, cap); };
+    const uint32_t frontier_cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
     AsyncBuf<RawCid> exec_raw;
     uint64_t raw_cap = 0;
-    auto alloc_vals = [&]() {
-        raw_cap = std::min<uint64_t>(bound_of(last_round) * 8, 8 * cap);
+
+    // ---- (a) dense walk: plan the level layout on the host (see k_amt_dense)
+    struct DensePlan { bool ok = false; uint32_t rounds = 0; uint64_t nraw = 0; std::vector<uint32_t> fofs, ftot; std::vector<uint64_t> per_amt; } plan;
+    {
+        const uint64_t* cnts = (const uint64_t*)(hw + 128);
+        const bool force_general = getenv("IPCFP_BFS_GENERAL") != nullptr;   // read per call: tests toggle it
+        bool ok = namt > 0 && namt <= namt_max && !force_general;
+        for (uint32_t k = 0; ok && k < namt; k++) ok = misc_h[64 + k] <= 20 && cnts[k] <= (1ull << 40);
+        if (ok) {
+            plan.rounds = last_round + 1;
+            plan.fofs.assign((size_t)plan.rounds * namt, 0);
+            plan.ftot.assign(plan.rounds, 0);
+            plan.per_amt.assign(4ull * namt, 0);   // vbase | cnt | lo | hi
+            uint64_t vb = 0;
+            for (uint32_t k = 0; k < namt; k++) {
+                const uint64_t c = cnts[k];
+                const uint64_t l = std::min(h_rng[k], c), h = std::max(l, std::min(h_rng[2 * IPCFP_MAX_PARENTS + k], c));
+                plan.per_amt[k] = vb; plan.per_amt[namt + k] = c; plan.per_amt[2ull * namt + k] = l; plan.per_amt[3ull * namt + k] = h;
+                vb += h - l;
+            }
+            plan.nraw = vb;
+            for (uint32_t r = 0; ok && r < plan.rounds; r++) {
+                uint64_t run = 0;
+                for (uint32_t k = 0; k < namt; k++) {
+                    plan.fofs[(size_t)r * namt + k] = (uint32_t)run;
+                    const uint32_t hk = misc_h[64 + k];
+                    if (r > hk) continue;                              // this AMT is shallower: already finished
+                    const uint64_t l = plan.per_amt[2ull * namt + k], h = plan.per_amt[3ull * namt + k];
+                    const uint32_t sh = 3 * (hk - r + 1);              // a node of this round spans 2^sh indices
+                    uint64_t nodes = r == 0 ? 1 : (l < h ? (sh >= 64 ? 1 : ((h - 1) >> sh) - (l >> sh) + 1) : 0);
+                    run += nodes;
+                    if (run > frontier_cap) { ok = false; break; }
+                }
+                plan.ftot[r] = (uint32_t)run;
+            }
+            const size_t tbytes = plan.fofs.size() * 4 + plan.ftot.size() * 4 + plan.per_amt.size() * 8 + 64;
+            if (plan.nraw > 8ull * cap || tbytes > STAGE_TABLES) ok = false;
+        }
+        plan.ok = ok;
+    }
+    AsyncBuf<uint8_t> d_tables;
+    auto run_dense = [&]() {
+        // tables: per_amt (u64) | fofs (u32) | ftot (u32) through the pinned staging block
+        const size_t nb_amt = plan.per_amt.size() * 8, nb_fofs = plan.fofs.size() * 4, nb_ftot = plan.ftot.size() * 4;
+        uint8_t* ht = s->stage.p + tables_off;
+        memcpy(ht, plan.per_amt.data(), nb_amt);
+        memcpy(ht + nb_amt, plan.fofs.data(), nb_fofs);
+        memcpy(ht + nb_amt + nb_fofs, plan.ftot.data(), nb_ftot);
+        d_tables.alloc(nb_amt + nb_fofs + nb_ftot + 64, st);
+        IPCFP_CUDA(cudaMemcpyAsync(d_tables.p, ht, nb_amt + nb_fofs + nb_ftot, cudaMemcpyHostToDevice, st));
+        raw_cap = plan.nraw;
         exec_raw.alloc(raw_cap + 64, st);
-        ea.vals = exec_raw.p;
+        DenseArgs da;
+        da.store = s->view;
+        da.ping = Frontier{fA_blk.p, fA_meta.p, fA_base.p}; da.pong = Frontier{fB_blk.p, fB_meta.p, fB_base.p};
+        da.vals = exec_raw.p;
+        const uint64_t* pa = (const uint64_t*)d_tables.p;
+        da.vbase = pa; da.cnt = pa + namt; da.lo = pa + 2ull * namt; da.hi = pa + 3ull * namt;
+        da.fofs = (const uint32_t*)(d_tables.p + nb_amt); da.ftot = (const uint32_t*)(d_tables.p + nb_amt + nb_fofs);
+        da.namt = namt; da.record = skip_tx ? 0 : 1; da.wbits = wbits.p; da.fail = (uint32_t*)(dw + 14);
+        uint32_t top = 0;
+        while (top < plan.rounds && plan.ftot[top] <= 1024) top++;
+        if (top) { k_amt_dense<<<1, 1024, 0, st>>>(da, 0, top); IPCFP_LAUNCH_CHECK(); }
+        for (uint32_t r = top; r < plan.rounds; r++) {
+            k_amt_dense<<<div_up((uint64_t)plan.ftot[r] * 8, 256), 256, 0, st>>>(da, r, 1); IPCFP_LAUNCH_CHECK();
+        }
     };
-    // fused single-CTA rounds while the static bound fits one CTA
-    uint32_t top_rounds = 0;
-    while (top_rounds <= last_round && bound_of(top_rounds) <= TOP_CAP) top_rounds++;
-    uint32_t round = 0;
-    if (top_rounds) {
-        if (top_rounds > last_round) alloc_vals();  // the last round is inside the fused kernel
-        ExpandArgs a0 = ea;
-        a0.in = fcur; a0.in_count = ccount; a0.out = fnxt; a0.round = 0; a0.out_off = out_off.p;
-        k_amt_top<<<1, TOP_CAP, 0, st>>>(a0, fcur, fnxt, ccount, 0, top_rounds, out_off.p); IPCFP_LAUNCH_CHECK();
-        if (top_rounds & 1) std::swap(fcur, fnxt);
-        round = top_rounds;
-    }
-    for (; round <= last_round; round++) {
-        uint64_t items = bound_of(round);
-        if (round == last_round) alloc_vals();
-        unsigned grid = div_up(std::max<uint64_t>(items, 1), 128);
-        k_amt_count<<<grid, 128, 0, st>>>(s->view, fcur, ccount, round, last_round, ea.cap, counts.p, ea.rlo, ea.rhi); IPCFP_LAUNCH_CHECK();
-        exclusive_scan_u32(counts.p, out_off.p, (uint64_t)grid * 128, (uint64_t*)total_dev, scratch.p, st);
-        ExpandArgs a = ea;
-        a.in = fcur; a.in_count = ccount; a.out = fnxt; a.round = round; a.out_off = out_off.p;
-        k_amt_expand<<<grid, 128, 0, st>>>(a, counts.p, ncount, total_dev); IPCFP_LAUNCH_CHECK();
-        std::swap(fcur, fnxt);
-        std::swap(ccount, ncount);
-    }
-    // *ccount now holds the number of raw execution entries (k_amt_top leaves it in place as well).
+
+    // ---- (b) general walk: count → scan → expand per level, any AMT shape, exact errors
+    AsyncBuf<uint64_t> d_rng;
+    auto run_general = [&]() {
+        d_rng.alloc(4 * IPCFP_MAX_PARENTS, st);
+        IPCFP_CUDA(cudaMemcpyAsync(d_rng.p, h_rng.data(), h_rng.size() * 8, cudaMemcpyHostToDevice, st));
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+        Frontier fcur{fA_blk.p, fA_meta.p, fA_base.p}, fnxt{fB_blk.p, fB_meta.p, fB_base.p};
+        ccount = dw + 1; ncount = dw + 2;
+        ExpandArgs ea;
+        ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw;
+        ea.vals = nullptr; ea.cap = frontier_cap;
+        ea.rlo = d_rng.p; ea.rhi = d_rng.p + 2 * IPCFP_MAX_PARENTS;
+        // static frontier bound per round: namt * 8^round
+        auto bound_of = [&](uint32_t round) { uint64_t b = namt; for (uint32_t k = 0; k < round && b <= cap; k++) b *= 8; return std::min<uint64_t>(b, cap); };
+        auto alloc_vals = [&]() {
+            raw_cap = std::min<uint64_t>(bound_of(last_round) * 8, 8 * cap);
+            exec_raw.alloc(raw_cap + 64, st);
+            ea.vals = exec_raw.p;
+        };
+        // fused single-CTA rounds while the static bound fits one CTA
+        uint32_t top_rounds = 0;
+        while (top_rounds <= last_round && bound_of(top_rounds) <= TOP_CAP) top_rounds++;
+        uint32_t round = 0;
+        if (top_rounds) {
+            if (top_rounds > last_round) alloc_vals();  // the last round is inside the fused kernel
+            ExpandArgs a0 = ea;
+            a0.in = fcur; a0.in_count = ccount; a0.out = fnxt; a0.round = 0; a0.out_off = out_off.p;
+            k_amt_top<<<1, TOP_CAP, 0, st>>>(a0, fcur, fnxt, ccount, 0, top_rounds, out_off.p); IPCFP_LAUNCH_CHECK();
+            if (top_rounds & 1) std::swap(fcur, fnxt);
+            round = top_rounds;
+        }
+        for (; round <= last_round; round++) {
+            uint64_t items = bound_of(round);
+            if (round == last_round) alloc_vals();
+            unsigned grid = div_up(std::max<uint64_t>(items, 1), 128);
+            k_amt_count<<<grid, 128, 0, st>>>(s->view, fcur, ccount, round, last_round, ea.cap, counts.p, ea.rlo, ea.rhi); IPCFP_LAUNCH_CHECK();
+            exclusive_scan_u32(counts.p, out_off.p, (uint64_t)grid * 128, (uint64_t*)total_dev, scratch.p, st);
+            ExpandArgs a = ea;
+            a.in = fcur; a.in_count = ccount; a.out = fnxt; a.round = round; a.out_off = out_off.p;
+            k_amt_expand<<<div_up(std::max<uint64_t>(items, 1) * 8, 128), 128, 0, st>>>(a, counts.p, ncount, total_dev); IPCFP_LAUNCH_CHECK();
+            std::swap(fcur, fnxt);
+            std::swap(ccount, ncount);
+        }
+        // *ccount now holds the number of raw execution entries (k_amt_top leaves it in place as well).
+    };
+    bool dense_used = plan.ok;
+    if (dense_used) run_dense(); else run_general();
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
     wbuild.snapshot(wbits.p);
-    publish_words(s, 0, 16);   // dw[1]/dw[2] hold the frontier counters: ccount is one of them
-    const uint32_t ccount_idx = (uint32_t)(ccount - dw);
+    publish_words(s, 0, 16);   // error word, frontier counters (dw[1]/dw[2]), witness counts (dw[8], dw[9]), dense-walk flag (dw[14])
     IPCFP_CUDA(cudaStreamSynchronize(st));
+    if (dense_used && hw[14] != 0) {   // the AMTs are not what the dense walk assumes: redo the walk with the general kernels
+        dense_used = false;
+        k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();   // re-seed the frontier (same outputs as before)
+        run_general();
+        wbuild.snapshot(wbits.p);
+        publish_words(s, 0, 16);
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+    }
+    const uint32_t ccount_idx = (uint32_t)(ccount - dw);
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
-    uint64_t nraw = std::min<uint64_t>(hw[ccount_idx], raw_cap);
-    wbuild.start_copy(hw[8]);
+    uint64_t nraw = dense_used ? plan.nraw : std::min<uint64_t>(hw[ccount_idx], raw_cap);
+    wbuild.start_copy(hw[8], hw[9]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
     if (sharded) IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));   // execution order is resolved across ranks by the caller
@@ -849,7 +1043,9 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     p1.store = s->view; p1.store_dev = s->view_dev.p; p1.m_dev = d_matcher; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
     p1.match_bits = match_bits.p; p1.cnt = cnt.p; p1.nbytes = nby.p; p1.err = dw; p1.stats = dw + 4;
     if (N) {
-        static const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 6;
+        static const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 8;
+        static const int tune = getenv("IPCFP_PASS1_TUNE") ? atoi(getenv("IPCFP_PASS1_TUNE")) : 0;
+        p1.tune = (uint32_t)tune;
         if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
         else if (minb >= 8) k_pass1_occ8<<<div_up(N, 128), 128, 0, st>>>(p1);
         else k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1);

@@ -204,16 +204,15 @@ __device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_
     uint64_t w0, w1;
     win_load(p + pos, w0, w1);
     if ((w0 & 0xff) != 0x82) return FAST_FAIL;
-    // emitter: any minimal uint head
+    // emitter: a minimal uint head with ≤ 4 argument bytes (actor ids); 8-byte arguments take the strict parser
     uint32_t eb = (uint32_t)(w0 >> 8) & 0xff;
-    if (eb >= 0x1c) return FAST_FAIL;                       // not major 0 / reserved ai
-    uint32_t enb = eb < 24 ? 0 : (1u << (eb - 24));          // 0,1,2,4,8 argument bytes
-    uint64_t raw = (w0 >> 16) | (w1 << 48);                  // the 8 bytes after the emitter head byte
-    uint64_t be = ((uint64_t)__byte_perm((uint32_t)raw, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(raw >> 32), 0, 0x0123);
-    uint64_t earg = enb ? (be >> (64 - 8 * enb)) : eb;
-    uint64_t emin = eb == 24 ? 24ull : (eb == 25 ? 0x100ull : (eb == 26 ? 0x10000ull : (eb == 27 ? 0x100000000ull : 0ull)));
+    if (eb >= 0x1b) return FAST_FAIL;                       // 8-byte argument, not major 0, or reserved ai
+    uint32_t enb = eb < 24 ? 0 : (1u << (eb - 24));          // 0,1,2,4 argument bytes
+    uint32_t be = __byte_perm((uint32_t)(w0 >> 16), 0, 0x0123);   // bytes 2..5, big-endian
+    uint32_t earg = enb ? (be >> (32 - 8 * enb)) : eb;
+    uint32_t emin = eb == 24 ? 24u : (eb == 25 ? 0x100u : (eb == 26 ? 0x10000u : 0u));
     if (earg < emin) return FAST_FAIL;                       // non-minimal → let the strict parser report it
-    uint32_t hb = win_byte(w0, w1, 2 + enb);                 // entries array head (enb ≤ 8 → byte ≤ 10)
+    uint32_t hb = (uint32_t)(w0 >> (16 + 8 * enb)) & 0xffu;  // entries array head (enb ≤ 4 → byte ≤ 6)
     if ((hb & 0xe0) != 0x80 || (hb & 31) >= 24) return FAST_FAIL;
     uint32_t ne = hb & 31;
     uint32_t cur = pos + 3 + enb;
@@ -223,40 +222,57 @@ __device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_
     for (uint32_t e = 0; e < ne; e++) {
         if (n - cur < 5) return FAST_FAIL;
         win_load(p + cur, w0, w1);
-        uint32_t b0 = (uint32_t)w0 & 0xff, fl = (uint32_t)(w0 >> 8) & 0xff, th = (uint32_t)(w0 >> 16) & 0xff;
-        if (b0 != 0x84 || fl >= 24) return FAST_FAIL;
-        uint32_t klen = th - 0x60;                           // text head 0x61/0x62/0x64/0x66
-        uint32_t kind;                                       // 0..3 tK, 4 d, 5 topics, 6 data
-        uint32_t k4 = (uint32_t)(w0 >> 24);                  // key bytes 0..3
-        if (klen == 2) {
-            uint32_t idx = ((k4 >> 8) & 0xff) - (uint32_t)'1';
-            if ((k4 & 0xff) != 't' || idx >= 4) return FAST_FAIL;
-            kind = idx;
-        } else if (klen == 1) {
-            if ((k4 & 0xff) != 'd') return FAST_FAIL;
+        // the one shape almost every entry has — an indexed topic  84 fl 62 't' '1'..'4' 18 cc 58 LL  — is
+        // recognised with constant masks on the window (all offsets static); anything else goes through the
+        // general head decoder below. Both accept exactly the same encodings with the same (kind, voff, vlen).
+        const uint32_t lo = (uint32_t)w0, hi = (uint32_t)(w0 >> 32), ll = (uint32_t)w1 & 0xffu;
+        const uint32_t tidx = (hi & 0xffu) - (uint32_t)'1';
+        const uint32_t fl8 = (lo >> 8) & 0xffu;
+        bool canon = (lo & 0xffff00ffu) == 0x74620084u && fl8 < 24u && (hi & 0xff00ff00u) == 0x58001800u && tidx < 4u && ((hi >> 16) & 0xffu) >= 24u && ll >= 24u;
+        uint32_t kind = tidx, vlen = ll, voff = cur + 9;
+        // second static shape, the data entry  84 fl 61 'd' 18 cc <40+n | 58 nn | 59 nnnn>
+        if ((lo & 0xffff00ffu) == 0x64610084u && fl8 < 24u && (hi & 0xffu) == 0x18u && ((hi >> 8) & 0xffu) >= 24u) {
+            const uint32_t vb = (hi >> 16) & 0xffu, b7 = hi >> 24, l16 = (b7 << 8) | ll;
             kind = 4;
-        } else if (klen == 6) {
-            uint64_t key = (w0 >> 24) | (w1 << 40);          // key bytes 0..5 in the low 48 bits
-            if ((key & 0xffffffffffffull) != 0x736369706f74ull) return FAST_FAIL;  // "topics"
-            kind = 5;
-        } else if (klen == 4) {
-            if (k4 != 0x61746164u) return FAST_FAIL;          // "data"
-            kind = 6;
-        } else return FAST_FAIL;
-        uint32_t k = 3 + klen;                               // codec head position (≤ 9)
-        uint32_t cb = win_byte(w0, w1, k);
-        uint32_t clen;
-        if (cb < 24) clen = 1;
-        else if (cb == 24 && win_byte(w0, w1, k + 1) >= 24) clen = 2;
-        else return FAST_FAIL;
-        k += clen;                                           // value head position (≤ 11)
-        uint32_t vb = win_byte(w0, w1, k);
-        uint32_t vlen, vh;
-        if (vb >= 0x40 && vb < 0x58) { vlen = vb - 0x40; vh = 1; }
-        else if (vb == 0x58) { vlen = win_byte(w0, w1, k + 1); vh = 2; if (vlen < 24) return FAST_FAIL; }
-        else if (vb == 0x59) { vlen = (win_byte(w0, w1, k + 1) << 8) | win_byte(w0, w1, k + 2); vh = 3; if (vlen < 256) return FAST_FAIL; }
-        else return FAST_FAIL;
-        uint32_t voff = cur + k + vh;
+            if (vb - 0x40u < 0x18u) { vlen = vb - 0x40u; voff = cur + 7; canon = true; }
+            else if (vb == 0x58u && b7 >= 24u) { vlen = b7; voff = cur + 8; canon = true; }
+            else if (vb == 0x59u && l16 >= 256u) { vlen = l16; voff = cur + 9; canon = true; }
+        }
+        if (!canon) {
+            uint32_t b0 = (uint32_t)w0 & 0xff, fl = (uint32_t)(w0 >> 8) & 0xff, th = (uint32_t)(w0 >> 16) & 0xff;
+            if (b0 != 0x84 || fl >= 24) return FAST_FAIL;
+            uint32_t klen = th - 0x60;                           // text head 0x61/0x62/0x64/0x66
+            uint32_t k4 = (uint32_t)(w0 >> 24);                  // key bytes 0..3
+            if (klen == 2) {
+                uint32_t idx = ((k4 >> 8) & 0xff) - (uint32_t)'1';
+                if ((k4 & 0xff) != 't' || idx >= 4) return FAST_FAIL;
+                kind = idx;
+            } else if (klen == 1) {
+                if ((k4 & 0xff) != 'd') return FAST_FAIL;
+                kind = 4;
+            } else if (klen == 6) {
+                uint64_t key = (w0 >> 24) | (w1 << 40);          // key bytes 0..5 in the low 48 bits
+                if ((key & 0xffffffffffffull) != 0x736369706f74ull) return FAST_FAIL;  // "topics"
+                kind = 5;
+            } else if (klen == 4) {
+                if (k4 != 0x61746164u) return FAST_FAIL;          // "data"
+                kind = 6;
+            } else return FAST_FAIL;
+            uint32_t k = 3 + klen;                               // codec head position (≤ 9)
+            uint32_t cb = win_byte(w0, w1, k);
+            uint32_t clen;
+            if (cb < 24) clen = 1;
+            else if (cb == 24 && win_byte(w0, w1, k + 1) >= 24) clen = 2;
+            else return FAST_FAIL;
+            k += clen;                                           // value head position (≤ 11)
+            uint32_t vb = win_byte(w0, w1, k);
+            uint32_t vh;
+            if (vb >= 0x40 && vb < 0x58) { vlen = vb - 0x40; vh = 1; }
+            else if (vb == 0x58) { vlen = win_byte(w0, w1, k + 1); vh = 2; if (vlen < 24) return FAST_FAIL; }
+            else if (vb == 0x59) { vlen = (win_byte(w0, w1, k + 1) << 8) | win_byte(w0, w1, k + 2); vh = 3; if (vlen < 256) return FAST_FAIL; }
+            else return FAST_FAIL;
+            voff = cur + k + vh;
+        }
         if (voff > n || vlen > n - voff) return FAST_FAIL;
         if (kind < 4) a.topic(kind, voff, vlen);
         else if (kind == 4) { a.have |= 16; a.d_off = voff; a.d_len = vlen; }

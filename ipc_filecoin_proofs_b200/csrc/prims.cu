@@ -73,6 +73,45 @@ template <class Load> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_fin
     for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
 
+// The whole scan in one CTA (n ≤ SCAN_SMALL): tiles in sequence with a running carry — one launch instead of three.
+static constexpr uint64_t SCAN_SMALL = 8 * SCAN_TILE;
+template <class Load> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_dev, Load load) {
+    uint64_t carry = 0;
+    for (uint64_t tile = 0; tile < n; tile += SCAN_TILE) {
+        uint64_t base = tile + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint64_t s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? load(in, base + k) : 0; s += v[k]; }
+        uint64_t tot;
+        uint64_t ex = block_exclusive_scan(s, &tot) + carry;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total_dev) *total_dev = carry;
+}
+// Second kernel of the two-launch scan: every CTA first adds up the tile sums of the tiles before it (≤ SCAN_FUSED_BLOCKS
+// values, L2-resident) instead of waiting for a separate single-CTA pass over them.
+static constexpr unsigned SCAN_FUSED_BLOCKS = 8192;
+template <class Load> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final_fused(const uint32_t* in, uint64_t* out, uint64_t n, const uint64_t* block_sums,
+                                                                                        uint64_t* total_dev, Load load) {
+    uint64_t mine = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) mine += block_sums[i];
+    uint64_t prefix;
+    block_exclusive_scan(mine, &prefix);
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? load(in, base + k) : 0; s += v[k]; }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan(s, &tot) + prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && total_dev) *total_dev = prefix + tot;
+}
+
 size_t scan_scratch_elems(uint64_t n) { return (size_t)div_up(n, SCAN_TILE) + 1; }
 
 template <class Load> static void scan_impl(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_dev, uint64_t* scratch, cudaStream_t st, Load load) {
@@ -80,8 +119,10 @@ template <class Load> static void scan_impl(const uint32_t* in, uint64_t* out, u
         if (total_dev) IPCFP_CUDA(cudaMemsetAsync(total_dev, 0, 8, st));
         return;
     }
+    if (n <= SCAN_SMALL) { k_scan_small<<<1, SCAN_THREADS, 0, st>>>(in, out, n, total_dev, load); IPCFP_LAUNCH_CHECK(); return; }
     unsigned nb = div_up(n, SCAN_TILE);
     k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(in, n, scratch, load); IPCFP_LAUNCH_CHECK();
+    if (nb <= SCAN_FUSED_BLOCKS) { k_scan_final_fused<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch, total_dev, load); IPCFP_LAUNCH_CHECK(); return; }
     k_scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(scratch, nb, total_dev); IPCFP_LAUNCH_CHECK();
     k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch, load); IPCFP_LAUNCH_CHECK();
 }

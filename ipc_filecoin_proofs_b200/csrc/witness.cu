@@ -146,24 +146,26 @@ WitnessBuilder::WitnessBuilder(Store* store) : s(store) {
     scratch.alloc(scan_scratch_elems(std::max<uint64_t>(nwords, n)) + 8, st);
 }
 
-// enqueue: bitmap → idx[0..mA), padded offsets; totals land in dev_words[8] (mA) and [9] (bytesA)
+// padded length of every candidate slot of idx[] (the count is only known on the device: zero past it)
+__global__ void k_padded_lengths_dev(const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ count, uint64_t n_max,
+                                     const uint32_t* __restrict__ lengths, uint32_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_max) out[i] = i < *count ? (lengths[idx[i]] + 15u) & ~15u : 0u;
+}
+// enqueue: bitmap → idx[0..mA), padded offsets; totals land in dev_words[8] (mA) and [9] (bytesA) — the caller
+// publishes both and syncs ONCE before start_copy
 void WitnessBuilder::snapshot(const uint32_t* wbits) {
     unsigned long long* dw = s->dev_words.p;
     IPCFP_CUDA(cudaMemcpyAsync(bitsA.p, wbits, nwords * 4, cudaMemcpyDeviceToDevice, st));
     bitmap_to_indices(bitsA.p, s->n, idx.p, (uint64_t*)(dw + 8), word_prefix.p, scratch.p, st);
-    // padded lengths for every candidate slot (count is only known on the device: bound by n)
-    // → done after the host learns mA in start_copy; here only the count is produced.
+    if (s->n) { k_padded_lengths_dev<<<div_up(s->n, 256), 256, 0, st>>>(idx.p, dw + 8, s->n, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
+    exclusive_scan_u32(plen.p, offs.p, s->n, (uint64_t*)(dw + 9), scratch.p, st);
     have_snapshot = true;
 }
-// host knows mA: scan padded lengths, gather on the side stream, start the D2H
-void WitnessBuilder::start_copy(uint64_t mA_) {
+// host knows mA and bytesA: gather on the side stream, start the D2H
+void WitnessBuilder::start_copy(uint64_t mA_, uint64_t bytesA_) {
     mA = mA_;
-    unsigned long long* dw = s->dev_words.p;
-    if (mA) { k_padded_lengths<<<div_up(mA, 256), 256, 0, st>>>(idx.p, mA, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
-    exclusive_scan_u32(plen.p, offs.p, mA, (uint64_t*)(dw + 9), scratch.p, st);
-    publish_words(s, 9, 1);
-    IPCFP_CUDA(cudaStreamSynchronize(st));
-    bytesA = s->host_words.p[9];
+    bytesA = bytesA_;
     host_cap = bytesA + bytesA / 8 + (8u << 20);
     host_blob = PinnedArray(s->pool, host_cap);
     host_cap = host_blob.cap;
@@ -239,9 +241,9 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
 void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out) {
     WitnessBuilder wb(s);
     wb.snapshot(wbits_dev);
-    publish_words(s, 8, 1);
+    publish_words(s, 8, 2);
     IPCFP_CUDA(cudaStreamSynchronize(s->stream));
-    wb.start_copy(s->host_words.p[8]);
+    wb.start_copy(s->host_words.p[8], s->host_words.p[9]);
     wb.finish(0, out);
 }
 

@@ -265,6 +265,50 @@ def test_error_parity(api, oracle_mod, synth_mod, ts1):
     assert seen_err >= 15
 
 
+def test_sparse_message_amt_takes_general_walk(api, oracle_mod, synth_mod, ts1):
+    """The dense message-AMT walk (index arithmetic, one launch per level) must hand over to the general
+    count → scan → expand walk when an AMT has holes or its `count` lies; results stay those of the reference."""
+    import cbor2
+    from tests.test_oracle_cpu import _patched
+    d = ts1.as_dict()
+    spec = spec_of(ts1)
+    tm = cbor2.loads(d[bytes(ts1.parent_txmeta_cids[0])])
+    ran = 0
+    for which in (0, 1):
+        root_cid = tm[which].value[1:]
+        height, count, node = cbor2.loads(d[root_cid])
+        cur_cid, cur, is_root = root_cid, node, True
+        while cur[1]:
+            cur_cid = cur[1][0].value[1:]
+            cur, is_root = cbor2.loads(d[cur_cid]), False
+        bmap, links, vals = cur
+        if len(vals) < 2:
+            continue
+        for drop_first in (True, False):
+            slots = [b for b in range(8) if bmap[0] >> b & 1]
+            gone = slots[0] if drop_first else slots[-1]
+            node2 = [bytes([bmap[0] & ~(1 << gone)]), [], vals[1:] if drop_first else vals[:-1]]
+            new = cbor2.dumps([height, count, node2]) if is_root else cbor2.dumps(node2)
+            o, g = _both(api, oracle_mod, _patched(ts1, cur_cid, new), spec)
+            assert o[0] == g[0], (which, drop_first, o, g)
+            if o[0] == "ok":
+                assert_event_results_equal(g[1], o[1])
+            else:
+                assert o[1:] == g[1:], (which, drop_first, o, g)
+            ran += 1
+    assert ran >= 2
+
+
+def test_general_walk_forced(api, oracle_mod, synth_mod, monkeypatch):
+    """IPCFP_BFS_GENERAL=1 disables the dense walk: the general kernels alone must give the same answers."""
+    monkeypatch.setenv("IPCFP_BFS_GENERAL", "1")
+    for cfg in (1, 2):
+        ts = synth_mod.Tipset(synth_mod.config_params(cfg))
+        exp = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec_of(ts))
+        got = api.BlockStore.from_tipset(ts).generate_event_proof(ts, spec_of(ts))
+        assert_event_results_equal(got, exp)
+
+
 def test_receipt_missing_from_amt_is_skipped(api, oracle_mod, synth_mod):
     """events/generator.rs:249-251: r_amt.get(i) == None ⇒ `continue` (no proof, no events recording)."""
     import cbor2
