@@ -56,8 +56,8 @@ struct Store {
     // small persistent scratch
     DevBuf<unsigned long long> dev_words;  // [0] error word, [1..] counters
     PinnedBuf<uint64_t> host_words;
-    PinnedBuf<uint8_t> stage;              // pinned staging for small per-call uploads (spec, tipset CIDs, walk tables): no host sync needed
-    cudaEvent_t ev[8] = {};
+    PinnedArray stage;                     // pinned staging (from the process-wide pool) for small per-call uploads: spec, tipset CIDs, walk tables
+    cudaEvent_t ev[10] = {};
     ~Store();
     void use() const { IPCFP_CUDA(cudaSetDevice(device)); }
 };
@@ -135,9 +135,11 @@ struct WitnessBuilder {
     PinnedArray host_blob;
     explicit WitnessBuilder(Store* store);
     void snapshot(const uint32_t* wbits);        // enqueue; count → dev_words[8]
-    void start_copy(uint64_t mA, uint64_t bytesA);  // host knows the counts: gather + D2H on the side stream
+    // host knows the counts: gather in two parts (the first split_idx blocks = split_bytes bytes, then the rest) so that the D2H of
+    // the first part is on the wire while the second is still being gathered
+    void start_copy(uint64_t mA, uint64_t bytesA, uint64_t split_idx, uint64_t split_bytes);
     void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10]
-    void finish(uint64_t mB, WitnessOut& out);   // late blocks, Cid-order index arrays, join
+    void finish(uint64_t mB, WitnessOut& out, bool want_sorted_idx = false);   // late blocks, Cid-order index arrays, join
 };
 void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out);
 

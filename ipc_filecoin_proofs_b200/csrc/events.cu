@@ -643,9 +643,9 @@ __device__ __forceinline__ void amt_item_dense(const DenseArgs& a, const Frontie
     if (level) {
         int32_t child = store_lookup(a.store, item + 5);
         if (child < 0) { *a.fail = 1; return; }
-        if (a.record) witness_mark(a.wbits, (uint32_t)child);
         const uint64_t d = (uint64_t)a.fofs[(round + 1) * a.namt + amt] + ((cb >> sh) - (lo >> sh));
         out.blk[d] = (uint32_t)child; out.meta[d] = make_meta(amt, 0, level - 1); out.base[d] = cb;
+        if (a.record) witness_mark(a.wbits, (uint32_t)child);
     } else {
         const uint8_t* src = item + 5;
         RawCid c;
@@ -803,13 +803,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     static_assert(sizeof(Matcher) <= 1024, "Matcher must fit its staging slot");
     const size_t STAGE_TABLES = 32768;                    // second half of the staging block: dense-walk tables
     const size_t tables_off = std::max<size_t>(STAGE_TABLES, (small_bytes + 63) & ~(size_t)63);
-    s->stage.ensure(tables_off + STAGE_TABLES);
+    if (!s->stage.p || s->stage.cap < tables_off + STAGE_TABLES) s->stage = PinnedArray(s->pool, tables_off + STAGE_TABLES);
     AsyncBuf<uint8_t> small(small_bytes, st);
     uint8_t* d_sig = small.p + 1024;                       // 8-byte aligned
     uint8_t* d_cids = small.p + 1024 + sig_cap;
     Matcher* d_matcher = (Matcher*)small.p;
     {
-        uint8_t* hs = s->stage.p;
+        uint8_t* hs = s->stage.as<uint8_t>();
         memset(hs, 0, small_bytes);
         memcpy(hs, &mh, sizeof(Matcher));
         memcpy(hs + 1024, spec->event_signature, siglen);
@@ -841,13 +841,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     sa.amt_count = amt_count.p;
     sa.sig = d_sig; sa.sig_len = (uint32_t)siglen; sa.matcher = d_matcher;
     k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();
-    IPCFP_CUDA(cudaMemcpyAsync(hw + 16, d_matcher, 32, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw + 400, d_matcher, 32, cudaMemcpyDeviceToHost, st));   // t0 → hw[400..404)
     IPCFP_CUDA(cudaMemcpyAsync(hw + 24, misc.p, (64 + 2 * IPCFP_MAX_PARENTS) * 4, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw + 128, amt_count.p, 2 * IPCFP_MAX_PARENTS * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
-    memcpy(mh.t0, hw + 16, 32);
+    memcpy(mh.t0, hw + 400, 32);
     const uint32_t* misc_h = (const uint32_t*)(hw + 24);
     const uint32_t receipts_root_blk = misc_h[0];
     const bool missing_base = misc_h[1] != 0;
@@ -931,7 +931,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     auto run_dense = [&]() {
         // tables: per_amt (u64) | fofs (u32) | ftot (u32) through the pinned staging block
         const size_t nb_amt = plan.per_amt.size() * 8, nb_fofs = plan.fofs.size() * 4, nb_ftot = plan.ftot.size() * 4;
-        uint8_t* ht = s->stage.p + tables_off;
+        uint8_t* ht = s->stage.as<uint8_t>() + tables_off;
         memcpy(ht, plan.per_amt.data(), nb_amt);
         memcpy(ht + nb_amt, plan.fofs.data(), nb_fofs);
         memcpy(ht + nb_amt + nb_fofs, plan.ftot.data(), nb_ftot);
@@ -1006,21 +1006,21 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
     wbuild.snapshot(wbits.p);
-    publish_words(s, 0, 16);   // error word, frontier counters (dw[1]/dw[2]), witness counts (dw[8], dw[9]), dense-walk flag (dw[14])
+    publish_words(s, 0, 18);   // error word, frontier counters (dw[1]/dw[2]), witness counts (dw[8], dw[9]), dense-walk flag (dw[14]), gather split (dw[16], dw[17])
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (dense_used && hw[14] != 0) {   // the AMTs are not what the dense walk assumes: redo the walk with the general kernels
         dense_used = false;
         k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();   // re-seed the frontier (same outputs as before)
         run_general();
         wbuild.snapshot(wbits.p);
-        publish_words(s, 0, 16);
+        publish_words(s, 0, 18);
         IPCFP_CUDA(cudaStreamSynchronize(st));
     }
     const uint32_t ccount_idx = (uint32_t)(ccount - dw);
     if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
     if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
     uint64_t nraw = dense_used ? plan.nraw : std::min<uint64_t>(hw[ccount_idx], raw_cap);
-    wbuild.start_copy(hw[8], hw[9]);
+    wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
     if (sharded) IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));   // execution order is resolved across ranks by the caller

@@ -197,7 +197,6 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     cudaStream_t st = s->stream;
     s->dev_words.alloc(64);
     s->host_words.alloc(512);
-    s->stage.alloc(1 << 16);
     {
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr); }

@@ -146,6 +146,14 @@ WitnessBuilder::WitnessBuilder(Store* store) : s(store) {
     scratch.alloc(scan_scratch_elems(std::max<uint64_t>(nwords, n)) + 8, st);
 }
 
+// where to split the snapshot gather: dev_words[16] = number of blocks in the first part, [17] = their padded bytes
+__global__ void k_chunk_bounds(const uint64_t* __restrict__ offs, const unsigned long long* count, const unsigned long long* total, unsigned long long* out) {
+    const uint64_t m = *count;
+    uint64_t ia = m / 8;
+    if (ia < 1024) ia = m < 1024 ? m : 1024;
+    out[0] = ia;
+    out[1] = ia < m ? offs[ia] : *total;
+}
 // padded length of every candidate slot of idx[] (the count is only known on the device: zero past it)
 __global__ void k_padded_lengths_dev(const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ count, uint64_t n_max,
                                      const uint32_t* __restrict__ lengths, uint32_t* out) {
@@ -160,21 +168,27 @@ void WitnessBuilder::snapshot(const uint32_t* wbits) {
     bitmap_to_indices(bitsA.p, s->n, idx.p, (uint64_t*)(dw + 8), word_prefix.p, scratch.p, st);
     if (s->n) { k_padded_lengths_dev<<<div_up(s->n, 256), 256, 0, st>>>(idx.p, dw + 8, s->n, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
     exclusive_scan_u32(plen.p, offs.p, s->n, (uint64_t*)(dw + 9), scratch.p, st);
+    k_chunk_bounds<<<1, 1, 0, st>>>(offs.p, dw + 8, dw + 9, dw + 16); IPCFP_LAUNCH_CHECK();
     have_snapshot = true;
 }
-// host knows mA and bytesA: gather on the side stream, start the D2H
-void WitnessBuilder::start_copy(uint64_t mA_, uint64_t bytesA_) {
+// host knows mA and bytesA: gather (main stream, two parts), D2H on the side stream as soon as each part is there
+void WitnessBuilder::start_copy(uint64_t mA_, uint64_t bytesA_, uint64_t split_idx, uint64_t split_bytes) {
     mA = mA_;
     bytesA = bytesA_;
     host_cap = bytesA + bytesA / 8 + (8u << 20);
     host_blob = PinnedArray(s->pool, host_cap);
     host_cap = host_blob.cap;
     dblobA.alloc(bytesA + 64, st);
+    const uint64_t ia = std::min(split_idx, mA), ba = ia == mA ? bytesA : std::min(split_bytes, bytesA);
+    if (ia) { k_witness_copy<<<div_up(ia * 32, 256), 256, 0, st>>>(idx.p, ia, s->view, offs.p, dblobA.p); IPCFP_LAUNCH_CHECK(); }
     IPCFP_CUDA(cudaEventRecord(s->ev[6], st));
     IPCFP_CUDA(cudaStreamWaitEvent(st2, s->ev[6], 0));
-    if (mA) {
-        k_witness_copy<<<div_up(mA * 32, 256), 256, 0, st2>>>(idx.p, mA, s->view, offs.p, dblobA.p); IPCFP_LAUNCH_CHECK();
-        IPCFP_CUDA(cudaMemcpyAsync(host_blob.p, dblobA.p, bytesA, cudaMemcpyDeviceToHost, st2));
+    if (ba) IPCFP_CUDA(cudaMemcpyAsync(host_blob.p, dblobA.p, ba, cudaMemcpyDeviceToHost, st2));
+    if (mA > ia) {
+        k_witness_copy<<<div_up((mA - ia) * 32, 256), 256, 0, st>>>(idx.p + ia, mA - ia, s->view, offs.p + ia, dblobA.p); IPCFP_LAUNCH_CHECK();
+        IPCFP_CUDA(cudaEventRecord(s->ev[8], st));
+        IPCFP_CUDA(cudaStreamWaitEvent(st2, s->ev[8], 0));
+        if (bytesA > ba) IPCFP_CUDA(cudaMemcpyAsync((uint8_t*)host_blob.p + ba, dblobA.p + ba, bytesA - ba, cudaMemcpyDeviceToHost, st2));
     }
     IPCFP_CUDA(cudaEventRecord(s->ev[7], st2));
 }
@@ -185,7 +199,7 @@ void WitnessBuilder::finish_enqueue(const uint32_t* wbits) {
     k_andnot<<<div_up(nwords ? nwords : 1, 256), 256, 0, st>>>(wbits, bitsA.p, bitsB.p, nwords); IPCFP_LAUNCH_CHECK();
     bitmap_to_indices(bitsB.p, s->n, idx.p + mA, (uint64_t*)(dw + 10), word_prefix.p, scratch.p, st);
 }
-void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
+void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out, bool want_sorted_idx) {
     mB = mB_;
     unsigned long long* dw = s->dev_words.p;
     uint64_t m = mA + mB;
@@ -223,12 +237,12 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out) {
     out.cids = PinnedArray(s->pool, m * 38 + 64);
     out.offsets = PinnedArray(s->pool, (m + 1) * 8);
     out.lengths = PinnedArray(s->pool, (m + 1) * 4);
-    out.sorted_idx = PinnedArray(s->pool, (m + 1) * 4);
+    if (want_sorted_idx) out.sorted_idx = PinnedArray(s->pool, (m + 1) * 4);
     if (m) {
         IPCFP_CUDA(cudaMemcpyAsync(out.cids.p, d_cids.p, m * 38, cudaMemcpyDeviceToHost, st));
         IPCFP_CUDA(cudaMemcpyAsync(out.offsets.p, d_offs.p, m * 8, cudaMemcpyDeviceToHost, st));
         IPCFP_CUDA(cudaMemcpyAsync(out.lengths.p, d_lens.p, m * 4, cudaMemcpyDeviceToHost, st));
-        IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, d_idx.p, m * 4, cudaMemcpyDeviceToHost, st));
+        if (want_sorted_idx) IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, d_idx.p, m * 4, cudaMemcpyDeviceToHost, st));
     }
     out.cids_dev = std::move(d_cids);
     IPCFP_CUDA(cudaStreamWaitEvent(st, s->ev[7], 0));  // the big copy on the side stream
@@ -243,8 +257,8 @@ void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out) {
     wb.snapshot(wbits_dev);
     publish_words(s, 8, 2);
     IPCFP_CUDA(cudaStreamSynchronize(s->stream));
-    wb.start_copy(s->host_words.p[8], s->host_words.p[9]);
-    wb.finish(0, out);
+    wb.start_copy(s->host_words.p[8], s->host_words.p[9], s->host_words.p[8], s->host_words.p[9]);   // one part
+    wb.finish(0, out, true);
 }
 
 }  // namespace ipcfp
