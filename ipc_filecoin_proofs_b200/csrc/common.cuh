@@ -95,6 +95,7 @@ template <class T> struct PinnedBuf {
         }
     }
     void ensure(size_t count) { if (count > n) alloc(count); }
+    void swap(PinnedBuf& o) { std::swap(p, o.p); std::swap(dev, o.dev); std::swap(n, o.n); }
 };
 
 // ------------------------------------------------------------------ device error word

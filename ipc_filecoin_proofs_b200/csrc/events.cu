@@ -602,6 +602,8 @@ struct DenseArgs {
     uint32_t namt, record;
     uint32_t* wbits;
     uint32_t* fail;
+    uint64_t* f_off[2];      // where each frontier item's block is (arena offset, length), by round parity — rounds ≥ 1
+    uint32_t* f_len[2];
 };
 // Eight lanes per node. The walk only has to DETECT anything unusual, not name it, so instead of the sequential
 // strict decoder the node is matched against the one byte layout a bw-3 node the strict decoder accepts can have:
@@ -609,11 +611,15 @@ struct DenseArgs {
 // with every link  d8 2a 58 27 00 01 …  — all lanes check the frame, lane j checks (and then resolves or copies) item j.
 // Whatever this accepts the strict decoder accepts with the same meaning; whatever it rejects goes to the general walk.
 __device__ __forceinline__ void amt_item_dense(const DenseArgs& a, const Frontier& in, const Frontier& out, uint32_t round, uint32_t it, uint32_t j) {
-    const uint32_t blk = in.blk[it], meta = in.meta[it];
+    const uint32_t meta = in.meta[it];
     const uint64_t base = in.base[it];
     const uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    // where the block is: carried with the frontier item by the level above (same record line its lookup compared);
+    // the roots (round 0, seeded by k_setup) go through the store
     uint32_t len;
-    const uint8_t* p = store_block(a.store, blk, len);
+    const uint8_t* p;
+    if (round == 0) p = store_block(a.store, in.blk[it], len);
+    else { const uint32_t par = round & 1; len = a.f_len[par][it]; p = a.store.blob + a.f_off[par][it]; }
     uint32_t q0 = 0;                                    // offset of the node inside the block
     if (is_root) {
         Rd r(p, len);
@@ -622,29 +628,39 @@ __device__ __forceinline__ void amt_item_dense(const DenseArgs& a, const Frontie
         if (r.err) { *a.fail = 1; return; }
         q0 = r.pos;
     }
-    if (len < q0 + 5) { *a.fail = 1; return; }
+    if (len < q0 + 5) { *a.fail = 1; return; }         // the smallest node (empty) is 5 bytes
     const uint8_t* q = p + q0;
     const uint32_t nlen = len - q0;
-    const uint32_t w = (uint32_t)load_u64_any(q);       // 83 41 bm 8n
-    const uint32_t bm8 = (w >> 16) & 0xffu, nl = (w >> 24) - 0x80u;
-    if ((w & 0xffffu) != 0x4183u || nl > 8u || 4u + 43u * nl >= nlen) { *a.fail = 1; return; }
-    const uint32_t nv = (uint32_t)q[4 + 43 * nl] - 0x80u;
-    if (nv > 8u || nlen != 5u + 43u * (nl + nv) || (nl && nv) || (nl && level == 0) || (nv && level != 0) || (uint32_t)__popc(bm8) != nl + nv) { *a.fail = 1; return; }
     const uint64_t cnt = a.cnt[amt], lo = a.lo[amt], hi = a.hi[amt];
     const uint32_t sh = 3 * level;                      // a child (a value at level 0) spans 2^sh indices; the host admits sh ≤ 60 only
     uint32_t n_exp = 0;                                 // slots a dense AMT has under this node
     if (cnt > base) { uint64_t n = ((cnt - base - 1) >> sh) + 1; n_exp = n > 8 ? 8u : (uint32_t)n; }
+    // the three reads of the node — frame head, values-array head, this lane's item — are issued together from the
+    // EXPECTED layout (clamped into the block), then checked: one memory round trip instead of three
+    const uint32_t exp_nl = level ? n_exp : 0u;
+    const uint32_t tpos = min(4u + 43u * exp_nl, nlen - 1u);
+    const uint32_t ipos = min((level ? 4u : 5u) + 43u * j, nlen - min(nlen, 8u));   // never starts past the block: the 8-byte read stays inside block + arena padding
+    const uint32_t w = (uint32_t)load_u64_any(q);       // 83 41 bm 8n
+    const uint32_t tb = q[tpos];
+    const uint64_t iw = load_u64_any(q + ipos);
+    const uint32_t bm8 = (w >> 16) & 0xffu, nl = (w >> 24) - 0x80u;
+    if ((w & 0xffffu) != 0x4183u || nl != exp_nl || 4u + 43u * nl >= nlen) { *a.fail = 1; return; }   // now tpos is the values head
+    const uint32_t nv = tb - 0x80u;
+    if (nv > 8u || nlen != 5u + 43u * (nl + nv) || (nl && nv) || (nl && level == 0) || (nv && level != 0) || (uint32_t)__popc(bm8) != nl + nv) { *a.fail = 1; return; }
     if (bm8 != (1u << n_exp) - 1u || (level ? nl : nv) != n_exp) { *a.fail = 1; return; }
     if (j >= n_exp) return;
-    const uint8_t* item = q + (level ? 4u : 5u) + 43u * j;   // link j (nv == 0) or value j (nl == 0)
-    if ((load_u64_any(item) & 0xffffffffffffull) != 0x010027582ad8ull) { *a.fail = 1; return; }   // d8 2a 58 27 00 01
+    const uint8_t* item = q + (level ? 4u : 5u) + 43u * j;   // link j (nv == 0) or value j (nl == 0); == q + ipos for a well-formed node
+    if ((iw & 0xffffffffffffull) != 0x010027582ad8ull) { *a.fail = 1; return; }   // d8 2a 58 27 00 01
     const uint64_t cb = base + ((uint64_t)j << sh), ce = cb + (1ull << sh);   // indices under slot j
     if (!(cb < hi && ce > lo)) return;                  // not in this call's share
     if (level) {
         int32_t child = store_lookup(a.store, item + 5);
         if (child < 0) { *a.fail = 1; return; }
         const uint64_t d = (uint64_t)a.fofs[(round + 1) * a.namt + amt] + ((cb >> sh) - (lo >> sh));
-        out.blk[d] = (uint32_t)child; out.meta[d] = make_meta(amt, 0, level - 1); out.base[d] = cb;
+        const BlockRec* rec = a.store.recs + child;
+        const uint32_t par = (round + 1) & 1;
+        out.meta[d] = make_meta(amt, 0, level - 1); out.base[d] = cb;
+        a.f_off[par][d] = __ldg(&rec->off); a.f_len[par][d] = __ldg(&rec->len);
         if (a.record) witness_mark(a.wbits, (uint32_t)child);
     } else {
         const uint8_t* src = item + 5;
@@ -928,6 +944,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         plan.ok = ok;
     }
     AsyncBuf<uint8_t> d_tables;
+    AsyncBuf<uint64_t> d_foff;
+    AsyncBuf<uint32_t> d_flen;
     auto run_dense = [&]() {
         // tables: per_amt (u64) | fofs (u32) | ftot (u32) through the pinned staging block
         const size_t nb_amt = plan.per_amt.size() * 8, nb_fofs = plan.fofs.size() * 4, nb_ftot = plan.ftot.size() * 4;
@@ -947,6 +965,10 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         da.vbase = pa; da.cnt = pa + namt; da.lo = pa + 2ull * namt; da.hi = pa + 3ull * namt;
         da.fofs = (const uint32_t*)(d_tables.p + nb_amt); da.ftot = (const uint32_t*)(d_tables.p + nb_amt + nb_fofs);
         da.namt = namt; da.record = skip_tx ? 0 : 1; da.wbits = wbits.p; da.fail = (uint32_t*)(dw + 14);
+        uint64_t fmax = 1;
+        for (uint32_t r = 0; r < plan.rounds; r++) fmax = std::max<uint64_t>(fmax, plan.ftot[r]);
+        d_foff.alloc(2 * fmax + 8, st); d_flen.alloc(2 * fmax + 8, st);
+        da.f_off[0] = d_foff.p; da.f_off[1] = d_foff.p + fmax; da.f_len[0] = d_flen.p; da.f_len[1] = d_flen.p + fmax;
         uint32_t top = 0;
         while (top < plan.rounds && plan.ftot[top] <= 1024) top++;
         if (top) { k_amt_dense<<<1, 1024, 0, st>>>(da, 0, top); IPCFP_LAUNCH_CHECK(); }

@@ -34,8 +34,34 @@ void PinnedPool::give(void* p, size_t cap) {
     free_list.push_back({p, cap});
 }
 
+// mapped counter blocks (host_words) are recycled per device across stores: cudaHostAlloc / cudaFreeHost are
+// slow, synchronising calls and a caller that re-ingests per request creates and destroys a store every time
+static std::mutex g_hw_mu;
+static std::vector<std::pair<int, std::unique_ptr<PinnedBuf<uint64_t>>>> g_hw_cache;
+static void host_words_take(int device, PinnedBuf<uint64_t>& out, size_t count) {
+    {
+        std::lock_guard<std::mutex> g(g_hw_mu);
+        for (size_t i = 0; i < g_hw_cache.size(); i++)
+            if (g_hw_cache[i].first == device && g_hw_cache[i].second->n >= count) {
+                out.swap(*g_hw_cache[i].second);
+                g_hw_cache.erase(g_hw_cache.begin() + (long)i);
+                return;
+            }
+    }
+    out.alloc(count);
+}
+static void host_words_give(int device, PinnedBuf<uint64_t>& b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(g_hw_mu);
+    if (g_hw_cache.size() >= 16) return;   // beyond that the buffer is simply freed by its owner
+    std::unique_ptr<PinnedBuf<uint64_t>> keep(new PinnedBuf<uint64_t>());
+    keep->swap(b);
+    g_hw_cache.emplace_back(device, std::move(keep));
+}
+
 Store::~Store() {
     cudaSetDevice(device);
+    host_words_give(device, host_words);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
@@ -196,7 +222,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     for (auto& e : s->ev) IPCFP_CUDA(cudaEventCreate(&e));
     cudaStream_t st = s->stream;
     s->dev_words.alloc(64);
-    s->host_words.alloc(512);
+    host_words_take(device, s->host_words, 512);
     {
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr); }
