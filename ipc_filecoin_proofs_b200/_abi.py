@@ -241,6 +241,40 @@ def event_result_from_c(r):
                          int(r.pass1_bytes), int(r.pass1_nodes), raw, data)
 
 
+def pack_event_proofs(proofs):
+    """list of EventProofPy → (packed ipcfp_event_proof records as uint8, data blob as uint8): the layout the C ABI returns."""
+    n = len(proofs)
+    recs = (EventProofC * max(n, 1))()
+    blob = bytearray()
+    for i, p in enumerate(proofs):
+        r = recs[i]
+        r.exec_index, r.event_index, r.emitter = int(p.exec_index), int(p.event_index), int(p.emitter)
+        r.n_topics, r.data_len = len(p.topics), len(p.data)
+        r.topics_off = len(blob)
+        for t in p.topics:
+            blob += bytes(t)
+        r.data_off = len(blob)
+        blob += bytes(p.data)
+        r.message_cid[:] = list(bytes(p.message_cid))
+    raw = np.frombuffer(bytes(recs)[:n * C.sizeof(EventProofC)], dtype=np.uint8).copy()
+    return raw, np.frombuffer(bytes(blob) + bytes(16), dtype=np.uint8).copy()
+
+
+def pack_storage_proofs(proofs):
+    """list of StorageProofPy → packed ipcfp_storage_proof records as uint8."""
+    n = len(proofs)
+    recs = (StorageProofC * max(n, 1))()
+    for i, p in enumerate(proofs):
+        r = recs[i]
+        r.actor_id = int(p.actor_id)
+        r.actor_state_cid[:] = list(bytes(p.actor_state_cid))
+        r.storage_root[:] = list(bytes(p.storage_root))
+        r.slot[:] = list(bytes(p.slot))
+        r.value[:] = list(bytes(p.value))
+        r.found, r.raw_len = int(bool(p.found)), int(p.raw_len)
+    return np.frombuffer(bytes(recs)[:n * C.sizeof(StorageProofC)], dtype=np.uint8).copy()
+
+
 @dataclass
 class StorageProofPy:
     actor_id: int
