@@ -920,6 +920,9 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
             for (uint32_t k = 0; k < namt; k++) {
                 const uint64_t c = cnts[k];
                 const uint64_t l = std::min(h_rng[k], c), h = std::max(l, std::min(h_rng[2 * IPCFP_MAX_PARENTS + k], c));
+                // an EMPTY share strictly inside an AMT (a shard without a single message): the general walk still follows the
+                // path to that position (its range test is "child begins before hi and ends after lo"); leave that corner to it
+                if (l == h && l > 0) ok = false;
                 plan.per_amt[k] = vb; plan.per_amt[namt + k] = c; plan.per_amt[2ull * namt + k] = l; plan.per_amt[3ull * namt + k] = h;
                 vb += h - l;
             }
