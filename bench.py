@@ -371,7 +371,7 @@ def run_engine(args, world, rank, local):
             "witness_bytes_per_s": stats["witness_bytes"] * world * args.steps / (dev_ms_max / 1e3),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "device_ms_breakdown": stats["ms"],
-            "roofline": {"kernel": "k_pass1", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"kernel": "k_pass1_occ8 (pass1_body, csrc/events.cu)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": pass1_traffic(), "algorithmic_bytes_per_launch": stats["pass1_bytes"], "ms_per_launch": p1,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_baseline,
