@@ -134,6 +134,9 @@ ipcfp_status ipcfp_host_alloc(size_t bytes, void** out) {
         if (!out) throw Error(IPCFP_ERR_INVALID_ARG, "null out");
         int cnt = 0;
         if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); throw Error(IPCFP_ERR_NO_DEVICE, "no CUDA device"); }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        NumaPrefer numa(dev);   // pages of the caller's staging buffers next to the GPU they feed
         IPCFP_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
     });
 }

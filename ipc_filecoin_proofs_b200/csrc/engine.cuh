@@ -13,6 +13,16 @@ namespace ipcfp {
 
 // Grow-only cache of pinned host buffers so result read-backs run at PCIe rate without paying
 // cudaHostAlloc on every call.
+// Pinned host buffers should live on the NUMA node the GPU's PCIe root hangs off: a D2H / H2D that crosses the socket
+// interconnect loses bandwidth, and with one process per GPU on a two-socket box half of the ranks would otherwise land
+// on the far socket. Best effort and silent: the node comes from sysfs, the preference is a thread-local mempolicy
+// (MPOL_PREFERRED, so allocation never fails because of it) that lasts for the lifetime of this guard.
+struct NumaPrefer {
+    bool on = false;
+    explicit NumaPrefer(int device);
+    ~NumaPrefer();
+};
+
 struct PinnedPool {
     struct Buf { void* p; size_t cap; };
     std::mutex mu;

@@ -1,12 +1,51 @@
 // store.cu — ingest of the flat block set into the device arena, CID hash index build,
 // Blake2b-256 CID verification (K1), Blockstore::get/has, batched hash entry points (K1/K2/K2b).
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "engine.cuh"
 #include "hashes.cuh"
 
 namespace ipcfp {
+
+// ------------------------------------------------------------------------------------------ NUMA placement of pinned memory
+static int gpu_numa_node(int device) {
+    static std::mutex mu;
+    static std::vector<int> cache;          // per device: -2 unknown, -1 none
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64) return -1;
+    if ((int)cache.size() <= device) cache.resize(device + 1, -2);
+    if (cache[device] != -2) return cache[device];
+    int node = -1;
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus - 1, device) == cudaSuccess) {
+        for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+        if (FILE* f = fopen(path.c_str(), "r")) {
+            int v = -1;
+            if (fscanf(f, "%d", &v) == 1 && v >= 0 && v < 64) node = v;
+            fclose(f);
+        }
+    } else cudaGetLastError();
+    cache[device] = node;
+    return node;
+}
+NumaPrefer::NumaPrefer(int device) {
+    if (getenv("IPCFP_NO_NUMA")) return;
+    int node = gpu_numa_node(device);
+    if (node < 0) return;
+    unsigned long mask = 1ul << node;
+    on = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 8 * sizeof mask + 1) == 0;
+}
+NumaPrefer::~NumaPrefer() {
+    if (on) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+}
 
 // ------------------------------------------------------------------------------------------ pinned pool
 PinnedPool::~PinnedPool() { for (auto& b : free_list) cudaFreeHost(b.p); }
@@ -25,6 +64,9 @@ void* PinnedPool::take(size_t bytes, size_t* cap_out) {
     }
     size_t cap = bytes < 4096 ? 4096 : bytes + bytes / 8;
     void* p = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    NumaPrefer numa(dev);
     IPCFP_CUDA(cudaMallocHost(&p, cap));
     *cap_out = cap;
     return p;
