@@ -19,6 +19,8 @@ namespace ipcfp {
 // (MPOL_PREFERRED, so allocation never fails because of it) that lasts for the lifetime of this guard.
 struct NumaPrefer {
     bool on = false;
+    int old_mode = 0;
+    unsigned long old_mask[16] = {};   // the caller's own policy (e.g. numactl) is put back afterwards
     explicit NumaPrefer(int device);
     ~NumaPrefer();
 };

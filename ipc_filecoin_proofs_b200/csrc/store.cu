@@ -40,11 +40,14 @@ NumaPrefer::NumaPrefer(int device) {
     if (getenv("IPCFP_NO_NUMA")) return;
     int node = gpu_numa_node(device);
     if (node < 0) return;
+    if (syscall(SYS_get_mempolicy, &old_mode, old_mask, 8 * sizeof old_mask, nullptr, 0) != 0) return;
     unsigned long mask = 1ul << node;
     on = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 8 * sizeof mask + 1) == 0;
 }
 NumaPrefer::~NumaPrefer() {
-    if (on) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    if (!on) return;
+    if (old_mode == 0 /* MPOL_DEFAULT */) syscall(SYS_set_mempolicy, 0, nullptr, 0);
+    else syscall(SYS_set_mempolicy, old_mode, old_mask, 8 * sizeof old_mask);
 }
 
 // ------------------------------------------------------------------------------------------ pinned pool
