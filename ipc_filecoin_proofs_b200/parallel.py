@@ -5,8 +5,8 @@ Two things span shards and are resolved here with a handful of small collectives
 
   * the execution order (reference events/utils.rs:48-94: concatenate every message AMT, first
     occurrence of a CID wins) — a distributed hash join: bucketize → all-to-all → dedup →
-    all-gather of the (tiny) duplicate position lists → exec index ↔ raw position arithmetic →
-    fetch of the message CIDs the local proofs need;
+    one all-gather of the (tiny) duplicate position lists and of the exec indices each rank's proofs need →
+    exec index ↔ raw position arithmetic for everybody's requests → fetch on the owners + all-reduce;
   * the witness CID set (reference common/witness.rs:24-40 BTreeSet union) — all-gather of the
     per-shard sorted CID lists + merge (sort/unique) on the device.
 
@@ -233,45 +233,51 @@ def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indic
         recv = coll.all_to_all_bytes(send, cap * ENTRY)
     with _Phase("x.dedup"):
         dups_local = ops.dedup(recv, recv_counts, world, cap)
-    # one fixed-size all-gather carries the duplicate positions of every owner ([count, positions…]);
-    # the rare overflow falls back to the variable-length path
+    # ONE fixed-size all-gather carries, per rank, the duplicate positions it found as an owner and the exec indices its
+    # proofs need: [n_dups, n_need, dups…(DUP_CAP), need…(capq)]. Every rank then knows D and every rank's requests, so the
+    # raw positions of ALL requests are derived locally (no second round trip). The rare overflow of the duplicate list
+    # falls back to the variable-length gather.
     DUP_CAP = 1023
+    need = np.unique(np.asarray(proof_exec_indices, dtype=np.uint64))
+    if need_counts is None:
+        with _Phase("x.need_counts"):
+            need_counts = coll.all_gather_i64([len(need)])[:, 0]
+    req_counts = np.asarray(need_counts, dtype=np.int64)
+    capq = int(req_counts.max()) if len(req_counts) else 0
     with _Phase("x.dups_gather"):
-        pad = np.zeros(DUP_CAP + 1, dtype=np.int64)
+        pad = np.zeros(2 + DUP_CAP + capq, dtype=np.int64)
         pad[0] = len(dups_local)
+        pad[1] = len(need)
         k = min(len(dups_local), DUP_CAP)
-        pad[1:1 + k] = dups_local[:k].view(np.int64)
+        pad[2:2 + k] = dups_local[:k].view(np.int64)
+        pad[2 + DUP_CAP:2 + DUP_CAP + len(need)] = need.view(np.int64)
         allp = coll.all_gather_i64(pad)
         if int(allp[:, 0].max()) > DUP_CAP:
             dups, _ = coll.all_gather_var_u64(dups_local)
         else:
-            dups = np.concatenate([allp[r, 1:1 + int(allp[r, 0])] for r in range(world)]).view(np.uint64)
+            dups = np.concatenate([allp[r, 2:2 + int(allp[r, 0])] for r in range(world)]).view(np.uint64)
     D = np.sort(dups)
     n_exec = nraw - len(D)
-    # exec.get(i) must exist for every matching receipt (checked in ascending order by the reference);
-    # the verdict travels with the position requests
+    # exec.get(i) must exist for every matching receipt (checked in ascending order by the reference, events/generator.rs:244-246);
+    # each rank's verdict rides on the answer all-reduce below, so all ranks fail together
     matching = np.asarray(matching, dtype=np.uint64)
     bad = matching[matching >= np.uint64(n_exec)]
-    my_bad = int(bad.min()) if len(bad) else np.iinfo(np.int64).max
-    need = np.unique(np.asarray(proof_exec_indices, dtype=np.uint64))
-    pos = raw_positions_of(np.minimum(need, np.uint64(max(n_exec, 1) - 1)), D)
-    with _Phase("x.req_gather"):
-        if need_counts is None:
-            need_counts = coll.all_gather_i64([len(need)])[:, 0]
-        req_counts = np.asarray(need_counts, dtype=np.int64)
-        capq = int(req_counts.max()) if len(req_counts) else 0
-        padq = np.zeros(capq + 1, dtype=np.int64)      # [MISSING_EXEC verdict, positions…]
-        padq[0] = my_bad
-        padq[1:1 + len(pos)] = pos.view(np.int64)
-        allq = coll.all_gather_i64(padq)
-        first_bad = int(allq[:, 0].min())
-        if first_bad != np.iinfo(np.int64).max:
-            raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
-        req_all = np.concatenate([allq[r, 1:1 + int(req_counts[r])] for r in range(world)]).view(np.uint64) if capq else np.zeros(0, np.uint64)
+    NO_BAD = np.iinfo(np.int64).max
+    my_bad = int(bad.min()) if len(bad) else NO_BAD
+    last = np.uint64(max(n_exec, 1) - 1)
+    req_all = np.concatenate([raw_positions_of(np.minimum(allp[r, 2 + DUP_CAP:2 + DUP_CAP + int(allp[r, 1])].view(np.uint64), last), D)
+                              for r in range(world)]) if capq else np.zeros(0, np.uint64)
     with _Phase("x.fetch"):
         ans = ops.fetch(seg_ptr, nseg, pos0, req_all)                # zeros where another rank owns the position
     with _Phase("x.ans_reduce"):
-        ans = coll.all_reduce_sum_i64(ans.reshape(-1).view(np.int64)).view(np.uint8).reshape(-1, REC)
+        verdict = np.zeros(world, dtype=np.int64)
+        verdict[rank] = my_bad
+        flat = np.concatenate([np.ascontiguousarray(ans).reshape(-1).view(np.int64), verdict])
+        red = coll.all_reduce_sum_i64(flat)
+        first_bad = int(red[len(red) - world:].min())
+        if first_bad != NO_BAD:
+            raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
+        ans = red[:len(red) - world].view(np.uint8).reshape(-1, REC)
     start = int(req_counts[:rank].sum())
     mine = ans[start:start + len(need)]
     return n_exec, (need, mine)
