@@ -23,6 +23,11 @@ def test_cross_shard_protocol_gloo_cpu():
     dist_worker.run(dist_worker.cpu_worker, world=2)
 
 
+def test_cross_shard_protocol_gloo_cpu_world4():
+    """Same at world size 4: shares that start and end inside different message AMTs, three ranks without duplicates."""
+    dist_worker.run(dist_worker.cpu_worker, world=4)
+
+
 @pytest.mark.gpu
 def test_cross_shard_engine_two_ranks_one_gpu():
     """2 processes sharing cuda:0 over gloo: the CUDA engine on sharded stores + ipcfp_exec_* helpers."""
