@@ -1110,6 +1110,58 @@ oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, 
     return s;
 }
 void oracle_store_destroy(oracle_store* s) { delete s; }
+
+// TEST HOOK for tests/host_fuzz: pass 1 over one events-AMT root block, see oracle.h
+ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t* n_events, uint64_t* idx, uint64_t* emitter, uint8_t* some,
+                                      uint32_t* ntopics, uint64_t* dlen, uint64_t cap) {
+    try {
+        MemoryBlockstore bs;
+        Cid c;
+        memset(c.b.data(), 0, 38);
+        static const uint8_t prefix[6] = {0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20};
+        memcpy(c.b.data(), prefix, 6);
+        bs.m.emplace(c, std::make_pair(block, (uint32_t)n));
+        auto amt = Amt<StampedEvent>::load(c, bs, 3);
+        uint64_t k = 0;
+        amt.for_each([&](uint64_t j, const StampedEvent& se) {
+            auto log = extract_evm_log(se.event);
+            if (k < cap) {
+                idx[k] = j; emitter[k] = se.emitter; some[k] = log ? 1 : 0;
+                ntopics[k] = log ? (uint32_t)log->topics.size() : 0;
+                dlen[k] = log ? log->data.size() : 0;
+            }
+            k++;
+        });
+        *n_events = k;
+        return IPCFP_OK;
+    } catch (const Err& e) {
+        return e.status;
+    }
+}
+
+// TEST HOOK for tests/host_fuzz: one StampedEvent item + extract_evm_log, see oracle.h
+ipcfp_status oracle_decode_event(const uint8_t* p, uint64_t n, uint64_t* consumed, uint64_t* emitter, uint32_t* some, uint32_t* ntopics,
+                                 uint8_t* topics_out, uint64_t topics_cap, uint8_t* data_out, uint64_t data_cap, uint64_t* data_len) {
+    try {
+        Dec d(p, (size_t)n);
+        StampedEvent se = ValueDec<StampedEvent>::dec(d);
+        *consumed = d.pos;
+        *emitter = se.emitter;
+        auto log = extract_evm_log(se.event);
+        *some = log ? 1 : 0;
+        *ntopics = 0;
+        *data_len = 0;
+        if (log) {
+            *ntopics = (uint32_t)log->topics.size();
+            for (size_t k = 0; k < log->topics.size() && 32 * (k + 1) <= topics_cap; k++) memcpy(topics_out + 32 * k, log->topics[k].data(), 32);
+            *data_len = log->data.size();
+            memcpy(data_out, log->data.data(), std::min<size_t>(log->data.size(), (size_t)data_cap));
+        }
+        return IPCFP_OK;
+    } catch (const Err& e) {
+        return e.status;
+    }
+}
 uint64_t oracle_store_verify_cids(const oracle_store* s, uint32_t threads) {
     if (threads < 1) threads = 1;
     std::vector<uint64_t> bad(threads, UINT64_MAX);

@@ -66,6 +66,18 @@ ipcfp_status oracle_verify_storage_proofs(const ipcfp_witness* w, const ipcfp_ti
                                           const ipcfp_storage_proof* proofs, uint64_t n_proofs, uint8_t* results);
 
 /* unit helpers */
+/* TEST HOOK (differential fuzzing, tests/host_fuzz): decode ONE StampedEvent item starting at p (events/generator.rs:218 via
+ * fvm_shared StampedEvent) and run extract_evm_log on it (common/evm.rs:13-59). Returns IPCFP_OK or IPCFP_ERR_DECODE.
+ * consumed = bytes of the item; some = log is Some; topics_out receives min(ntopics, cap/32) topics; data_len the full length. */
+ipcfp_status oracle_decode_event(const uint8_t* p, uint64_t n, uint64_t* consumed, uint64_t* emitter, uint32_t* some, uint32_t* ntopics,
+                                 uint8_t* topics_out, uint64_t topics_cap, uint8_t* data_out, uint64_t data_cap, uint64_t* data_len);
+
+/* TEST HOOK: what pass 1 does with ONE events-AMT root block: Amt::<StampedEvent>::load (v3) + for_each + extract_evm_log
+ * (events/generator.rs:215-236) over a store that holds only this block (a child link therefore fails as a missing block).
+ * Per visited event (up to cap): AMT index, emitter, Some/None, number of topics, data length. */
+ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t* n_events, uint64_t* idx, uint64_t* emitter, uint8_t* some,
+                                      uint32_t* ntopics, uint64_t* dlen, uint64_t cap);
+
 void oracle_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]);

@@ -1,0 +1,38 @@
+"""Differential fuzz of the device decoders, compiled for the HOST from the very same headers (tests/host_fuzz/fuzz_events.cu):
+  * register-window fast path `fast_stamped_event` vs the strict decoder `parse_stamped_event` (csrc/ipld.cuh),
+  * byte-layout check of the dense message-AMT walk vs `amt_node_begin` / `rd_cid` / `amt_node_finish`,
+  * the strict device decoder + extract_evm_log vs the CPU oracle (an independent implementation) on every fuzzed event,
+  * pass 1's per-receipt unit (one events-AMT root block: status class and the visited event list) vs the oracle.
+Whatever a shortcut accepts, the strict decoder must accept with the same meaning — that is what lets the kernels take the
+shortcut without changing a result — and the strict decoder must agree with the oracle on well-formed AND malformed input.
+No GPU involved (nvcc host pass only); the oracle is linked as the checker."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fast_paths_agree_with_strict_decoders():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "fuzz_events")
+    src = os.path.join(ROOT, "tests", "host_fuzz", "fuzz_events.cu")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe, src, os.path.join(ROOT, "oracle", "oracle.cpp"), "-lpthread"],
+                          cwd=ROOT)
+    for seed in ("535", "20260922"):
+        out = subprocess.run([exe, "600000", seed], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("ok:")]
+        assert len(lines) == 3, out.stdout
+        # the shortcuts must actually be taken on a large share of the inputs, or the comparison says nothing
+        for l in lines:
+            if "accepted" in l:
+                total, acc = int(l.split()[1]), int(l.split("accepted")[1].split()[0])
+                assert acc > total // 4, l
+        assert any("compared with the oracle" in l for l in lines) and any("root blocks agree with the oracle" in l for l in lines)
