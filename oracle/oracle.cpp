@@ -1111,6 +1111,29 @@ oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, 
 }
 void oracle_store_destroy(oracle_store* s) { delete s; }
 
+// TEST HOOK for tests/host_fuzz: one receipts-AMT node, see oracle.h
+ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t height, uint32_t* n_links, uint32_t* n_vals, uint8_t* has_root,
+                                         uint8_t* roots38, uint64_t cap) {
+    try {
+        Dec d(p, (size_t)n);
+        AmtNode<Receipt> nd = decode_amt_node<Receipt>(d, 3, height);
+        d.end();
+        uint32_t nl = 0, nv = 0;
+        for (auto& l : nd.links) if (l) nl++;
+        for (auto& v : nd.vals) if (v) {
+            if (nv < cap) {
+                has_root[nv] = v->events_root ? 1 : 0;
+                if (v->events_root) memcpy(roots38 + 38 * nv, v->events_root->b.data(), 38);
+            }
+            nv++;
+        }
+        *n_links = nl; *n_vals = nv;
+        return IPCFP_OK;
+    } catch (const Err& e) {
+        return e.status;
+    }
+}
+
 // TEST HOOK for tests/host_fuzz: pass 1 over one events-AMT root block, see oracle.h
 ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t* n_events, uint64_t* idx, uint64_t* emitter, uint8_t* some,
                                       uint32_t* ntopics, uint64_t* dlen, uint64_t cap) {

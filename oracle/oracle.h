@@ -78,6 +78,12 @@ ipcfp_status oracle_decode_event(const uint8_t* p, uint64_t n, uint64_t* consume
 ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t* n_events, uint64_t* idx, uint64_t* emitter, uint8_t* some,
                                       uint32_t* ntopics, uint64_t* dlen, uint64_t cap);
 
+/* TEST HOOK: one node of an Amtv0<Receipt> (non-root: [bmap, [links], [receipts]]) at the given height, whole-node decode as
+ * fvm_ipld_amt does it (events/generator.rs:196,249). Out: number of links / values; per value (up to cap) whether it has an
+ * events root and the 38 CID bytes. */
+ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t height, uint32_t* n_links, uint32_t* n_vals, uint8_t* has_root,
+                                         uint8_t* roots38, uint64_t cap);
+
 void oracle_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]);

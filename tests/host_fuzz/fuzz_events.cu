@@ -280,6 +280,95 @@ static int fuzz_events_roots(uint64_t iters) {
     return 0;
 }
 
+// ---- fifth property: one receipts-AMT node (the unit of pass 2's path walk, receipts_get in csrc/events.cu) vs the oracle ---
+static int fuzz_receipt_nodes(uint64_t iters) {
+    uint64_t okn = 0, bad = 0;
+    std::vector<uint8_t> buf;
+    for (uint64_t it = 0; it < iters; it++) {
+        uint32_t height = (uint32_t)(rnd() % 3), n = (uint32_t)(rnd() % 9);
+        std::vector<uint8_t> node;
+        put_head(node, 4, 3);
+        put_head(node, 2, 1);
+        uint8_t bm = 0;
+        for (uint32_t k = 0; k < n;) { uint32_t b = (uint32_t)(rnd() % 8); if (!(bm >> b & 1)) { bm |= (uint8_t)(1u << b); k++; } }
+        node.push_back(bm);
+        auto cid = [&]() {
+            static const uint8_t head[11] = {0xd8, 0x2a, 0x58, 0x27, 0x00, 0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20};
+            node.insert(node.end(), head, head + 11);
+            for (int b = 0; b < 32; b++) node.push_back((uint8_t)rnd());
+        };
+        if (height) { put_head(node, 4, n); for (uint32_t k = 0; k < n; k++) cid(); put_head(node, 4, 0); }
+        else {
+            put_head(node, 4, 0);
+            put_head(node, 4, n);
+            for (uint32_t k = 0; k < n; k++) {
+                put_head(node, 4, 4);
+                put_head(node, rnd() % 32 == 0 ? 1 : 0, rnd() % 8 == 0 ? rnd() : rnd() % 40);   // exit code (sometimes negative / huge)
+                size_t rl = rnd() % 8 == 0 ? rnd() % 70 : 0;
+                put_head(node, 2, rl);
+                for (size_t b = 0; b < rl; b++) node.push_back((uint8_t)rnd());
+                put_head(node, 0, rnd() % (1ull << 33));
+                if (rnd() % 4 == 0) node.push_back(0xf6); else cid();
+            }
+        }
+        unsigned nmut = it % 2 ? 1 + (unsigned)(rnd() % 2) : 0;
+        for (unsigned m = 0; m < nmut; m++) {
+            size_t at = rnd() % node.size();
+            switch (rnd() % 4) {
+                case 0: node[at] = (uint8_t)rnd(); break;
+                case 1: node[at] ^= (uint8_t)(1u << (rnd() % 8)); break;
+                case 2: node.erase(node.begin() + (long)at); break;
+                default: node.insert(node.begin() + (long)at, (uint8_t)rnd()); break;
+            }
+            if (node.empty()) node.push_back(0x83);
+        }
+        unsigned lead = (unsigned)(rnd() % 16);
+        buf.assign(16 + lead, 0xEE);
+        buf.insert(buf.end(), node.begin(), node.end());
+        buf.insert(buf.end(), 48, (uint8_t)rnd());
+        const uint8_t* p = buf.data() + 16 + lead;
+        const uint32_t len = (uint32_t)node.size();
+        Rd r(p, len);
+        AmtNodeHdr h;
+        amt_node_begin(r, 3, h);
+        uint32_t nv = rd_array(r);
+        uint32_t root_off[8];
+        for (uint32_t v = 0; v < nv && !r.err; v++) {           // parse_receipt, keeping where the events root is
+            rd_array_exact(r, 4);
+            uint64_t ec = rd_uint(r);
+            if (!r.err && ec > 0xffffffffull) rd_fail(r, CE_RANGE);
+            uint32_t l;
+            (void)rd_bytes(r, l);
+            (void)rd_uint(r);
+            uint32_t off = rd_opt_cid(r);
+            if (v < 8) root_off[v] = off;
+        }
+        amt_node_finish(r, h, nv, height);
+        uint32_t onl = 0, onv = 0;
+        uint8_t has[16], roots[16 * 38];
+        int ost = (int)oracle_decode_receipts_node(p, len, height, &onl, &onv, has, roots, 16);
+        bool ok = (ost == IPCFP_OK) == (r.err == 0);
+        if (ok && !r.err) {
+            ok = onl == h.nl && onv == nv;
+            for (uint32_t v = 0; ok && v < nv && v < 8; v++) {
+                bool dev_has = root_off[v] != 0xffffffffu;
+                ok = dev_has == (has[v] != 0) && (!dev_has || memcmp(p + root_off[v], roots + 38 * v, 38) == 0);
+            }
+        }
+        if (!ok) {
+            fprintf(stderr, "RECEIPT NODE MISMATCH at iteration %llu: device err %u nl %u nv %u; oracle status %d nl %u nv %u\nnode:", (unsigned long long)it, r.err, h.nl, nv,
+                    ost, onl, onv);
+            for (size_t k = 0; k < node.size(); k++) fprintf(stderr, " %02x", node[k]);
+            fprintf(stderr, "\n");
+            return 1;
+        }
+        if (r.err) bad++; else okn++;
+    }
+    printf("ok: %llu receipts-AMT nodes agree with the oracle (%llu decoded, %llu decode errors)\n", (unsigned long long)iters, (unsigned long long)okn,
+           (unsigned long long)bad);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     uint64_t iters = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
     rng_state = argc > 2 ? strtoull(argv[2], nullptr, 10) : 0x1FC0FFEEull;
@@ -351,6 +440,7 @@ int main(int argc, char** argv) {
     }
     if (fuzz_amt_nodes(iters / 2)) return 1;
     if (fuzz_events_roots(iters / 8)) return 1;
+    if (fuzz_receipt_nodes(iters / 4)) return 1;
     printf("ok: %llu events, fast path accepted %llu (all equal to the strict decoder), declined %llu; strict decoder accepted %llu; %llu compared with the oracle\n",
            (unsigned long long)iters, (unsigned long long)accepted, (unsigned long long)rejected, (unsigned long long)strict_ok, (unsigned long long)oracle_checked);
     return 0;
