@@ -1095,6 +1095,16 @@ using namespace orc;
 
 struct oracle_store { MemoryBlockstore bs; std::vector<std::pair<const uint8_t*, uint32_t>> order; std::vector<Cid> cids; };
 
+template <class V> static void hamt_node_lookup_t(const Bytes& raw, uint32_t idx, const Bytes& key, int32_t* kind, const std::function<void(const V&)>& on_value,
+                                                  const std::function<void(const Cid&)>& on_link) {
+    HamtNode<V> nd = decode_hamt_node<V>(raw);
+    *kind = 0;
+    if (!nd.test(idx)) return;
+    auto& p = nd.ptrs[nd.index_for(idx)];
+    if (std::holds_alternative<Cid>(p)) { *kind = 2; on_link(std::get<Cid>(p)); return; }
+    for (auto& kv : std::get<std::vector<typename HamtNode<V>::KV>>(p))
+        if (kv.key == key) { *kind = 1; on_value(kv.val); return; }
+}
 extern "C" {
 
 oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t* lengths, const uint8_t* blob,
@@ -1110,6 +1120,22 @@ oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, 
     return s;
 }
 void oracle_store_destroy(oracle_store* s) { delete s; }
+
+// TEST HOOK for tests/host_fuzz: one HAMT node, see oracle.h
+ipcfp_status oracle_hamt_node_lookup(const uint8_t* p, uint64_t n, int vkind, uint32_t idx, const uint8_t* key, uint32_t keylen, int32_t* kind,
+                                     uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+    try {
+        Bytes raw(p, p + n), k(key, key + keylen);
+        *out_len = 0;
+        auto put = [&](const uint8_t* q, size_t m) { *out_len = m; memcpy(out, q, std::min<size_t>(m, (size_t)out_cap)); };
+        auto on_link = [&](const Cid& c) { put(c.b.data(), 38); };
+        if (vkind == 0) hamt_node_lookup_t<ActorState>(raw, idx, k, kind, [&](const ActorState& a) { put(a.state.b.data(), 38); }, on_link);
+        else hamt_node_lookup_t<RawU8Vec>(raw, idx, k, kind, [&](const RawU8Vec& v) { put(v.v.data(), v.v.size()); }, on_link);
+        return IPCFP_OK;
+    } catch (const Err& e) {
+        return e.status;
+    }
+}
 
 // TEST HOOK for tests/host_fuzz: one receipts-AMT node, see oracle.h
 ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t height, uint32_t* n_links, uint32_t* n_vals, uint8_t* has_root,

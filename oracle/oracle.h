@@ -84,6 +84,12 @@ ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t
 ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t height, uint32_t* n_links, uint32_t* n_vals, uint8_t* has_root,
                                          uint8_t* roots38, uint64_t cap);
 
+/* TEST HOOK: one HAMT node (fvm_ipld_hamt v3 layout), whole-node decode, then the pointer of slot `idx` for `key`
+ * (storage/decode.rs:79-96, common/decode.rs:29-39). vkind 0 = ActorState values, 1 = Vec<u8> values (CBOR array of u8).
+ * kind: 0 None, 1 value (out = ActorState.state CID, 38 bytes / the u8 elements), 2 link (out = the 38 CID bytes). */
+ipcfp_status oracle_hamt_node_lookup(const uint8_t* p, uint64_t n, int vkind, uint32_t idx, const uint8_t* key, uint32_t keylen, int32_t* kind,
+                                     uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+
 void oracle_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]);

@@ -369,6 +369,116 @@ static int fuzz_receipt_nodes(uint64_t iters) {
     return 0;
 }
 
+// ---- sixth property: one HAMT node (state tree / EVM storage, csrc/storage.cu hamt_get's unit) vs the oracle --------------
+static int fuzz_hamt_nodes(uint64_t iters) {
+    uint64_t okn = 0, bad = 0, hits = 0, links = 0;
+    std::vector<uint8_t> buf;
+    for (uint64_t it = 0; it < iters; it++) {
+        int vkind = (int)(rnd() % 2);
+        uint32_t np = (uint32_t)(rnd() % 6);
+        // bitfield with np bits among the low 32 slots (bit width 5), big-endian, right aligned, minimal or padded
+        uint32_t bits = 0;
+        for (uint32_t k = 0; k < np;) { uint32_t b = (uint32_t)(rnd() % 32); if (!(bits >> b & 1)) { bits |= 1u << b; k++; } }
+        std::vector<uint8_t> bf;
+        for (int s = 24; s >= 0; s -= 8) if (!bf.empty() || (bits >> s) & 0xff || rnd() % 8 == 0) bf.push_back((uint8_t)(bits >> s));
+        if (rnd() % 16 == 0) bf.insert(bf.begin(), (size_t)(rnd() % 30), 0);
+        std::vector<uint8_t> node;
+        put_head(node, 4, 2);
+        put_head(node, 2, bf.size());
+        node.insert(node.end(), bf.begin(), bf.end());
+        put_head(node, 4, np);
+        std::vector<std::vector<uint8_t>> keys;
+        auto cid = [&]() {
+            static const uint8_t head[11] = {0xd8, 0x2a, 0x58, 0x27, 0x00, 0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20};
+            node.insert(node.end(), head, head + 11);
+            for (int b = 0; b < 32; b++) node.push_back((uint8_t)rnd());
+        };
+        for (uint32_t k = 0; k < np; k++) {
+            if (rnd() % 3 == 0) { cid(); continue; }
+            uint32_t nk = 1 + (uint32_t)(rnd() % 3);
+            put_head(node, 4, nk);
+            for (uint32_t j = 0; j < nk; j++) {
+                put_head(node, 4, 2);
+                std::vector<uint8_t> key(vkind ? 32 : 1 + rnd() % 9);
+                for (auto& b : key) b = (uint8_t)rnd();
+                if (!keys.empty() && rnd() % 16 == 0) key = keys[rnd() % keys.size()];    // a repeated key: the first one wins
+                keys.push_back(key);
+                put_head(node, 2, key.size());
+                node.insert(node.end(), key.begin(), key.end());
+                if (vkind == 0) {
+                    put_head(node, 4, 5);
+                    cid(); cid();
+                    put_head(node, 0, rnd() % 100000);
+                    size_t bl = rnd() % 12;
+                    put_head(node, 2, bl);
+                    for (size_t b = 0; b < bl; b++) node.push_back((uint8_t)rnd());
+                    if (rnd() % 2) node.push_back(0xf6); else { put_head(node, 2, 3); node.push_back(1); node.push_back(2); node.push_back(3); }
+                } else {
+                    size_t vl = rnd() % 34;
+                    put_head(node, 4, vl);
+                    for (size_t b = 0; b < vl; b++) put_head(node, 0, rnd() % 16 == 0 ? rnd() % 300 : rnd() % 256);
+                }
+            }
+        }
+        unsigned nmut = it % 2 ? 1 + (unsigned)(rnd() % 2) : 0;
+        for (unsigned m = 0; m < nmut; m++) {
+            size_t at = rnd() % node.size();
+            switch (rnd() % 4) {
+                case 0: node[at] = (uint8_t)rnd(); break;
+                case 1: node[at] ^= (uint8_t)(1u << (rnd() % 8)); break;
+                case 2: node.erase(node.begin() + (long)at); break;
+                default: node.insert(node.begin() + (long)at, (uint8_t)rnd()); break;
+            }
+            if (node.empty()) node.push_back(0x82);
+        }
+        std::vector<uint8_t> key = (!keys.empty() && rnd() % 4) ? keys[rnd() % keys.size()] : std::vector<uint8_t>(vkind ? 32 : 3, (uint8_t)rnd());
+        uint32_t idx = rnd() % 4 ? (uint32_t)(rnd() % 32) : (uint32_t)(rnd() % 256);
+        if (bits && rnd() % 2) { do idx = (uint32_t)(rnd() % 32); while (!(bits >> idx & 1)); }
+        unsigned lead = (unsigned)(rnd() % 16);
+        buf.assign(16 + lead, 0xEE);
+        buf.insert(buf.end(), node.begin(), node.end());
+        buf.insert(buf.end(), 48, (uint8_t)rnd());
+        const uint8_t* p = buf.data() + 16 + lead;
+        const uint32_t len = (uint32_t)node.size();
+        Rd r(p, len);
+        HamtHit hit;
+        hamt_node_lookup(r, vkind, idx, key.data(), (uint32_t)key.size(), hit);
+        int32_t okind = 0;
+        uint8_t oout[4096];
+        uint64_t olen = 0;
+        int ost = (int)oracle_hamt_node_lookup(p, len, vkind, idx, key.data(), (uint32_t)key.size(), &okind, oout, sizeof oout, &olen);
+        bool ok = (ost == IPCFP_OK) == (r.err == 0);
+        if (ok && !r.err) {
+            ok = okind == hit.kind;
+            if (ok && hit.kind == 2) ok = olen == 38 && memcmp(p + hit.link_off, oout, 38) == 0;
+            if (ok && hit.kind == 1) {
+                Rd r2(p, len);
+                r2.pos = hit.val_off;
+                if (vkind == 0) { uint32_t so; parse_actor_state(r2, so); ok = !r2.err && olen == 38 && memcmp(p + so, oout, 38) == 0; }
+                else {
+                    uint32_t fo;
+                    uint32_t ne = parse_u8vec(r2, fo);
+                    ok = !r2.err && ne == olen;
+                    Rd r3(p, len);
+                    r3.pos = fo;
+                    for (uint32_t e = 0; ok && e < ne; e++) ok = rd_uint(r3) == oout[e];
+                }
+            }
+        }
+        if (!ok) {
+            fprintf(stderr, "HAMT NODE MISMATCH at iteration %llu: device err %u kind %d; oracle status %d kind %d len %llu\nnode:", (unsigned long long)it, r.err, hit.kind, ost,
+                    okind, (unsigned long long)olen);
+            for (size_t k = 0; k < node.size(); k++) fprintf(stderr, " %02x", node[k]);
+            fprintf(stderr, "\n");
+            return 1;
+        }
+        if (r.err) bad++; else { okn++; hits += hit.kind == 1; links += hit.kind == 2; }
+    }
+    printf("ok: %llu HAMT nodes agree with the oracle (%llu decoded: %llu values found, %llu links; %llu decode errors)\n", (unsigned long long)iters,
+           (unsigned long long)okn, (unsigned long long)hits, (unsigned long long)links, (unsigned long long)bad);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     uint64_t iters = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
     rng_state = argc > 2 ? strtoull(argv[2], nullptr, 10) : 0x1FC0FFEEull;
@@ -441,6 +551,7 @@ int main(int argc, char** argv) {
     if (fuzz_amt_nodes(iters / 2)) return 1;
     if (fuzz_events_roots(iters / 8)) return 1;
     if (fuzz_receipt_nodes(iters / 4)) return 1;
+    if (fuzz_hamt_nodes(iters / 4)) return 1;
     printf("ok: %llu events, fast path accepted %llu (all equal to the strict decoder), declined %llu; strict decoder accepted %llu; %llu compared with the oracle\n",
            (unsigned long long)iters, (unsigned long long)accepted, (unsigned long long)rejected, (unsigned long long)strict_ok, (unsigned long long)oracle_checked);
     return 0;

@@ -3,7 +3,8 @@
   * byte-layout check of the dense message-AMT walk vs `amt_node_begin` / `rd_cid` / `amt_node_finish`,
   * the strict device decoder + extract_evm_log vs the CPU oracle (an independent implementation) on every fuzzed event,
   * pass 1's per-receipt unit (one events-AMT root block: status class and the visited event list) vs the oracle,
-  * one receipts-AMT node (the unit of pass 2's path walk: links / receipts / events roots) vs the oracle.
+  * one receipts-AMT node (the unit of pass 2's path walk: links / receipts / events roots) vs the oracle,
+  * one HAMT node (state tree and EVM storage: bitfield, links, buckets, ActorState / Vec<u8> values) vs the oracle.
 Whatever a shortcut accepts, the strict decoder must accept with the same meaning — that is what lets the kernels take the
 shortcut without changing a result — and the strict decoder must agree with the oracle on well-formed AND malformed input.
 No GPU involved (nvcc host pass only); the oracle is linked as the checker."""
@@ -30,11 +31,11 @@ def test_fast_paths_agree_with_strict_decoders():
         out = subprocess.run([exe, "600000", seed], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-2000:]
         lines = [l for l in out.stdout.splitlines() if l.startswith("ok:")]
-        assert len(lines) == 4, out.stdout
+        assert len(lines) == 5, out.stdout
         # the shortcuts must actually be taken on a large share of the inputs, or the comparison says nothing
         for l in lines:
             if "accepted" in l:
                 total, acc = int(l.split()[1]), int(l.split("accepted")[1].split()[0])
                 assert acc > total // 4, l
         assert any("compared with the oracle" in l for l in lines) and any("root blocks agree with the oracle" in l for l in lines)
-        assert any("receipts-AMT nodes agree with the oracle" in l for l in lines)
+        assert any("receipts-AMT nodes agree with the oracle" in l for l in lines) and any("HAMT nodes agree with the oracle" in l for l in lines)
