@@ -870,8 +870,13 @@ static EventGenOut generate_event_proof(const Blockstore& net, const TipsetIn& t
                 else {
                     uint64_t glo = ts.n_receipts ? (uint64_t)((__uint128_t)nraw * lo / ts.n_receipts) : 0, ghi = ts.n_receipts ? (uint64_t)((__uint128_t)nraw * hi / ts.n_receipts) : 0;
                     (void)rank; (void)world;
-                    uint64_t base = bases[ai];
+                    // ownership of a share of the raw list, per AMT (same rule as the engine): an AMT that ends at or
+                    // before the share's start contributes nothing (its right-most nodes may span indices past its count — they
+                    // belong to the shard that owns its tail); the shard that reaches an AMT's end owns everything from there on
+                    uint64_t base = bases[ai], end = base + amt.count;
                     uint64_t l = glo > base ? glo - base : 0, h = ghi > base ? ghi - base : 0;
+                    if (glo >= end && !(end == base && glo == base)) l = h = 0;
+                    else if (ghi >= end) h = UINT64_MAX;
                     if (h > l) amt.for_each_range_node(amt.root, amt.height, 0, l, h, [](uint64_t, const Cid&) {});
                 }
                 ai++;
@@ -1120,6 +1125,27 @@ oracle_store* oracle_store_create(const uint8_t* cids, const uint64_t* offsets, 
     return s;
 }
 void oracle_store_destroy(oracle_store* s) { delete s; }
+
+// TEST HOOK for tests/host_fuzz: the raw message list, see oracle.h
+ipcfp_status oracle_message_list(const oracle_store* s, const ipcfp_tipset_desc* t, uint8_t* out38, uint64_t cap, uint64_t* n) {
+    try {
+        uint64_t k = 0;
+        for (uint32_t b = 0; b < t->n_parents; b++) {
+            Cid tx = cid_from(t->parent_txmeta_cids + 38 * b);
+            Bytes raw;
+            if (!s->bs.get(tx, raw)) throw Err(IPCFP_ERR_MISSING_BLOCK, "missing TxMeta " + cid_hex(tx), b);
+            auto roots = decode_txmeta(raw);
+            for (const Cid* r : {&roots.first, &roots.second}) {
+                auto amt = Amt<Cid>::load(*r, s->bs, 0);
+                amt.for_each([&](uint64_t, const Cid& c) { if (k < cap) memcpy(out38 + 38 * k, c.b.data(), 38); k++; });
+            }
+        }
+        *n = k;
+        return IPCFP_OK;
+    } catch (const Err& e) {
+        return e.status;
+    }
+}
 
 // TEST HOOK for tests/host_fuzz: one HAMT node, see oracle.h
 ipcfp_status oracle_hamt_node_lookup(const uint8_t* p, uint64_t n, int vkind, uint32_t idx, const uint8_t* key, uint32_t keylen, int32_t* kind,

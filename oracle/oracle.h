@@ -90,6 +90,10 @@ ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t 
 ipcfp_status oracle_hamt_node_lookup(const uint8_t* p, uint64_t n, int vkind, uint32_t idx, const uint8_t* key, uint32_t keylen, int32_t* kind,
                                      uint8_t* out, uint64_t out_cap, uint64_t* out_len);
 
+/* TEST HOOK: the concatenated ("raw") message list of a tipset — every BLS then SECP message AMT of every parent block,
+ * in order, BEFORE the first-seen dedup (events/utils.rs:48-94) — as 38-byte CIDs. */
+ipcfp_status oracle_message_list(const oracle_store* s, const ipcfp_tipset_desc* t, uint8_t* out38, uint64_t cap, uint64_t* n);
+
 void oracle_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]);
 void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]);

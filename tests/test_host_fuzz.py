@@ -39,3 +39,21 @@ def test_fast_paths_agree_with_strict_decoders():
                 assert acc > total // 4, l
         assert any("compared with the oracle" in l for l in lines) and any("root blocks agree with the oracle" in l for l in lines)
         assert any("receipts-AMT nodes agree with the oracle" in l for l in lines) and any("HAMT nodes agree with the oracle" in l for l in lines)
+
+
+def test_dense_walk_emulated_on_cpu_matches_oracle():
+    """tests/host_fuzz/emu_walk.cu: `amt_item_dense`, `shard_amt_ranges` and `make_dense_plan` (csrc/walk.cuh) compiled for the
+    host and run level by level, item by item, lane by lane over a host copy of the block store (arena + BlockRec array + CID
+    index laid out as ipcfp_store_create does), for whole tipsets and for every shard at world sizes 1, 2, 3 and 8 — against the
+    oracle's raw message list and its recorded block set."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "emu_walk")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(ROOT, "tests", "host_fuzz", "emu_walk.cu"),
+                           os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
+    out = subprocess.run([exe, "60", "11"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.startswith("ok: dense walk on the CPU == oracle for 60 tipsets"), out.stdout
