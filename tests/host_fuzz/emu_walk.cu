@@ -16,67 +16,14 @@
 #include <set>
 #include <vector>
 
-#undef __device__
-#define __device__ __location__(host) __location__(device)
-#ifndef __CUDA_ARCH__
-static inline unsigned host_funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
-#define __funnelshift_r(lo, hi, s) host_funnelshift_r((lo), (hi), (s))
-#define __byte_perm(x, y, s) 0u
-#define __popc(x) __builtin_popcount(x)
-#define __popcll(x) __builtin_popcountll(x)
-#define __ffs(x) __builtin_ffs(x)
-#define __ffsll(x) __builtin_ffsll(x)
-#define __ldg(p) (*(p))
-#define atomicMin(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
-#define atomicOr(p, v) (*(p) |= (v))
-#endif
+#include "host_shims.h"
 
 #include "../../ipc_filecoin_proofs_b200/csrc/walk.cuh"
 #include "../../oracle/oracle.h"
 #include "../../synth/synth.h"
+#include "host_store.h"
 
 using namespace ipcfp;
-
-struct HostStore {
-    std::vector<uint8_t> arena;
-    std::vector<BlockRec> recs;
-    std::vector<uint64_t> table;
-    StoreView view;
-    // mirrors ipcfp_store_create (csrc/store.cu): one CID class, digests from the CID bytes, equal CIDs keep the smallest index
-    HostStore(const uint8_t* cids, const uint64_t* offs, const uint32_t* lens, const uint8_t* blob, uint64_t blob_size, uint64_t n) {
-        arena.assign(16 + blob_size + 32, 0);
-        memcpy(arena.data() + 16, blob, blob_size);
-        recs.resize(n);
-        memset(&view, 0, sizeof view);
-        view.n_classes = 1;
-        memcpy(view.class_prefix[0], cids, 6);
-        uint64_t slots = 64;
-        while (slots < 2 * n) slots <<= 1;
-        table.assign(slots, 0);
-        for (uint64_t i = 0; i < n; i++) {
-            if (memcmp(cids + 38 * i, cids, 6)) { fprintf(stderr, "emu: several CID classes are not modelled\n"); exit(2); }
-            BlockRec r;
-            memset(&r, 0, sizeof r);
-            memcpy(r.d.w, cids + 38 * i + 6, 32);
-            r.off = offs[i]; r.len = lens[i]; r.cls = 0;
-            recs[i] = r;
-            uint64_t h = digest_hash(r.d, 0);
-            uint32_t fp = (uint32_t)(h >> 32) | 1u;
-            uint64_t slot = h & (slots - 1);
-            for (;;) {
-                uint64_t e = table[slot];
-                if (e == 0) { table[slot] = ((uint64_t)fp << 32) | (i + 1); break; }
-                if ((uint32_t)(e >> 32) == fp && digest_eq(recs[(uint32_t)e - 1].d, r.d)) break;   // first occurrence stays
-                slot = (slot + 1) & (slots - 1);
-            }
-        }
-        view.blob = arena.data() + 16;
-        view.recs = recs.data();
-        view.table = table.data();
-        view.mask = slots - 1;
-        view.n = (uint32_t)n;
-    }
-};
 
 static int fail(const char* what, uint64_t a = 0, uint64_t b = 0) {
     fprintf(stderr, "EMU MISMATCH: %s (%llu, %llu)\n", what, (unsigned long long)a, (unsigned long long)b);

@@ -57,3 +57,25 @@ def test_dense_walk_emulated_on_cpu_matches_oracle():
     out = subprocess.run([exe, "60", "11"], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.startswith("ok: dense walk on the CPU == oracle for 60 tipsets"), out.stdout
+
+
+def test_storage_path_emulated_on_cpu_matches_oracle():
+    """tests/host_fuzz/emu_storage.cu: `storage_proof_one`, `read_storage_slot`, `hamt_get` and the value decoders (csrc/storage.cuh)
+    compiled for the host and run spec by spec over a host copy of the store, against `oracle_generate_storage_proofs` — on the
+    synthetic state trees (six EVM actors = the six root shapes A1/A2/A3/B1/B2/C, present / absent / special slots, a missing
+    actor) and with one block of a proof path replaced by a mutated copy under the same CID: equal values, found flags, CIDs and
+    per-proof recorded block sets, or the same status at the same spec index."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "emu_storage")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20091", "-o", exe,
+                           os.path.join(ROOT, "tests", "host_fuzz", "emu_storage.cu"), os.path.join(ROOT, "oracle", "oracle.cpp"),
+                           os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
+    out = subprocess.run([exe, "8", "250", "77"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.startswith("ok: storage path on the CPU == oracle for 8 state trees"), out.stdout
+    runs_ok, runs_err = int(out.stdout.split(":")[2].split()[0]), int(out.stdout.split("equal,")[1].split()[0])
+    assert runs_ok > 100 and runs_err > 500, out.stdout
