@@ -79,3 +79,26 @@ def test_storage_path_emulated_on_cpu_matches_oracle():
     assert out.stdout.startswith("ok: storage path on the CPU == oracle for 8 state trees"), out.stdout
     runs_ok, runs_err = int(out.stdout.split(":")[2].split()[0]), int(out.stdout.split("equal,")[1].split()[0])
     assert runs_ok > 100 and runs_err > 500, out.stdout
+
+
+def test_event_path_emulated_on_cpu_matches_oracle():
+    """tests/host_fuzz/emu_events.cu: the per-item device code of generate_event_proof — k_setup's sequence, the dense message-AMT
+    walk, pass 1's per-receipt decode, `pass2_item` / `receipts_get` / `walk_events` (csrc/events_items.cuh, csrc/walk.cuh) —
+    compiled for the host and driven item by item over a host copy of the store, against `oracle_generate_event_proof`: matching
+    receipts, every EventProof field (message CID included), n_exec and the witness CID set on tipsets of many shapes (multi-node
+    events AMTs, Case A, malformed events, null roots, duplicate messages), and the same status at the same index when an
+    events / receipts block is mutated under its CID or missing."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "emu_events")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20091", "-o", exe,
+                           os.path.join(ROOT, "tests", "host_fuzz", "emu_events.cu"), os.path.join(ROOT, "oracle", "oracle.cpp"),
+                           os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
+    out = subprocess.run([exe, "24", "120", "5"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.startswith("ok: event path on the CPU == oracle for 24 tipsets"), out.stdout
+    runs_ok, runs_err = int(out.stdout.split(":")[2].split()[0]), int(out.stdout.split("field,")[1].split()[0])
+    assert runs_ok > 200 and runs_err > 1000, out.stdout
