@@ -32,6 +32,105 @@ __device__ __forceinline__ uint32_t slot_mask(uint64_t base, uint32_t level, uin
     return m;
 }
 
+// ---- message-AMT walk: order-preserving level-synchronous BFS (count → scan → expand) -----------------
+// A frontier item is one AMT node: block index, meta (amt ordinal << 16 | is_root << 8 | level),
+// base index. Every level first counts each item's outputs (from the node's bitmap), an exclusive
+// scan assigns output slots, then the node is fully decoded/validated and its children (or, in the
+// last round, its values) are written in place — so frontiers and the final value list stay in
+// (AMT, index) order, which is the reference's in-order `for_each` order. Leaves of shallow AMTs are
+// parked (re-emitted unchanged) until the last round.
+
+
+__device__ __forceinline__ uint32_t amt_item_count(const StoreView& s, uint32_t blk, uint32_t meta, uint64_t base, uint32_t round, uint32_t last_round,
+                                                   const uint64_t* rlo, const uint64_t* rhi) {
+    if (meta == AMT_SENTINEL) return 0;
+    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    if (level == 0 && round < last_round) return 1;  // parked
+    uint32_t len;
+    const uint8_t* p = store_block(s, blk, len);
+    Rd r(p, len);
+    if (is_root) { uint32_t bw, h; uint64_t c; amt_root_begin(r, 0, bw, h, c); }
+    rd_array_exact(r, 3);
+    uint32_t bl;
+    uint32_t bo = rd_bytes(r, bl);
+    if (r.err || bl != 1) return 0;  // reported by the expand pass
+    if (level != 0 || round == last_round) return (uint32_t)__popc((uint32_t)p[bo] & slot_mask(base, level, rlo[amt], rhi[amt]));
+    return 0;
+}
+
+struct ExpandArgs {
+    StoreView store;
+    Frontier in;
+    const unsigned long long* in_count;
+    const uint64_t* out_off;   // exclusive scan of the counts
+    uint32_t round, last_round, record;
+    uint32_t* wbits;
+    unsigned long long* err;
+    Frontier out;              // rounds < last_round
+    RawCid* vals;              // last round
+    uint32_t cap;
+    const uint64_t* rlo;       // per message AMT: index range this call walks
+    const uint64_t* rhi;
+};
+// Eight lanes per frontier item (a bw-3 node has ≤ 8 links or values). Every lane runs the same strict decode of
+// the node (same bytes → one memory transaction per group; the decode is a few hundred instructions), then lane j
+// resolves link j (hash probe + witness mark) or copies value j — the eight dependent store lookups of a node
+// proceed in parallel instead of back to back. No lane depends on another, so there is no intra-group sync.
+__device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t, uint32_t j, uint32_t blk, uint32_t meta, uint64_t base, uint32_t expect) {
+    if (meta == AMT_SENTINEL) return;
+    uint32_t level = meta & 0xff, is_root = (meta >> 8) & 1, amt = meta >> 16;
+    uint64_t o = a.out_off[t];
+    if (level == 0 && a.round < a.last_round) {  // park
+        if (j == 0 && o < a.cap) { a.out.blk[o] = blk; a.out.meta[o] = meta; a.out.base[o] = base; }
+        return;
+    }
+    uint32_t len;
+    const uint8_t* p = store_block(a.store, blk, len);
+    Rd r(p, len);
+    if (is_root) { uint32_t bw, h; uint64_t c; amt_root_begin(r, 0, bw, h, c); }
+    AmtNodeHdr h;
+    amt_node_begin(r, 3, h);
+    uint32_t nv = rd_array(r);
+    uint32_t vals_off = r.pos;
+    for (uint32_t v = 0; v < nv && !r.err; v++) (void)rd_cid(r);
+    amt_node_finish(r, h, nv, level);
+    uint64_t eidx = 3ull * (amt >> 1) + 1 + (amt & 1);
+    const uint32_t smask = slot_mask(base, level, a.rlo[amt], a.rhi[amt]);
+    const uint32_t bm8 = (uint32_t)h.bm.b0 & 0xffu;
+    uint32_t produced = 0;   // outputs of the whole node (same value in every lane)
+    if (r.err) { if (j == 0) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err); }
+    else if (h.nl || a.round == a.last_round) {
+        produced = (uint32_t)__popc(bm8 & smask);
+        if (produced > expect) produced = expect;
+        const uint32_t n_items = h.nl ? h.nl : nv;                 // == popc(bm8) after amt_node_finish
+        if (j < n_items) {
+            uint32_t slot = bm_select(h.bm, j);
+            uint32_t rank = (uint32_t)__popc(bm8 & smask & ((1u << slot) - 1u));   // selected items before this one
+            if (((smask >> slot) & 1) && rank < expect) {
+                uint64_t d = o + rank;
+                if (h.nl) {
+                    int32_t child = store_lookup(a.store, p + h.links_off + 43 * j + 5);
+                    if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
+                    else {
+                        if (a.record) witness_mark(a.wbits, (uint32_t)child);
+                        if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
+                    }
+                } else {
+                    const uint8_t* src = p + vals_off + 43 * j + 5;
+                    RawCid c;
+                    c.w[4] = load_u64_any(src) & 0xffffffffffffull;
+                    Digest dg = load_digest(src + 6);
+                    c.w[0] = dg.w[0]; c.w[1] = dg.w[1]; c.w[2] = dg.w[2]; c.w[3] = dg.w[3];
+                    a.vals[d] = c;
+                }
+            }
+        }
+    }
+    // slots promised by the count pass but not produced (malformed node): neutralise them
+    if (a.round < a.last_round) for (uint32_t k = produced + j; k < expect; k += 8) if (o + k < a.cap) a.out.meta[o + k] = AMT_SENTINEL;
+    if (a.round == a.last_round) for (uint32_t k = produced + j; k < expect; k += 8) { RawCid z{}; a.vals[o + k] = z; }
+}
+
 // ---- dense message-AMT walk ---------------------------------------------------------------------------------
 // Message AMTs are built from arrays: index i of an AMT with `count` values exists iff i < count. While every
 // node's bitmap agrees with that (checked node by node), the position of a node inside its level and of a value

@@ -22,6 +22,7 @@
 #include "../../oracle/oracle.h"
 #include "../../synth/synth.h"
 #include "host_store.h"
+#include "host_walk.h"
 
 using namespace ipcfp;
 
@@ -138,6 +139,23 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
         std::set<std::vector<uint8_t>> got, exp;
         for (uint64_t i = 0; i < n; i++) if (wbits[i >> 5] >> (i & 31) & 1) got.insert(std::vector<uint8_t>(cids + 38 * i, cids + 38 * i + 38));
         for (uint64_t i = 0; i < er->witness.n_blocks; i++) exp.insert(std::vector<uint8_t>(er->witness.cids + 38 * i, er->witness.cids + 38 * i + 38));
+        {   // ---- the GENERAL walk over the same share must give the same list and the same recorded blocks
+            std::vector<uint32_t> wb2((n + 31) / 32 + 8, 0);
+            auto mark2 = [&](const uint8_t* cid) { int32_t b = store_lookup(sv, cid); if (b >= 0) witness_mark(wb2.data(), (uint32_t)b); };
+            for (uint32_t b = 0; b < P; b++) { mark2(td.parent_cids + 38 * b); mark2(td.parent_txmeta_cids + 38 * b); }
+            mark2(td.child_cid); mark2(td.receipts_root);
+            for (uint32_t k = 0; k < namt; k++) witness_mark(wb2.data(), f_blk[k]);
+            unsigned long long gerr = IPCFP_NO_ERROR;
+            uint32_t last_round = 0;
+            for (uint32_t k = 0; k < namt; k++) last_round = std::max(last_round, heights[k]);
+            std::vector<RawCid> gvals;
+            uint64_t gn = 0;
+            host_general_walk(sv, namt, f_blk, f_meta, last_round, rlo.data(), rhi.data(), 1, wb2.data(), &gerr, 4 * n + 1024, gvals, gn);
+            if (gerr != IPCFP_NO_ERROR) return fail("the general walk reported an error on a well-formed tipset", rank, world);
+            if (gn != plan.nraw) return fail("general walk: share size", gn, plan.nraw);
+            for (uint64_t k = 0; k < gn; k++) if (memcmp(gvals[k].w, vals[k].w, 40)) return fail("general walk: raw list differs from the dense walk at", k, rank);
+            if (wb2 != wbits) return fail("general walk: recorded blocks differ from the dense walk", rank, world);
+        }
         if (got != exp) {
             rc = fail("recorded block set differs from the oracle's witness", got.size(), exp.size());
             fprintf(stderr, "  world %u rank %u receipts [%llu,%llu) of %llu; Nraw %llu share [%llu,%llu)\n", world, rank, (unsigned long long)lo, (unsigned long long)hi,
@@ -182,7 +200,7 @@ int main(int argc, char** argv) {
         static const uint32_t worlds[] = {1, 2, 3, 8};
         for (uint32_t w : worlds) { if (run_case(sp, w, &walked)) return 1; runs += w; }
     }
-    printf("ok: dense walk on the CPU == oracle for %llu tipsets, %llu (tipset, shard) runs, %llu AMT nodes walked\n", (unsigned long long)cases,
+    printf("ok: dense walk == general walk == oracle on the CPU for %llu tipsets, %llu (tipset, shard) runs, %llu AMT nodes walked\n", (unsigned long long)cases,
            (unsigned long long)runs, (unsigned long long)walked);
     return 0;
 }
