@@ -136,7 +136,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     // ---- dense walk
     std::vector<uint64_t> rlo(namt), rhi(namt);
     shard_amt_ranges(namt, counts.data(), false, 0, td.n_receipts, td.n_receipts, rlo.data(), rhi.data());
-    DensePlan plan = make_dense_plan(namt, heights.data(), counts.data(), rlo.data(), rhi.data(), 1u << 30, 1ull << 40, 1u << 20);
+    DensePlan plan = make_dense_plan(namt, heights.data(), counts.data(), rlo.data(), rhi.data(), 4 * B.n + 1024, 8 * (4 * B.n + 1024), 32768);   // the engine's own limits
     std::vector<RawCid> vals;
     uint64_t nraw = 0;
     bool dense_done = false;

@@ -88,7 +88,7 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
         std::vector<uint64_t> rlo(namt), rhi(namt);
         const uint64_t nraw_total = shard_amt_ranges(namt, counts.data(), sharded, lo, hi, td.n_receipts, rlo.data(), rhi.data());
         if (nraw_total != nraw_oracle) return fail("Nraw differs from the oracle", nraw_total, nraw_oracle);
-        DensePlan plan = make_dense_plan(namt, heights.data(), counts.data(), rlo.data(), rhi.data(), 1u << 30, 1ull << 40, 1u << 20);
+        DensePlan plan = make_dense_plan(namt, heights.data(), counts.data(), rlo.data(), rhi.data(), 4 * n + 1024, 8 * (4 * n + 1024), 32768);   // the engine's own limits
         if (!plan.ok) continue;                               // geometry left to the general walk (e.g. a shard without messages)
         // ---- the walk: rounds × items × 8 lanes, exactly the kernel's indexing
         uint64_t fmax = 1;
