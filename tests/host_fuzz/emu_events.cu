@@ -71,7 +71,9 @@ static void fail_key(Outcome& o, uint64_t key) {   // csrc/events.cu throw_devic
 }
 
 // the engine's device logic, item by item (dense walk first, the general walk when the dense one declines — as the host does)
-static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, Outcome& o) {
+static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, Outcome& o, bool sharded = false,
+                   uint64_t lo = 0, uint64_t hi = UINT64_MAX) {
+    if (!sharded) { lo = 0; hi = td.n_receipts; }
     HostStore hs(B.cids.data(), B.offs.data(), B.lens.data(), B.blob.data(), B.blob.size(), B.n);
     const StoreView& sv = hs.view;
     const uint32_t P = td.n_parents, namt = 2 * P;
@@ -135,7 +137,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     if (err != IPCFP_NO_ERROR) { fail_key(o, err); return true; }
     // ---- dense walk
     std::vector<uint64_t> rlo(namt), rhi(namt);
-    shard_amt_ranges(namt, counts.data(), false, 0, td.n_receipts, td.n_receipts, rlo.data(), rhi.data());
+    shard_amt_ranges(namt, counts.data(), sharded, lo, hi, td.n_receipts, rlo.data(), rhi.data());
     DensePlan plan = make_dense_plan(namt, heights.data(), counts.data(), rlo.data(), rhi.data(), 4 * B.n + 1024, 8 * (4 * B.n + 1024), 32768);   // the engine's own limits
     std::vector<RawCid> vals;
     uint64_t nraw = 0;
@@ -182,7 +184,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
         for (uint64_t k = 0; k < nraw; k++) if (seen.insert(std::string((const char*)vals[k].w, 40)).second) exec_idx.push_back((uint32_t)k);
     }
     unsigned long long n_exec = exec_idx.size();
-    o.n_exec = n_exec;
+    o.n_exec = sharded ? 0 : n_exec;
     // ---- matcher (EventMatcher::new)
     Matcher m;
     memset(&m, 0, sizeof m);
@@ -192,7 +194,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     // ---- pass 1 (pass1_body's per-receipt sequence)
     const uint64_t N = td.n_receipts;
     std::vector<uint32_t> cnt(N + 1, 0), nby(N + 1, 0), match_rel;
-    for (uint64_t i = 0; i < N; i++) {
+    for (uint64_t i = lo; i < hi; i++) {
         if (!td.has_events_root[i]) continue;
         int32_t blk = store_lookup(sv, td.events_roots + 38 * i);
         if (blk < 0) { report_error(&err, ST_PASS1, i, DC_MISSING, 0); continue; }
@@ -232,7 +234,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     p2.store = sv; p2.store_dev = &sv; p2.m_dev = &m; p2.m = m; p2.events_roots = td.events_roots; p2.lo = 0; p2.match_rel = match_rel.data(); p2.n_match = match_rel.size();
     p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = vals.data(); p2.exec_idx = exec_idx.data(); p2.n_exec = &n_exec;
     p2.wbits = wbits.data(); p2.err = &err; p2.cnt = cnt.data(); p2.proof_base = pbase.data(); p2.byte_base = bbase.data();
-    p2.proofs = proofs.data(); p2.blob = blob.data(); p2.any_skip = &any_skip; p2.resolve_msg = 1;
+    p2.proofs = proofs.data(); p2.blob = blob.data(); p2.any_skip = &any_skip; p2.resolve_msg = sharded ? 0 : 1;
     for (uint64_t t = 0; t < match_rel.size(); t++) pass2_item(p2, t);
     if (err != IPCFP_NO_ERROR) { fail_key(o, err); return true; }
     for (uint32_t i : match_rel) o.matching.push_back(i);
@@ -252,13 +254,14 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     return true;
 }
 
-static void oracle_side(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, Outcome& o) {
+static void oracle_side(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, Outcome& o, bool sharded = false,
+                        uint64_t lo = 0, uint64_t hi = 0, uint32_t world = 1, uint32_t rank = 0) {
     oracle_store* os = oracle_store_create(B.cids.data(), B.offs.data(), B.lens.data(), B.blob.data(), B.n);
     ipcfp_event_spec spec;
     memset(&spec, 0, sizeof spec);
     spec.event_signature = sig; spec.topic_1 = topic1; spec.has_actor_id_filter = has_actor ? 1 : 0; spec.actor_id_filter = actor;
     ipcfp_event_result* er = nullptr;
-    o.status = (int)oracle_generate_event_proof(os, &td, &spec, 0, 1, &er);
+    o.status = sharded ? (int)oracle_generate_event_proof_shard(os, &td, &spec, lo, hi, world, rank, 0, 1, &er) : (int)oracle_generate_event_proof(os, &td, &spec, 0, 1, &er);
     if (o.status != IPCFP_OK) o.index = oracle_last_error_index();
     else {
         for (uint64_t k = 0; k < er->n_matching; k++) o.matching.push_back(er->matching_indices[k]);
@@ -294,6 +297,33 @@ static int compare(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     if (!(e.proofs == o.proofs)) { fprintf(stderr, "EMU MISMATCH: proofs differ (%zu vs %zu)\n", e.proofs.size(), o.proofs.size()); return 1; }
     if (e.n_exec != o.n_exec) { fprintf(stderr, "EMU MISMATCH: n_exec %llu vs %llu\n", (unsigned long long)e.n_exec, (unsigned long long)o.n_exec); return 1; }
     if (e.witness != o.witness) { fprintf(stderr, "EMU MISMATCH: witness sets differ (%zu vs %zu)\n", e.witness.size(), o.witness.size()); return 1; }
+    (*n_ok)++;
+    return 0;
+}
+
+// one shard of a sharded call: message CIDs and the MISSING_EXEC check belong to the cross-shard protocol, everything else is local
+static int compare_shard(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, uint32_t world, uint32_t rank,
+                         uint64_t* n_ok, uint64_t* n_err) {
+    const uint64_t lo = td.n_receipts * rank / world, hi = td.n_receipts * (rank + 1) / world;
+    Outcome e, o;
+    engine(B, td, sig, topic1, has_actor, actor, e, true, lo, hi);
+    oracle_side(B, td, sig, topic1, has_actor, actor, o, true, lo, hi, world, rank);
+    if (o.status == IPCFP_ERR_MISSING_EXEC) return 0;
+    if (e.status == IPCFP_OK && o.status != IPCFP_OK && o.index == UINT64_MAX) {
+        // the oracle's shard function also builds the WHOLE execution order (a second walk over every message AMT): a fault in a
+        // part of the message AMTs this shard does not own surfaces there, while in the engine it belongs to the shard that owns it
+        Outcome full;
+        engine(B, td, sig, topic1, has_actor, actor, full);
+        if (full.status == o.status && full.index == o.index) return 0;
+    }
+    if (e.status != o.status || (e.status != IPCFP_OK && e.index != o.index)) {
+        fprintf(stderr, "EMU MISMATCH (shard %u/%u): engine status %d index %lld vs oracle status %d index %lld\n", rank, world, e.status, (long long)e.index, o.status, (long long)o.index);
+        return 1;
+    }
+    if (e.status != IPCFP_OK) { (*n_err)++; return 0; }
+    bool same = e.matching == o.matching && e.proofs.size() == o.proofs.size() && e.witness == o.witness;
+    for (size_t k = 0; same && k < e.proofs.size(); k++) { ProofRec a = e.proofs[k], b = o.proofs[k]; a.msg.clear(); b.msg.clear(); same = a == b; }
+    if (!same) { fprintf(stderr, "EMU MISMATCH (shard %u/%u): matching %zu/%zu proofs %zu/%zu witness %zu/%zu\n", rank, world, e.matching.size(), o.matching.size(), e.proofs.size(), o.proofs.size(), e.witness.size(), o.witness.size()); return 1; }
     (*n_ok)++;
     return 0;
 }
@@ -347,6 +377,8 @@ int main(int argc, char** argv) {
         const uint64_t actor = synth_target_actor(ts);
         std::vector<uint32_t> touched;
         if (compare(B, td, sig, t1, has_actor, actor, &touched, &n_ok, &n_err, &n_skip)) { fprintf(stderr, "  (tipset %llu as built)\n", (unsigned long long)c); return 1; }
+        for (uint32_t world : {2u, 3u}) for (uint32_t rank = 0; rank < world; rank++)
+            if (compare_shard(B, td, sig, t1, has_actor, actor, world, rank, &n_ok, &n_err)) { fprintf(stderr, "  (tipset %llu as built)\n", (unsigned long long)c); return 1; }
         std::vector<uint32_t> targets = touched;   // events blocks, receipts-AMT nodes, message-AMT nodes, TxMeta, headers
         std::sort(targets.begin(), targets.end());
         targets.erase(std::unique(targets.begin(), targets.end()), targets.end());
@@ -371,6 +403,7 @@ int main(int argc, char** argv) {
             M.lens[victim] = (uint32_t)blk.size();
             M.blob.insert(M.blob.end(), blk.begin(), blk.end());
             if (rnd() % 12 == 0) M.cids[38ull * victim + 20] ^= 0x5a;      // the block is simply not there
+            if (mi % 8 == 0 && compare_shard(M, td, sig, t1, has_actor, actor, 2, (uint32_t)(mi / 8 % 2), &n_ok, &n_err)) { fprintf(stderr, "  (tipset %llu, mutation %llu of block %u, shard)\n", (unsigned long long)c, (unsigned long long)mi, victim); return 1; }
             if (compare(M, td, sig, t1, has_actor, actor, nullptr, &n_ok, &n_err, &n_skip)) { fprintf(stderr, "  (tipset %llu, mutation %llu of block %u)\n", (unsigned long long)c, (unsigned long long)mi, victim); return 1; }
         }
         synth_free(ts);
