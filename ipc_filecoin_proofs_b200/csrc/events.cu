@@ -106,50 +106,14 @@ __global__ void __launch_bounds__(128, (CH * NSLOT <= 256 ? 6 : 3)) k_pass1_ring
     RingWin<CH, NSLOT> ring;
     if (blk >= 0) {
         p = store_block(a.store, (uint32_t)blk, len);
-        ring.init((uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * STRIDE, p, len, arena_end);
+        ring.init(ring_smem + threadIdx.x * STRIDE, p, len, arena_end);
         ring.top_up(0);                                 // first NSLOT chunks in flight before the dependent walk
     }
     __syncwarp();
     if (blk >= 0) {
         bytes = len + 38; nodes = 1;
-        bool taken = false;
         WalkOut wo{0, 0, false};
-        {
-            Rd r(ring.head_ptr(64), len);               // head of the node byte-wise from the ring (≤ 64 bytes, never wraps)
-            uint32_t bw, height;
-            uint64_t cnt;
-            amt_root_begin(r, 3, bw, height, cnt);
-            AmtNodeHdr h;
-            amt_node_begin_head(r, bw, h);
-            uint32_t nv = rd_array(r);
-            if (!r.err && h.nl == 0 && r.pos <= 64) {
-                uint32_t pos = r.pos;
-                bool bad = false;
-                for (uint32_t v = 0; v < nv && !bad; v++) {
-                    EvLog ev;
-                    uint32_t nx = fast_stamped_event_t(ring, pos, len, ev);
-                    if (nx == FAST_FAIL) {               // exact generic decoder, from the arena
-                        EvLog e2;
-                        uint32_t err = 0;
-                        nx = slow_stamped_event(p, pos, len, &e2, &err);
-                        ev = e2;
-                        if (err) { bad = true; break; }
-                    }
-                    pos = nx;
-                    if (event_matches(p, ev, a.m)) {
-                        wo.any = true;
-                        wo.nproofs++;
-                        wo.nbytes += 32 * ev.ntopics + ev.data_len;
-                    }
-                }
-                if (!bad) {
-                    r.pos = pos;
-                    amt_node_finish(r, h, nv, height);
-                    taken = !r.err;
-                }
-            }
-        }
-        cp_async_wait<0>();                              // nothing of this lane may still be landing when the CTA retires
+        const bool taken = pass1_ring_item(ring, p, len, a.m, wo);
         if (!taken) {                                    // the arena path decides (and reports) everything about this node
             wo = WalkOut{0, 0, false};
             Rd r(p, len);
