@@ -21,6 +21,7 @@
 #include "prims.cuh"
 #include "walk.cuh"
 #include "events_items.cuh"
+#include "pass1_ring.cuh"
 #include "rawcid.cuh"
 
 namespace ipcfp {
@@ -84,6 +85,64 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
 __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 8) k_pass1_occ8(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 10) k_pass1_occ10(Pass1Args a) { pass1_body(a); }
+
+// ---- EXPERIMENT (round 2): pass 1 through per-lane shared-memory rings, see pass1_ring.cuh. Same outputs as k_pass1;
+// a node the ring path cannot take (malformed head, links = taller AMT) is re-decoded by the arena path below.
+template <int CH, int NSLOT>
+__global__ void __launch_bounds__(128, (CH * NSLOT <= 256 ? 6 : 3)) k_pass1_ring(Pass1Args a, const uint8_t* arena_end) {
+    extern __shared__ __align__(16) uint8_t ring_smem[];
+    constexpr uint32_t STRIDE = CH * NSLOT + 16;      // 16-byte aligned rows, 4 banks apart
+    uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool matched = false;
+    uint32_t bytes = 0, nodes = 0, np_ = 0, nb_ = 0;
+    const bool valid = i < a.hi && a.has_root[i];
+    int32_t blk = -1;
+    if (valid) {
+        blk = store_lookup(a.store, a.events_roots + 38 * i);
+        if (blk < 0) report_error(a.err, ST_PASS1, i, DC_MISSING, 0);
+    }
+    uint32_t len = 0;
+    const uint8_t* p = nullptr;
+    RingWin<CH, NSLOT> ring;
+    if (blk >= 0) {
+        p = store_block(a.store, (uint32_t)blk, len);
+        ring.init(ring_smem + threadIdx.x * STRIDE, p, len, arena_end);
+        ring.top_up(0);                                 // first NSLOT chunks in flight before the dependent walk
+    }
+    __syncwarp();
+    if (blk >= 0) {
+        bytes = len + 38; nodes = 1;
+        WalkOut wo{0, 0, false};
+        const bool taken = pass1_ring_item(ring, p, len, a.m, wo);
+        if (!taken) {                                    // the arena path decides (and reports) everything about this node
+            wo = WalkOut{0, 0, false};
+            Rd r(p, len);
+            uint32_t bw, height;
+            uint64_t cnt;
+            amt_root_begin(r, 3, bw, height, cnt);
+            AmtNodeHdr h;
+            amt_node_begin(r, bw, h);
+            uint32_t nv = rd_array(r);
+            node_events<WALK_COUNT>(r, p, h, nv, 0, a.m, wo, nullptr, 2u);
+            amt_node_finish(r, h, nv, height);
+            if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
+            else if (h.nl) {
+                uint32_t detail = 0;
+                wo = WalkOut{0, 0, false};
+                uint32_t rc = walk_events<WALK_COUNT>(a.store_dev, (uint32_t)blk, a.m_dev, nullptr, wo, nullptr, &detail);
+                if (rc) { report_error(a.err, ST_PASS1, i, rc, detail); wo = WalkOut{0, 0, false}; }
+            }
+            if (r.err) wo = WalkOut{0, 0, false};
+        }
+        matched = wo.any;
+        np_ = wo.nproofs; nb_ = wo.nbytes;
+    }
+    if (i < a.hi) { a.cnt[i - a.lo] = np_; a.nbytes[i - a.lo] = nb_; }
+    unsigned b = __ballot_sync(0xffffffffu, matched);
+    if ((threadIdx.x & 31) == 0) a.match_bits[((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5] = b;
+    for (int o = 16; o; o >>= 1) { bytes += __shfl_xor_sync(0xffffffffu, bytes, o); nodes += __shfl_xor_sync(0xffffffffu, nodes, o); }
+    if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(a.stats, (unsigned long long)nodes); atomicAdd(a.stats + 1, (unsigned long long)bytes); }
+}
 
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -605,7 +664,17 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         static const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 8;
         static const int tune = getenv("IPCFP_PASS1_TUNE") ? atoi(getenv("IPCFP_PASS1_TUNE")) : 0;
         p1.tune = (uint32_t)tune;
-        if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
+        // EXPERIMENT: IPCFP_PASS1_RING=<chunk bytes>x<slots> (128x2, 128x4, 256x2) selects the shared-memory ring variant
+        static const char* ring_env = getenv("IPCFP_PASS1_RING");
+        auto launch_ring = [&](auto kern, size_t smem) {
+            static bool attr_set = false;
+            if (!attr_set) { IPCFP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            kern<<<div_up(N, 128), 128, smem, st>>>(p1, (const uint8_t*)s->arena.p + s->arena.n);
+        };
+        if (ring_env && !strcmp(ring_env, "128x2")) launch_ring(k_pass1_ring<128, 2>, 128 * (128 * 2 + 16));
+        else if (ring_env && !strcmp(ring_env, "128x4")) launch_ring(k_pass1_ring<128, 4>, 128 * (128 * 4 + 16));
+        else if (ring_env && !strcmp(ring_env, "256x2")) launch_ring(k_pass1_ring<256, 2>, 128 * (256 * 2 + 16));
+        else if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
         else if (minb >= 8) k_pass1_occ8<<<div_up(N, 128), 128, 0, st>>>(p1);
         else k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1);
         IPCFP_LAUNCH_CHECK();

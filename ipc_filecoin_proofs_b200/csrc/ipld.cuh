@@ -72,6 +72,25 @@ __device__ __forceinline__ void amt_node_begin(Rd& r, uint32_t bw, AmtNodeHdr& h
     h.links_off = r.pos;
     for (uint32_t k = 0; k < h.nl && !r.err; k++) (void)rd_cid(r);
 }
+// Same as amt_node_begin up to the links array head, WITHOUT touching the links (callers that cannot read further
+// than the first bytes of the node — the shared-memory ring of pass 1 — hand nodes with links to the full decoder).
+__device__ __forceinline__ void amt_node_begin_head(Rd& r, uint32_t bw, AmtNodeHdr& h) {
+    rd_array_exact(r, 3);
+    uint32_t blen;
+    uint32_t boff = rd_bytes(r, blen);
+    uint32_t want = bw <= 3 ? 1u : (1u << (bw - 3));
+    h.bm.clear();
+    h.pc = 0;
+    if (!r.err && blen != want) rd_fail(r, CE_AMT);
+    if (!r.err) {
+        for (uint32_t i = 0; i < blen; i++) h.bm.or_byte(i, r.p[boff + i]);
+        uint32_t width = 1u << bw;
+        if (width < 8 && (h.bm.b0 >> width)) rd_fail(r, CE_AMT);
+        h.pc = h.bm.popc();
+    }
+    h.nl = rd_array(r);
+    h.links_off = r.pos;
+}
 // after the values array has been consumed by the caller
 __device__ __forceinline__ void amt_node_finish(Rd& r, const AmtNodeHdr& h, uint32_t nv, uint32_t height) {
     if (r.err) return;
@@ -199,10 +218,16 @@ __device__ __forceinline__ uint32_t win_byte(uint64_t w0, uint64_t w1, uint32_t 
     uint64_t w = k < 8 ? w0 : w1;
     return (uint32_t)(w >> (8 * (k & 7))) & 0xffu;
 }
-__device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_t pos, uint32_t n, EvLog& ev) {
+// window source over global memory (the block arena)
+struct GlobalWin {
+    const uint8_t* p;
+    __device__ __forceinline__ void load(uint32_t pos, uint64_t& w0, uint64_t& w1) { win_load(p + pos, w0, w1); }
+};
+template <class Win>
+__device__ __forceinline__ uint32_t fast_stamped_event_t(Win& win, uint32_t pos, uint32_t n, EvLog& ev) {
     if (n - pos < 3) return FAST_FAIL;
     uint64_t w0, w1;
-    win_load(p + pos, w0, w1);
+    win.load(pos, w0, w1);
     if ((w0 & 0xff) != 0x82) return FAST_FAIL;
     // emitter: a minimal uint head with ≤ 4 argument bytes (actor ids); 8-byte arguments take the strict parser
     uint32_t eb = (uint32_t)(w0 >> 8) & 0xff;
@@ -221,7 +246,7 @@ __device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_
     a.clear();
     for (uint32_t e = 0; e < ne; e++) {
         if (n - cur < 5) return FAST_FAIL;
-        win_load(p + cur, w0, w1);
+        win.load(cur, w0, w1);
         // the one shape almost every entry has — an indexed topic  84 fl 62 't' '1'..'4' 18 cc 58 LL  — is
         // recognised with constant masks on the window (all offsets static); anything else goes through the
         // general head decoder below. Both accept exactly the same encodings with the same (kind, voff, vlen).
@@ -283,6 +308,10 @@ __device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_
     ev.emitter = earg;
     ev_finish(a, ev);
     return cur;
+}
+__device__ __forceinline__ uint32_t fast_stamped_event(const uint8_t* p, uint32_t pos, uint32_t n, EvLog& ev) {
+    GlobalWin g{p};
+    return fast_stamped_event_t(g, pos, n, ev);
 }
 // One StampedEvent at r.pos: fast path first, exact generic decoder on any deviation. The slow path
 // works on private copies so that the caller's reader and EvLog stay in registers.
