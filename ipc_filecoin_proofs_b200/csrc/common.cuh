@@ -113,9 +113,24 @@ enum DevCode : uint32_t { DC_MISSING = 1, DC_DECODE = 2, DC_MISSING_EXEC = 3, DC
 __host__ __device__ static inline uint64_t err_key(uint32_t stage, uint64_t index, uint32_t code, uint32_t detail) {
     return ((uint64_t)stage << 56) | ((index & 0xFFFFFFFFFFull) << 16) | ((uint64_t)(code & 0xff) << 8) | (detail & 0xff);
 }
+// Faults of the message-AMT stage (TxMeta blocks, BLS / SECP AMT roots and nodes) have their own word, ordered by WHERE the
+// reference's sequential, in-order walk (events/generator.rs:148-177, fvm_ipld_amt for_each) would meet them, so that with several
+// independent faults the level-synchronous walk still names the one the reference names:
+//   [ eidx:8 | base:44 | 31-level:5 | code:3 | detail:4 ]
+// eidx = 3·parent + {0 TxMeta, 1 BLS AMT, 2 SECP AMT}; base = first index below the faulting node (a missing child: the child's);
+// level = its height above the leaves (faults of the TxMeta / root header: 31). In-order DFS visits a node after everything with a
+// smaller base and, on the left-most path (equal base), parents before children — exactly this key order.
+#define IPCFP_TX_EIDX_NONE 0xffu
+__host__ __device__ static inline uint64_t tx_err_key(uint32_t eidx, uint64_t base, uint32_t level, uint32_t code, uint32_t detail) {
+    const uint64_t b = base > 0xFFFFFFFFFFFull ? 0xFFFFFFFFFFFull : base;
+    return ((uint64_t)(eidx & 0xff) << 56) | (b << 12) | ((uint64_t)(31u - (level > 31u ? 31u : level)) << 7) | ((uint64_t)(code & 7) << 4) | (detail & 15);
+}
 #ifdef __CUDACC__
 __device__ static inline void report_error(unsigned long long* word, uint32_t stage, uint64_t index, uint32_t code, uint32_t detail) {
     atomicMin(word, (unsigned long long)err_key(stage, index, code, detail));
+}
+__device__ static inline void report_tx_error(unsigned long long* word, uint32_t eidx, uint64_t base, uint32_t level, uint32_t code, uint32_t detail) {
+    atomicMin(word, (unsigned long long)tx_err_key(eidx, base, level, code, detail));
 }
 #endif
 

@@ -162,6 +162,7 @@ struct SetupArgs {
     uint32_t skip_tx;
     uint32_t* wbits;
     unsigned long long* err;
+    unsigned long long* txerr;     // message-AMT fault word (tx_err_key)
     // outputs
     uint32_t* receipts_root_blk;
     uint32_t* f_blk; uint32_t* f_meta; uint64_t* f_base;  // initial frontier: one item per message AMT
@@ -195,10 +196,12 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
         keccak256(a.sig, a.sig_len, d);
         a.matcher->t0[0] = d.w[0]; a.matcher->t0[1] = d.w[1]; a.matcher->t0[2] = d.w[2]; a.matcher->t0[3] = d.w[3];
     }
-    // TxMeta + message AMT roots (needed for the execution order even when skip_tx)
+    // TxMeta + message AMT roots (needed for the execution order even when skip_tx). An AMT whose root cannot be loaded keeps
+    // a sentinel seed (height / count 0): the walk goes on for the others, and the fault the reference meets FIRST wins the word
     if (t >= 32 && t < 96) for (uint32_t b = t - 32; b < P; b += 64) {
+        for (uint32_t k = 0; k < 2; k++) { a.f_meta[2 * b + k] = AMT_SENTINEL; a.f_blk[2 * b + k] = 0; a.f_base[2 * b + k] = 0; a.amt_height[2 * b + k] = 0; a.amt_count[2 * b + k] = 0; }
         int32_t tb = store_lookup(s, a.txmeta_cids + 38 * b);
-        if (tb < 0) { report_error(a.err, ST_TXMETA, 3 * b, DC_MISSING, 0); continue; }
+        if (tb < 0) { report_tx_error(a.txerr, 3 * b, 0, 31, DC_MISSING, 0); continue; }
         if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)tb);
         uint32_t len;
         const uint8_t* p = store_block(s, (uint32_t)tb, len);
@@ -206,10 +209,10 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
         rd_array_exact(r, 2);
         uint32_t c0 = rd_cid(r), c1 = rd_cid(r);
         rd_end(r);
-        if (r.err) { report_error(a.err, ST_TXMETA, 3 * b, DC_DECODE, r.err); continue; }
+        if (r.err) { report_tx_error(a.txerr, 3 * b, 0, 31, DC_DECODE, r.err); continue; }
         for (uint32_t k = 0; k < 2; k++) {
             int32_t rb = store_lookup(s, p + (k ? c1 : c0));
-            if (rb < 0) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_MISSING, 0); break; }
+            if (rb < 0) { report_tx_error(a.txerr, 3 * b + 1 + k, 0, 31, DC_MISSING, 0); break; }
             if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)rb);
             uint32_t rl;
             const uint8_t* rp = store_block(s, (uint32_t)rb, rl);
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
             uint32_t bw, h;
             uint64_t cnt;
             amt_root_begin(rr, 0, bw, h, cnt);
-            if (rr.err) { report_error(a.err, ST_TXMETA, 3 * b + 1 + k, DC_DECODE, rr.err); break; }
+            if (rr.err) { report_tx_error(a.txerr, 3 * b + 1 + k, 0, 31, DC_DECODE, rr.err); break; }
             const uint32_t amt = 2 * b + k;
             a.f_blk[amt] = (uint32_t)rb;
             a.f_meta[amt] = make_meta(amt, 1, h);
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128) k_amt_expand(ExpandArgs a, const uint32_t
     if (cnt > a.cap) cnt = a.cap;
     if (g == 0) {
         unsigned long long n = *total;
-        if (a.round < a.last_round && n > a.cap) { report_error(a.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = a.cap; }
+        if (a.round < a.last_round && n > a.cap) { report_tx_error(a.err, IPCFP_TX_EIDX_NONE, 0, 0, DC_UNSUPPORTED, 1); n = a.cap; }
         *out_count = n;
     }
     if (t >= cnt) return;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(TOP_CAP) k_amt_top(ExpandArgs a0, Frontier pin
         __syncthreads();
         if (t == 0) {
             unsigned long long n = s_total;
-            if (round < a0.last_round && n > a0.cap) { report_error(a0.err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = a0.cap; }
+            if (round < a0.last_round && n > a0.cap) { report_tx_error(a0.err, IPCFP_TX_EIDX_NONE, 0, 0, DC_UNSUPPORTED, 1); n = a0.cap; }
             *count_io = n;
         }
         __threadfence();
@@ -406,6 +409,26 @@ static void throw_device_error(uint64_t key) {
     throw Error(st, std::string(what) + " in " + stage_name + " (detail " + std::to_string(detail) + ")", out_index);
 }
 
+// message-AMT fault word (tx_err_key, common.cuh)
+static void throw_tx_error(uint64_t key) {
+    const uint32_t eidx = (uint32_t)(key >> 56), code = (uint32_t)(key >> 4) & 7, detail = (uint32_t)key & 15;
+    ipcfp_status st;
+    const char* what;
+    switch (code) {
+        case DC_MISSING: st = IPCFP_ERR_MISSING_BLOCK; what = "missing block"; break;
+        case DC_UNSUPPORTED: st = IPCFP_ERR_UNSUPPORTED; what = "unsupported input (frontier overflow)"; break;
+        default: st = IPCFP_ERR_DECODE; what = "decode error"; break;
+    }
+    uint64_t out_index = UINT64_MAX;
+    if (eidx != IPCFP_TX_EIDX_NONE && eidx % 3 == 0 && code == DC_MISSING) out_index = eidx / 3;   // missing TxMeta of parent b
+    throw Error(st, std::string(what) + " in message AMTs (detail " + std::to_string(detail) + ")", out_index);
+}
+// the failure the reference's sequential order meets first: message-AMT stage before everything else
+static void check_device_errors(const uint64_t* hw) {
+    if (hw[15] != IPCFP_NO_ERROR) throw_tx_error(hw[15]);
+    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+}
+
 void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
     s->use();
     if (!t || !t->child_cid || !t->receipts_root || (t->n_parents && (!t->parent_cids || !t->parent_txmeta_cids)))
@@ -445,6 +468,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     IPCFP_CUDA(cudaEventRecord(s->ev[0], st));
     IPCFP_CUDA(cudaMemsetAsync(dw, 0xff, 8, st));
     IPCFP_CUDA(cudaMemsetAsync(dw + 1, 0, 40 * 8, st));
+    IPCFP_CUDA(cudaMemsetAsync(dw + 15, 0xff, 8, st));   // message-AMT fault word
 
     // ---- matcher
     Matcher mh;
@@ -499,7 +523,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     sa.store = s->view; sa.n_parents = td.n_parents;
     sa.parent_cids = d_cids; sa.txmeta_cids = d_cids + 38ull * td.n_parents;
     sa.child_cid = d_cids + 76ull * td.n_parents; sa.receipts_root = sa.child_cid + 38;
-    sa.skip_tx = skip_tx; sa.wbits = wbits.p; sa.err = dw;
+    sa.skip_tx = skip_tx; sa.wbits = wbits.p; sa.err = dw; sa.txerr = dw + 15;
     sa.receipts_root_blk = misc.p; sa.missing_base = misc.p + 1; sa.amt_height = misc.p + 64;
     sa.f_blk = fA_blk.p; sa.f_meta = fA_meta.p; sa.f_base = fA_base.p; sa.f_count = dw + 1;
     sa.amt_count = amt_count.p;
@@ -508,9 +532,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     IPCFP_CUDA(cudaMemcpyAsync(hw + 400, d_matcher, 32, cudaMemcpyDeviceToHost, st));   // t0 → hw[400..404)
     IPCFP_CUDA(cudaMemcpyAsync(hw + 24, misc.p, (64 + 2 * IPCFP_MAX_PARENTS) * 4, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaMemcpyAsync(hw + 128, amt_count.p, 2 * IPCFP_MAX_PARENTS * 8, cudaMemcpyDeviceToHost, st));
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 16 * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    // A fault seen by the prologue (TxMeta / AMT root / receipts root) is NOT thrown yet: the reference walks the message AMTs
+    // before it loads the receipts root, and a fault inside an earlier AMT precedes a missing later root — walk first (general
+    // kernels: they cope with the sentinel seeds), then report the first one in the reference's order.
+    const bool early_fault = hw[0] != IPCFP_NO_ERROR || hw[15] != IPCFP_NO_ERROR;
     memcpy(mh.t0, hw + 400, 32);
     const uint32_t* misc_h = (const uint32_t*)(hw + 24);
     const uint32_t receipts_root_blk = misc_h[0];
@@ -536,7 +563,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // ---- (a) dense walk: plan the level layout on the host (see k_amt_dense)
     const bool force_general = getenv("IPCFP_BFS_GENERAL") != nullptr;   // read per call: tests toggle it
     DensePlan plan;
-    if (namt > 0 && namt <= namt_max && !force_general)
+    if (namt > 0 && namt <= namt_max && !force_general && !early_fault)
         plan = make_dense_plan(namt, misc_h + 64, (const uint64_t*)(hw + 128), h_rng.data(), h_rng.data() + 2 * IPCFP_MAX_PARENTS, frontier_cap, 8ull * cap,
                                STAGE_TABLES);
     AsyncBuf<uint8_t> d_tables;
@@ -553,6 +580,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         IPCFP_CUDA(cudaMemcpyAsync(d_tables.p, ht, nb_amt + nb_fofs + nb_ftot, cudaMemcpyHostToDevice, st));
         raw_cap = plan.nraw;
         exec_raw.alloc(raw_cap + 64, st);
+        exec_raw.zero();   // pool memory is not zeroed: an entry the walk failed to write must never look like a message CID
         DenseArgs da;
         da.store = s->view;
         da.ping = Frontier{fA_blk.p, fA_meta.p, fA_base.p}; da.pong = Frontier{fB_blk.p, fB_meta.p, fB_base.p};
@@ -582,7 +610,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         Frontier fcur{fA_blk.p, fA_meta.p, fA_base.p}, fnxt{fB_blk.p, fB_meta.p, fB_base.p};
         ccount = dw + 1; ncount = dw + 2;
         ExpandArgs ea;
-        ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw;
+        ea.store = s->view; ea.last_round = last_round; ea.record = skip_tx ? 0 : 1; ea.wbits = wbits.p; ea.err = dw + 15;
         ea.vals = nullptr; ea.cap = frontier_cap;
         ea.rlo = d_rng.p; ea.rhi = d_rng.p + 2 * IPCFP_MAX_PARENTS;
         // static frontier bound per round: namt * 8^round
@@ -590,6 +618,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         auto alloc_vals = [&]() {
             raw_cap = std::min<uint64_t>(bound_of(last_round) * 8, 8 * cap);
             exec_raw.alloc(raw_cap + 64, st);
+            exec_raw.zero();
             ea.vals = exec_raw.p;
         };
         // fused single-CTA rounds while the static bound fits one CTA
@@ -635,9 +664,9 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         IPCFP_CUDA(cudaStreamSynchronize(st));
     }
     const uint32_t ccount_idx = (uint32_t)(ccount - dw);
-    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
-    if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
-    uint64_t nraw = dense_used ? plan.nraw : std::min<uint64_t>(hw[ccount_idx], raw_cap);
+    check_device_errors(hw);
+    if (!dense_used && hw[ccount_idx] > raw_cap) throw Error(IPCFP_ERR_UNSUPPORTED, "unsupported input (message list longer than the walk's capacity)");
+    uint64_t nraw = dense_used ? plan.nraw : hw[ccount_idx];
     wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
@@ -688,7 +717,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
     publish_words(s, 0, 16);
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    check_device_errors(hw);
     const uint64_t n_exec = hw[3], M = hw[6];
     const uint64_t pass1_nodes = hw[4], pass1_bytes = hw[5];
     uint64_t n_proofs = hw[7], n_bytes = hw[12];
@@ -712,7 +741,10 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     publish_words(s, 0, 16);
     publish_words_from(s, misc.p, 20, 2);   // misc[2] = any_skip (32-bit words 0..3 land in hw[20..21])
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    if (hw[0] != IPCFP_NO_ERROR) throw_device_error(hw[0]);
+    check_device_errors(hw);
+    // base-witness CIDs (parent headers, child header, TxMeta) are only dereferenced by WitnessCollector::materialize
+    // (common/witness.rs:43-56, events/generator.rs:104), i.e. AFTER every receipts-root / pass-1 / pass-2 failure
+    if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
     const uint64_t mB = hw[10];
     const bool any_skip = ((const uint32_t*)(hw + 20))[2] != 0;
     IPCFP_CUDA(cudaEventRecord(s->ev[4], st));

@@ -163,7 +163,7 @@ __device__ bool read_storage_slot(const StoreView& s, Recorder& rec, const uint8
         uint32_t co = rd_cid(r);
         uint64_t b = rd_uint(r);
         rd_end(r);
-        if (!r.err) { hroot = p + co; bw = b > 0xffffffffull ? 0xffffffffull : b; goto do_hamt; }
+        if (!r.err) { hroot = p + co; bw = (uint32_t)b; goto do_hamt; }   // `bw as u32` (storage/decode.rs:79): truncation, not saturation
     }
     {   // B2: { root, bitwidth, … }
         Rd r(p, len);
@@ -181,7 +181,7 @@ __device__ bool read_storage_slot(const StoreView& s, Recorder& rec, const uint8
         }
         if (!r.err && !(hr && hb)) rd_fail(r, CE_FIELD);
         rd_end(r);
-        if (!r.err) { hroot = p + co; bw = b > 0xffffffffull ? 0xffffffffull : b; }
+        if (!r.err) { hroot = p + co; bw = (uint32_t)b; }                                // `bitwidth as u32` (storage/decode.rs:86)
     }
 do_hamt:
     bool found;

@@ -65,7 +65,7 @@ struct ExpandArgs {
     const uint64_t* out_off;   // exclusive scan of the counts
     uint32_t round, last_round, record;
     uint32_t* wbits;
-    unsigned long long* err;
+    unsigned long long* err;   // the message-AMT fault word (tx_err_key)
     Frontier out;              // rounds < last_round
     RawCid* vals;              // last round
     uint32_t cap;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
     const uint32_t smask = slot_mask(base, level, a.rlo[amt], a.rhi[amt]);
     const uint32_t bm8 = (uint32_t)h.bm.b0 & 0xffu;
     uint32_t produced = 0;   // outputs of the whole node (same value in every lane)
-    if (r.err) { if (j == 0) report_error(a.err, ST_TXMETA, eidx, DC_DECODE, r.err); }
+    if (r.err) { if (j == 0) report_tx_error(a.err, (uint32_t)eidx, base, level, DC_DECODE, r.err); }
     else if (h.nl || a.round == a.last_round) {
         produced = (uint32_t)__popc(bm8 & smask);
         if (produced > expect) produced = expect;
@@ -110,7 +110,11 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
                 uint64_t d = o + rank;
                 if (h.nl) {
                     int32_t child = store_lookup(a.store, p + h.links_off + 43 * j + 5);
-                    if (child < 0) { report_error(a.err, ST_TXMETA, eidx, DC_MISSING, 0); if (d < a.cap) a.out.meta[d] = AMT_SENTINEL; }
+                    if (child < 0) {   // Blockstore::get of child `slot` fails: met after everything below the earlier slots
+                        const uint64_t off = (uint64_t)slot * pow_sat(3, level);
+                        report_tx_error(a.err, (uint32_t)eidx, base + off < base ? ~0ull : base + off, level - 1, DC_MISSING, 0);
+                        if (d < a.cap) a.out.meta[d] = AMT_SENTINEL;
+                    }
                     else {
                         if (a.record) witness_mark(a.wbits, (uint32_t)child);
                         if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
@@ -259,7 +263,13 @@ inline DensePlan make_dense_plan(uint32_t namt, const uint32_t* heights, const u
     DensePlan plan;
     bool ok = namt > 0;
     uint32_t last_round = 0;
-    for (uint32_t k = 0; ok && k < namt; k++) { ok = heights[k] <= 20 && cnts[k] <= (1ull << 40); last_round = std::max(last_round, heights[k]); }
+    // a root whose count exceeds what its height can hold (8^(height+1)) is NOT dense by construction: every per-node check of
+    // amt_item_dense would pass on a completely full tree while count promises more values than exist — the general walk
+    // (which never trusts count) takes those
+    for (uint32_t k = 0; ok && k < namt; k++) {
+        ok = heights[k] <= 20 && cnts[k] <= (1ull << 40) && cnts[k] <= (1ull << (3 * (heights[k] + 1)));
+        last_round = std::max(last_round, heights[k]);
+    }
     if (ok) {
         plan.rounds = last_round + 1;
         plan.fofs.assign((size_t)plan.rounds * namt, 0);

@@ -724,7 +724,7 @@ static std::optional<Bytes> read_storage_slot(const Blockstore& store, const Cid
     {  // B1 (root, bitwidth)
         Cid r; uint64_t bw = 0;
         if (attempt([&] { Dec d(raw); d.array_exact(2); r = d.cid(); bw = d.uint(); d.end(); })) {
-            if (bw > 0xffffffffULL) bw = 0xffffffffULL;
+            // `bw as u32` (storage/decode.rs:79,86) truncates to the low 32 bits
             auto v = hamt_get<RawU8Vec>(store, r, (uint32_t)bw, key);
             return v ? std::optional<Bytes>(v->v) : std::nullopt;
         }
@@ -745,7 +745,7 @@ static std::optional<Bytes> read_storage_slot(const Blockstore& store, const Cid
                 if (!hr || !hb) fail_decode("missing field");
                 d.end();
             })) {
-            if (bw > 0xffffffffULL) bw = 0xffffffffULL;
+            // `bw as u32` (storage/decode.rs:79,86) truncates to the low 32 bits
             auto v = hamt_get<RawU8Vec>(store, r, (uint32_t)bw, key);
             return v ? std::optional<Bytes>(v->v) : std::nullopt;
         }
@@ -851,11 +851,22 @@ static EventGenOut generate_event_proof(const Blockstore& net, const TipsetIn& t
         uint64_t nraw = 0;
         std::vector<uint64_t> bases;
         if (sharded) {
+            // geometry of the raw list (start of every AMT in it). An AMT whose TxMeta / root cannot be loaded counts as empty here —
+            // the failure itself is raised by the walk below, in the reference's order (same rule as the engine: the first fault,
+            // in the order of the sequential walk, among those this shard meets)
             for (size_t b = 0; b < ts.txmeta.size(); b++) {
-                Bytes raw;
-                if (!net.get(ts.txmeta[b], raw)) throw Err(IPCFP_ERR_MISSING_BLOCK, "missing TxMeta", b);
-                auto roots = decode_txmeta(raw);
-                for (const Cid* r : {&roots.first, &roots.second}) { auto a = Amt<Cid>::load(*r, net, 0); bases.push_back(nraw); nraw += a.count; }
+                std::pair<Cid, Cid> roots;
+                bool have = false;
+                try {
+                    Bytes raw;
+                    if (net.get(ts.txmeta[b], raw)) { roots = decode_txmeta(raw); have = true; }
+                } catch (Err&) {}
+                for (int k = 0; k < 2; k++) {
+                    uint64_t cnt = 0;
+                    if (have) { try { cnt = Amt<Cid>::load(k ? roots.second : roots.first, net, 0).count; } catch (Err&) {} }
+                    bases.push_back(nraw);
+                    nraw += cnt;
+                }
             }
         }
         size_t ai = 0;

@@ -362,9 +362,9 @@ def read_storage_slot(rec, root, slot):
         return find(x)
     val = None
     if isinstance(x, list) and len(x) == 2 and isinstance(x[0], cbor2.CBORTag) and isinstance(x[1], int) and x[1] >= 0:
-        val = hamt_get(rec, _link(x[0]), x[1], slot)
+        val = hamt_get(rec, _link(x[0]), x[1] & 0xffffffff, slot)   # `bw as u32` (storage/decode.rs:79)
     elif isinstance(x, dict) and isinstance(x.get("root"), cbor2.CBORTag) and isinstance(x.get("bitwidth"), int):
-        val = hamt_get(rec, _link(x["root"]), x["bitwidth"], slot)
+        val = hamt_get(rec, _link(x["root"]), x["bitwidth"] & 0xffffffff, slot)   # `bitwidth as u32` (:86)
     else:
         val = hamt_get(rec, root, 5, slot)
     return None if val is None else bytes(val)  # Vec<u8> arrives as a list of ints

@@ -183,6 +183,17 @@ int main(int argc, char** argv) {
     uint64_t cases = argc > 1 ? strtoull(argv[1], nullptr, 10) : 40;
     uint64_t seed = argc > 2 ? strtoull(argv[2], nullptr, 10) : 7;
     uint64_t walked = 0, runs = 0;
+    {   // a root.count larger than the tree can hold (8^(height+1)) must never reach the dense walk: on a completely FULL tree every
+        // per-node check of amt_item_dense passes while `count` promises values that do not exist (csrc/walk.cuh)
+        struct Case { uint32_t h; uint64_t cnt; bool ok; } cases_[] = {{0, 8, true}, {0, 9, false}, {0, 12, false}, {1, 64, true}, {1, 65, false}, {1, 100, false},
+                                                                       {2, 512, true}, {2, 513, false}, {20, 1ull << 40, true}};
+        for (const Case& c : cases_) {
+            uint32_t hh[1] = {c.h};
+            uint64_t cc[1] = {c.cnt}, lo_[1] = {0}, hi_[1] = {UINT64_MAX};
+            DensePlan pl = make_dense_plan(1, hh, cc, lo_, hi_, 1ull << 42, 1ull << 43, 1 << 20);
+            if (pl.ok != c.ok) return fail("make_dense_plan: capacity rule", c.h, c.cnt);
+        }
+    }
     for (uint64_t c = 0; c < cases; c++) {
         synth_params sp;
         synth_default_params(&sp);

@@ -8,7 +8,7 @@
 
 namespace ipcfp {
 
-// roots: frontier seeds as k_setup writes them. rlo / rhi: per-AMT index ranges (shard_amt_ranges). Errors go to *err (atomicMin key).
+// roots: frontier seeds as k_setup writes them. rlo / rhi: per-AMT index ranges (shard_amt_ranges). Errors go to *err (the message-AMT fault word, tx_err_key).
 // On return vals holds the raw execution list of the share (nraw entries).
 inline void host_general_walk(const StoreView& sv, uint32_t namt, const std::vector<uint32_t>& f_blk, const std::vector<uint32_t>& f_meta, uint32_t last_round,
                               const uint64_t* rlo, const uint64_t* rhi, uint32_t record, uint32_t* wbits, unsigned long long* err, uint64_t cap,
@@ -35,7 +35,7 @@ inline void host_general_walk(const StoreView& sv, uint32_t namt, const std::vec
         for (uint64_t t = 0; t < items; t++)
             for (uint32_t j = 0; j < 8; j++) amt_item_expand(a, t, j, fcur.blk[t], fcur.meta[t], fcur.base[t], counts[t]);
         unsigned long long n = total;
-        if (round < last_round && n > cap) { report_error(err, ST_TXMETA, 0xFFFFFFFFFFull, DC_UNSUPPORTED, 1); n = cap; }
+        if (round < last_round && n > cap) { report_tx_error(err, IPCFP_TX_EIDX_NONE, 0, 0, DC_UNSUPPORTED, 1); n = cap; }
         cnt = n;
         std::swap(fcur, fnxt);
     }
