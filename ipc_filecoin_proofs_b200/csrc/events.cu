@@ -22,6 +22,7 @@
 #include "walk.cuh"
 #include "events_items.cuh"
 #include "pass1_ring.cuh"
+#include "pass1_stage.cuh"
 #include "rawcid.cuh"
 
 namespace ipcfp {
@@ -690,19 +691,34 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     p1.store = s->view; p1.store_dev = s->view_dev.p; p1.m_dev = d_matcher; p1.m = mh; p1.events_roots = td.events_roots.p; p1.has_root = td.has_root.p; p1.lo = lo; p1.hi = hi;
     p1.match_bits = match_bits.p; p1.cnt = cnt.p; p1.nbytes = nby.p; p1.err = dw; p1.stats = dw + 4;
     if (N) {
-        static const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 8;
-        static const int tune = getenv("IPCFP_PASS1_TUNE") ? atoi(getenv("IPCFP_PASS1_TUNE")) : 0;
-        p1.tune = (uint32_t)tune;
-        // EXPERIMENT: IPCFP_PASS1_RING=<chunk bytes>x<slots> (128x2, 128x4, 256x2) selects the shared-memory ring variant
-        static const char* ring_env = getenv("IPCFP_PASS1_RING");
+        // kernel variant: read per call so that one process can sweep them (tools/profile_step.py)
+        //   IPCFP_PASS1_STAGE=<chunk>x<slots>x<chunks per pass>   warp-cooperative shared-memory staging (pass1_stage.cuh)
+        //   IPCFP_PASS1_RING=<chunk>x<slots>                      per-lane cp.async rings (pass1_ring.cuh, round-1 experiment)
+        //   IPCFP_PASS1_MINB=6|8|10, IPCFP_PASS1_TUNE=<bits>      thread-per-node kernel straight from the arena (round 1)
+        const char* stage_env = getenv("IPCFP_PASS1_STAGE");
+        const char* ring_env = getenv("IPCFP_PASS1_RING");
+        const int minb = getenv("IPCFP_PASS1_MINB") ? atoi(getenv("IPCFP_PASS1_MINB")) : 8;
+        p1.tune = (uint32_t)(getenv("IPCFP_PASS1_TUNE") ? atoi(getenv("IPCFP_PASS1_TUNE")) : 0);
+        auto launch_stage = [&](auto kern, int warps, size_t warp_bytes) {
+            const size_t smem = warps * warp_bytes;
+            IPCFP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<div_up(N, 32 * warps), 32 * warps, smem, st>>>(p1);
+        };
         auto launch_ring = [&](auto kern, size_t smem) {
-            static bool attr_set = false;
-            if (!attr_set) { IPCFP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            IPCFP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<div_up(N, 128), 128, smem, st>>>(p1, (const uint8_t*)s->arena.p + s->arena.n);
         };
-        if (ring_env && !strcmp(ring_env, "128x2")) launch_ring(k_pass1_ring<128, 2>, 128 * (128 * 2 + 16));
-        else if (ring_env && !strcmp(ring_env, "128x4")) launch_ring(k_pass1_ring<128, 4>, 128 * (128 * 4 + 16));
-        else if (ring_env && !strcmp(ring_env, "256x2")) launch_ring(k_pass1_ring<256, 2>, 128 * (256 * 2 + 16));
+        auto is = [](const char* e, const char* v) { return e && !strcmp(e, v); };
+        if (is(stage_env, "128x4x1")) launch_stage(k_pass1_stage<128, 4, 1, 4, 3>, 4, StageGeom<128, 4, 1>::WARP_BYTES);
+        else if (is(stage_env, "128x4x1w2")) launch_stage(k_pass1_stage<128, 4, 1, 2, 6>, 2, StageGeom<128, 4, 1>::WARP_BYTES);
+        else if (is(stage_env, "128x4x2")) launch_stage(k_pass1_stage<128, 4, 2, 4, 3>, 4, StageGeom<128, 4, 2>::WARP_BYTES);
+        else if (is(stage_env, "64x8x2")) launch_stage(k_pass1_stage<64, 8, 2, 4, 3>, 4, StageGeom<64, 8, 2>::WARP_BYTES);
+        else if (is(stage_env, "64x4x2")) launch_stage(k_pass1_stage<64, 4, 2, 8, 3>, 8, StageGeom<64, 4, 2>::WARP_BYTES);
+        else if (is(stage_env, "256x2x1")) launch_stage(k_pass1_stage<256, 2, 1, 4, 3>, 4, StageGeom<256, 2, 1>::WARP_BYTES);
+        else if (is(stage_env, "256x4x1")) launch_stage(k_pass1_stage<256, 4, 1, 2, 3>, 2, StageGeom<256, 4, 1>::WARP_BYTES);
+        else if (is(ring_env, "128x2")) launch_ring(k_pass1_ring<128, 2>, 128 * (128 * 2 + 16));
+        else if (is(ring_env, "128x4")) launch_ring(k_pass1_ring<128, 4>, 128 * (128 * 4 + 16));
+        else if (is(ring_env, "256x2")) launch_ring(k_pass1_ring<256, 2>, 128 * (256 * 2 + 16));
         else if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
         else if (minb >= 8) k_pass1_occ8<<<div_up(N, 128), 128, 0, st>>>(p1);
         else k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1);

@@ -275,7 +275,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     IPCFP_CUDA(cudaMemsetAsync(s->dev_words.p, 0, 64 * 8, st));
 
     // device allocations
-    s->arena.alloc(blob_size + 48);
+    s->arena.alloc(blob_size + 48 + 512);   // + room for whole aligned chunks around the last block (pass-1 staging copies CH-aligned chunks)
     s->offsets.alloc(n + 1);
     s->lengths.alloc(n + 1);
     s->digests.alloc(n + 1);
