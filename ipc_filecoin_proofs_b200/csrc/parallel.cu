@@ -176,3 +176,353 @@ void exec_fetch(int device, const void* seg, uint64_t nseg, uint64_t pos0, const
 }
 
 }  // namespace ipcfp
+
+// =====================================================================================================================
+// In-library cross-shard protocol over NCCL (ipcfp_comm_init / ipcfp_generate_event_proof_sharded).
+//
+// One process per GPU. Receipts shard by index range (events/generator.rs:209-301 is independent per receipt); what spans
+// shards is (1) the execution order — every message AMT concatenated, first occurrence of a CID wins (events/utils.rs:48-94) —
+// and (2) the union of the per-shard witness CID sets (common/witness.rs:24-40). Everything is enqueued on CUDA streams with
+// sizes the host already knows; the host waits for its peers twice (H0: does every shard have a message list, how long; H2:
+// did every shard get through pass 2, how many matches / witness blocks), both while its own GPU is busy:
+//
+//   H0   all-gather  {ok, Nraw, nseg}                                      → global positions, exact buffer sizes, common abort
+//   X    bucketize by hash(cid) % world → all-to-all (ncclSend/ncclRecv group) → first-seen dedup on the owners → the owners set
+//        one bit per NON-first occurrence in a bitmap over the raw positions → all-reduce (sum of disjoint bitmaps = OR)
+//        [exchange stream: runs underneath pass 1]
+//   P    n_exec = zero bits; exec index i ↔ position of the (i+1)-th zero bit (prefix popcount + select) for the rank's matches;
+//        pass 2 runs with the global n_exec (so "Missing message at index" keeps its place in the error order)
+//   H2   all-gather  {first error key, matches, proofs, witness blocks}    → all ranks fail together with the SAME error
+//   F    all-gather of the wanted positions → every owner copies the CIDs it holds → all-reduce → EventProof.message_cid patched
+//   W    all-gather of the sorted per-shard witness CID lists → bucketed k-way merge + unique on every rank
+// NCCL is resolved with dlopen at ipcfp_comm_init (libnccl.so.2: the copy already in the process — e.g. PyTorch's — or the
+// system one), so the library itself keeps linking only cudart and loads on machines without NCCL.
+// =====================================================================================================================
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace ipcfp {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GetVersion)(int*);
+};
+static NcclApi* nccl_api() {
+    static std::mutex mu;
+    static NcclApi api;
+    static bool ready = false;
+    std::lock_guard<std::mutex> g(mu);
+    if (ready) return &api;
+    const char* names[] = {getenv("IPCFP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!h) throw Error(IPCFP_ERR_NCCL, std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) throw Error(IPCFP_ERR_NCCL, std::string("NCCL symbol missing: ") + n); return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    ready = true;
+    return &api;
+}
+#define IPCFP_NCCL(expr)                                                                                                     \
+    do {                                                                                                                     \
+        ncclResult_t _r = (expr);                                                                                            \
+        if (_r != ncclSuccess) throw ::ipcfp::Error(IPCFP_ERR_NCCL, std::string(#expr) + ": " + nccl_api()->GetErrorString(_r)); \
+    } while (0)
+
+struct Comm {
+    int device = 0;
+    uint32_t world = 1, rank = 0;
+    ncclComm_t cx = nullptr, cw = nullptr;   // exchange (execution order) / witness union: independent streams, independent communicators
+    cudaStream_t sx = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    // grow-only device scratch (allocated during warm-up, then reused)
+    DevBuf<uint8_t> sendbuf, recvbuf, gather, merged, recs;
+    DevBuf<unsigned long long> table, words, words2;
+    DevBuf<uint32_t> bitmap, bitmap_sum, zeros, flags, starts;
+    DevBuf<uint64_t> zprefix, scan_tmp, req, req_all, ans, ans_sum, fscan;
+    DevBuf<uint32_t> pos_of;
+    PinnedBuf<uint64_t> host;                // mapped: H0 / H2 read-backs
+    ~Comm() {
+        cudaSetDevice(device);
+        NcclApi* n = nullptr;
+        try { n = nccl_api(); } catch (...) {}
+        if (n) { if (cx) n->CommDestroy(cx); if (cw) n->CommDestroy(cw); }
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+        if (ev_c) cudaEventDestroy(ev_c);
+        if (sx) cudaStreamDestroy(sx);
+    }
+};
+
+void comm_unique_id(uint8_t* id128) {
+    ncclUniqueId id;
+    IPCFP_NCCL(nccl_api()->GetUniqueId(&id));
+    static_assert(sizeof id == IPCFP_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id128, &id, sizeof id);
+}
+Comm* comm_init(const uint8_t* id128, uint32_t world, uint32_t rank, int device) {
+    check_device(device);
+    if (!world || world > 256 || rank >= world) throw Error(IPCFP_ERR_INVALID_ARG, "bad world size / rank");
+    NcclApi* n = nccl_api();
+    std::unique_ptr<Comm> c(new Comm());
+    c->device = device; c->world = world; c->rank = rank;
+    IPCFP_CUDA(cudaStreamCreateWithFlags(&c->sx, cudaStreamNonBlocking));
+    IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
+    c->host.alloc(64 + 8 * 256);
+    c->words.alloc(64 + 8 * 256);
+    c->words2.alloc(64 + 8 * 256);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    IPCFP_NCCL(n->CommInitRank(&c->cx, (int)world, id, (int)rank));
+    // the second communicator's id travels over the first one
+    ncclUniqueId id2;
+    if (rank == 0) IPCFP_NCCL(n->GetUniqueId(&id2));
+    IPCFP_CUDA(cudaMemcpyAsync(c->words.p, &id2, sizeof id2, cudaMemcpyHostToDevice, c->sx));
+    IPCFP_NCCL(n->Broadcast(c->words.p, c->words.p, sizeof id2, ncclUint8, 0, c->cx, c->sx));
+    IPCFP_CUDA(cudaMemcpyAsync(&id2, c->words.p, sizeof id2, cudaMemcpyDeviceToHost, c->sx));
+    IPCFP_CUDA(cudaStreamSynchronize(c->sx));
+    IPCFP_NCCL(n->CommInitRank(&c->cw, (int)world, id2, (int)rank));
+    return c.release();
+}
+void comm_destroy(Comm* c) { delete c; }
+uint32_t comm_world(const Comm* c) { return c->world; }
+uint32_t comm_rank(const Comm* c) { return c->rank; }
+
+// ------------------------------------------------------------------------------------------ exchange kernels
+#define XSEG_HDR 48   // a segment = [count u64, 40 bytes pad][cap entries of 48 bytes]
+
+// counts per owner from the first sorted position of every owner (nseg where an owner has no entry); writes the segment headers
+__global__ void k_exec_seg_headers(const unsigned long long* __restrict__ start, uint64_t nseg, uint32_t world, uint64_t cap, uint8_t* send,
+                                   unsigned long long* overflow) {
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long next = nseg;
+    for (int r = (int)world - 1; r >= 0; r--) {
+        unsigned long long cnt = 0;
+        if (start[r] != nseg) { cnt = next - start[r]; next = start[r]; }
+        if (cnt > cap) { *overflow = 1; cnt = cap; }
+        *(unsigned long long*)(send + (uint64_t)r * (XSEG_HDR + cap * 48)) = cnt;
+    }
+}
+__global__ void k_exec_scatter_seg(const RawCid* __restrict__ seg, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t nseg,
+                                   uint64_t pos0, const unsigned long long* __restrict__ start, uint64_t cap, uint8_t* send) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nseg) return;
+    uint32_t owner = keys[j], src = vals[j];
+    uint64_t slot = j - start[owner];
+    if (slot < cap) {
+        ExecEntry e; e.c = seg[src]; e.pos = pos0 + src;
+        *(ExecEntry*)(send + (uint64_t)owner * (XSEG_HDR + cap * 48) + XSEG_HDR + slot * 48) = e;
+    }
+}
+// seg_off[0..world] from the received segment headers
+__global__ void k_recv_offsets(const uint8_t* __restrict__ recv, uint32_t world, uint64_t cap, uint64_t* seg_off) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t run = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        seg_off[r] = run;
+        uint64_t c = *(const unsigned long long*)(recv + (uint64_t)r * (XSEG_HDR + cap * 48));
+        run += c > cap ? cap : c;
+    }
+    seg_off[world] = run;
+}
+__device__ __forceinline__ const ExecEntry* recv_entry_seg(const uint8_t* recv, const uint64_t* seg_off, uint32_t world, uint64_t cap, uint64_t k) {
+    uint32_t r = 0;
+    while (r + 1 < world && k >= seg_off[r + 1]) r++;
+    return (const ExecEntry*)(recv + (uint64_t)r * (XSEG_HDR + cap * 48) + XSEG_HDR) + (k - seg_off[r]);
+}
+// one canonical slot per distinct CID holding the smallest entry ordinal (= smallest global position: segments arrive in rank
+// order and are position-ordered inside)
+__global__ void k_exec_claim_seg(const uint8_t* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap,
+                                 unsigned long long* table, uint64_t mask) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= seg_off[world]) return;
+    const ExecEntry* e = recv_entry_seg(recv, seg_off, world, cap, k);
+    uint64_t h = rawcid_hash(e->c);
+    uint32_t fp = (uint32_t)(h >> 40) | 1u;
+    unsigned long long mine = ((unsigned long long)fp << 32) | (unsigned long long)(k + 1);
+    uint64_t slot = h & mask;
+    for (;;) {
+        unsigned long long v = table[slot];
+        if (v == 0) { v = atomicCAS(&table[slot], 0ull, mine); if (v == 0) return; }
+        if ((uint32_t)(v >> 32) == fp && rawcid_eq(recv_entry_seg(recv, seg_off, world, cap, (uint32_t)v - 1)->c, e->c)) { atomicMin(&table[slot], mine); return; }
+        slot = (slot + 1) & mask;
+    }
+}
+// every entry that is not the first occurrence of its CID sets the bit of its global position
+__global__ void k_exec_mark_dups(const uint8_t* __restrict__ recv, const uint64_t* __restrict__ seg_off, uint32_t world, uint64_t cap,
+                                 const unsigned long long* __restrict__ table, uint64_t mask, uint32_t* bitmap) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= seg_off[world]) return;
+    const ExecEntry* e = recv_entry_seg(recv, seg_off, world, cap, k);
+    uint64_t h = rawcid_hash(e->c);
+    uint32_t fp = (uint32_t)(h >> 40) | 1u;
+    uint64_t slot = h & mask;
+    for (;;) {
+        unsigned long long v = table[slot];
+        if (v == 0) return;   // cannot happen: every entry was claimed
+        if ((uint32_t)(v >> 32) == fp && rawcid_eq(recv_entry_seg(recv, seg_off, world, cap, (uint32_t)v - 1)->c, e->c)) {
+            if ((uint32_t)v - 1 != (uint32_t)k) atomicOr(&bitmap[e->pos >> 5], 1u << (e->pos & 31));
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+// zero bits per word of the duplicate bitmap (positions past nraw do not count)
+__global__ void k_zero_counts(const uint32_t* __restrict__ bitmap, uint64_t nraw, uint32_t* zeros) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nwords = (nraw + 31) / 32;
+    if (w >= nwords) return;
+    uint32_t valid = (w == nwords - 1 && (nraw & 31)) ? ((1u << (nraw & 31)) - 1u) : 0xffffffffu;
+    zeros[w] = (uint32_t)__popc(~bitmap[w] & valid);
+}
+// exec index i of every matching receipt → raw position of the (i+1)-th zero bit (UINT64_MAX past the end)
+__global__ void k_select_positions(const uint32_t* __restrict__ match_rel, uint64_t n_match, uint64_t lo, const uint32_t* __restrict__ bitmap,
+                                   const uint64_t* __restrict__ zprefix, uint64_t nwords, const unsigned long long* __restrict__ n_exec,
+                                   uint64_t* out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_match) return;
+    const uint64_t i = lo + match_rel[t];
+    if (i >= *n_exec) { out[t] = ~0ull; return; }
+    uint64_t a = 0, b = nwords;            // largest w with zprefix[w] <= i
+    while (b - a > 1) { uint64_t m = (a + b) >> 1; if (zprefix[m] <= i) a = m; else b = m; }
+    uint32_t x = ~bitmap[a];
+    uint32_t k = (uint32_t)(i - zprefix[a]);
+    for (uint32_t j = 0; j < k; j++) x &= x - 1;
+    out[t] = a * 32 + (uint64_t)(__ffs((int)x) - 1);
+}
+__global__ void k_fetch_positions(const RawCid* __restrict__ seg, uint64_t nseg, uint64_t pos0, const uint64_t* __restrict__ req, uint64_t n, RawCid* out) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t p = req[j];
+    RawCid z{};
+    out[j] = (p >= pos0 && p - pos0 < nseg) ? seg[p - pos0] : z;
+}
+// EventProof.message_cid = exec[exec_index] (events/generator.rs:245, :289): answers are in the order of the matching list
+__global__ void k_patch_message_cids(ipcfp_event_proof* proofs, uint64_t n_proofs, const uint32_t* __restrict__ match_rel, uint64_t n_match, uint64_t lo,
+                                     const RawCid* __restrict__ answers) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_proofs) return;
+    const uint64_t i = proofs[k].exec_index;
+    if (i == 0xFFFFFFFFFFFFFFFFull || i < lo) return;
+    const uint32_t rel = (uint32_t)(i - lo);
+    uint64_t a = 0, b = n_match;
+    while (b - a > 1) { uint64_t m = (a + b) >> 1; if (match_rel[m] <= rel) a = m; else b = m; }
+    if (!n_match || match_rel[a] != rel) return;
+    const RawCid c = answers[a];
+    uint8_t* o = proofs[k].message_cid;
+    for (int q = 0; q < 6; q++) o[q] = (uint8_t)(c.w[4] >> (8 * q));
+    for (int q = 0; q < 32; q++) o[6 + q] = (uint8_t)(c.w[q >> 3] >> (8 * (q & 7)));
+}
+// n_exec = nraw − duplicates, published for pass 2 and the host
+__global__ void k_set_n_exec(const uint64_t* __restrict__ zprefix_total, unsigned long long* n_exec) { *n_exec = *zprefix_total; }
+
+// ------------------------------------------------------------------------------------------ witness union kernels
+// 38-byte CIDs ↔ 40-byte records {digest[32], prefix[6], 0, 0} (aligned words for the merge)
+__global__ void k_cids_to_recs(const uint8_t* __restrict__ cids, uint64_t n, uint64_t cap, RawCid* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    RawCid c{};
+    if (i < n) {
+        const uint8_t* s = cids + 38 * i;
+        uint64_t pre = 0;
+        for (int q = 0; q < 6; q++) pre |= (uint64_t)s[q] << (8 * q);
+        c.w[4] = pre;
+        for (int q = 0; q < 32; q++) c.w[q >> 3] |= (uint64_t)s[6 + q] << (8 * (q & 7));
+    }
+    out[i] = c;
+}
+__device__ __forceinline__ uint64_t bswap64_p(uint64_t x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+}
+// raw byte order of (prefix, digest) — `Cid` Ord for CIDs of one prefix (the Filecoin chain case, see ipcfp_merge_witness_cids)
+__device__ __forceinline__ int rec_cmp(const RawCid& a, const RawCid& b) {
+    uint64_t pa = bswap64_p(a.w[4] << 16), pb = bswap64_p(b.w[4] << 16);
+    if (pa != pb) return pa < pb ? -1 : 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint64_t x = bswap64_p(a.w[k]), y = bswap64_p(b.w[k]); if (x != y) return x < y ? -1 : 1; }
+    return 0;
+}
+__device__ __forceinline__ uint32_t rec_bucket(const RawCid& a) { return (uint32_t)((a.w[0] & 0xff) << 8 | ((a.w[0] >> 8) & 0xff)); }
+#define MERGE_BUCKETS 65536u
+// starts[b][B] = first index of list b whose bucket is >= B (B = 0..65536); lists are sorted, so every element fills the gap it closes
+__global__ void k_merge_starts(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap, uint32_t* starts) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)world * cap) return;
+    uint32_t b = (uint32_t)(g / cap);
+    uint64_t k = g % cap, n = counts[b];
+    uint32_t* st = starts + (uint64_t)b * (MERGE_BUCKETS + 1);
+    if (n == 0) { if (k == 0) for (uint32_t B = 0; B <= MERGE_BUCKETS; B++) st[B] = 0; return; }
+    if (k >= n) return;
+    const RawCid* L = lists + (uint64_t)b * cap;
+    uint32_t Bk = rec_bucket(L[k]);
+    uint32_t from = k == 0 ? 0 : rec_bucket(L[k - 1]) + 1;
+    for (uint32_t B = from; B <= Bk; B++) st[B] = (uint32_t)k;
+    if (k == n - 1) for (uint32_t B = Bk + 1; B <= MERGE_BUCKETS; B++) st[B] = (uint32_t)n;
+}
+// position of every element in the merged (still non-unique) order + is it the first of its CID
+__global__ void k_merge_rank(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap,
+                             const uint32_t* __restrict__ starts, uint32_t* pos_of, uint32_t* keep) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)world * cap) return;
+    uint32_t b = (uint32_t)(g / cap);
+    uint64_t k = g % cap;
+    if (k >= counts[b]) return;
+    const RawCid e = lists[(uint64_t)b * cap + k];
+    const uint32_t B = rec_bucket(e);
+    uint64_t pos = 0;
+    bool dup = false;
+    for (uint32_t q = 0; q < world; q++) {
+        const uint32_t* st = starts + (uint64_t)q * (MERGE_BUCKETS + 1);
+        uint32_t s0 = st[B], s1 = st[B + 1];
+        pos += s0;
+        if (q == b) { pos += k - s0; continue; }
+        const RawCid* L = lists + (uint64_t)q * cap;
+        for (uint32_t x = s0; x < s1; x++) {
+            int c = rec_cmp(L[x], e);
+            if (c < 0 || (c == 0 && q < b)) pos++;
+            if (c == 0 && q < b) dup = true;
+            if (c > 0) break;
+        }
+    }
+    pos_of[g] = (uint32_t)pos;
+    keep[pos] = dup ? 0u : 1u;
+}
+__global__ void k_merge_emit38(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap,
+                               const uint32_t* __restrict__ pos_of, const uint32_t* __restrict__ keep, const uint64_t* __restrict__ outidx, uint8_t* out) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)world * cap) return;
+    uint32_t b = (uint32_t)(g / cap);
+    uint64_t k = g % cap;
+    if (k >= counts[b]) return;
+    uint32_t pos = pos_of[g];
+    if (!keep[pos]) return;
+    const RawCid c = lists[(uint64_t)b * cap + k];
+    uint8_t* o = out + 38ull * outidx[pos];
+    for (int q = 0; q < 6; q++) o[q] = (uint8_t)(c.w[4] >> (8 * q));
+    for (int q = 0; q < 32; q++) o[6 + q] = (uint8_t)(c.w[q >> 3] >> (8 * (q & 7)));
+}
+
+}  // namespace ipcfp
