@@ -15,7 +15,7 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CU_HDRS)
 	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c $< -o $@
 
 $(LIB): $(CU_OBJS)
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) -lcudart
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) -lcudart -ldl
 
 synth/libipcfp_synth.so: synth/synth.cpp synth/synth.h synth/cpu_crypto.h
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ synth/synth.cpp

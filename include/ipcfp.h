@@ -67,8 +67,8 @@ typedef struct ipcfp_store ipcfp_store;
 
 #define IPCFP_STORE_VERIFY_CIDS 0x1u /* Blake2b-256 every block on the GPU and compare with its CID */
 
-/* cids: n*38 bytes; offsets[i]/lengths[i]: block i inside blob. Blocks whose offsets are all
- * 16-byte aligned are used in place; otherwise they are re-packed on the device. */
+/* cids: n*38 bytes; offsets[i]/lengths[i]: block i inside blob. Blocks are used in place at ANY offset / alignment
+ * (every device read is an aligned load plus a byte shift). */
 ipcfp_status ipcfp_store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t* lengths,
                                 const uint8_t* blob, uint64_t blob_size, uint64_t n_blocks,
                                 int device, uint32_t flags, ipcfp_store** out);
@@ -179,6 +179,17 @@ typedef struct ipcfp_event_result {
     const void* shard_exec_dev;
     uint64_t shard_exec_count;
     uint64_t shard_raw_total;         /* total length of the concatenated message list (all shards) */
+    /* ipcfp_generate_event_proof_sharded only: proofs[].message_cid and n_exec are final (resolved across shards inside the
+     * call); the union of ALL shards' witness CID sets (the BTreeSet union of src/proofs/common/witness.rs:24-40), sorted in
+     * `Cid` order, in DEVICE memory (n_union_cids*38 bytes, valid until the next sharded call on the same communicator) and —
+     * with IPCFP_SHARDED_UNION_TO_HOST — on the host; matches / proofs summed over all shards. */
+    const void* union_cids_dev;
+    uint64_t n_union_cids;
+    const uint8_t* union_cids;
+    uint64_t total_matching;
+    uint64_t total_proofs;
+    float ms_exchange, ms_fetch, ms_union; /* device time of the execution-order exchange (its own stream, under pass 1), the message-CID fetch, the witness union */
+    float _pad0;
 } ipcfp_event_result;
 
 typedef struct ipcfp_storage_proof {
@@ -222,6 +233,7 @@ typedef struct ipcfp_bundle {
  * ------------------------------------------------------------------------------------------ */
 #define IPCFP_SCAN_SKIP_TX_AMTS 0x1u  /* find_matching_events only: no record_transaction_amts / base witness;
                                          execution order still built                                          */
+#define IPCFP_SHARDED_UNION_TO_HOST 0x2u /* ipcfp_generate_event_proof_sharded: also copy the merged witness CID list to the host */
 
 /* generate_event_proof (src/proofs/events/generator.rs:60-107): base witness, message-AMT
  * recording, execution order, two-pass scan (find_matching_events :180-307), materialise. */
@@ -265,7 +277,27 @@ void ipcfp_bundle_free(ipcfp_bundle* b);
  * Receipts shard by index range; each rank scans its shard, then the per-shard witness CID sets
  * are all-gathered and merged (the BTreeSet union of src/proofs/common/witness.rs:24-40).
  * ------------------------------------------------------------------------------------------ */
-/* Scan receipts [lo, hi) only. events_roots/has_events_root in t cover ALL n_receipts. */
+/* In-library protocol (the reference's future-work "Parallel Generation", README.md:384): one communicator
+ * per process/GPU over NCCL (resolved with dlopen("libnccl.so.2") at init — the library itself links only cudart). Rank 0 makes
+ * the id and hands the 128 bytes to the other ranks by any means (MPI, a file, torch.distributed …).
+ * ipcfp_generate_event_proof_sharded = generate_event_proof (src/proofs/events/generator.rs:60-107) for ONE tipset whose
+ * receipts are split by index range bounds[rank] .. bounds[rank+1] (bounds: world+1 ascending values, bounds[0] = 0,
+ * bounds[world] = n_receipts); every rank's store holds the blocks its range needs (events blocks, receipts-AMT paths, its share
+ * of the message AMTs, the shared top levels). Inside the call: all-to-all + all-reduce for the first-seen dedup of the
+ * execution order (src/proofs/events/utils.rs:48-94), exec index → message CID fetch for the rank's proofs, and ONE all-gather of
+ * the per-shard witness CID sets merged on every rank. All ranks must make the call; they succeed or fail together and a
+ * failure names the same (status, index) everywhere — the one the reference's sequential order meets first over all shards.
+ * Errors: IPCFP_ERR_NCCL (library missing / communicator failure). */
+#define IPCFP_COMM_ID_BYTES 128
+typedef struct ipcfp_comm ipcfp_comm;
+ipcfp_status ipcfp_comm_unique_id(uint8_t id[IPCFP_COMM_ID_BYTES]);
+ipcfp_status ipcfp_comm_init(const uint8_t id[IPCFP_COMM_ID_BYTES], uint32_t world_size, uint32_t rank, int device, ipcfp_comm** out);
+void ipcfp_comm_destroy(ipcfp_comm* c);
+ipcfp_status ipcfp_generate_event_proof_sharded(ipcfp_comm* c, ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec,
+                                                const uint64_t* bounds /* world_size + 1 */, uint32_t flags, ipcfp_event_result** out);
+
+/* Lower-level pieces (the caller owns the collectives — e.g. torch.distributed with the gloo backend on hosts without NCCL):
+ * scan receipts [lo, hi) only. events_roots/has_events_root in t cover ALL n_receipts. */
 ipcfp_status ipcfp_generate_event_proof_shard(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_spec* spec,
                                               uint64_t lo, uint64_t hi, uint32_t world_size, uint32_t rank,
                                               uint32_t flags, ipcfp_event_result** out);

@@ -20,9 +20,12 @@ pub const IPCFP_ERR_NO_DEVICE: ipcfp_status = -10;
 pub const IPCFP_ERR_UNSUPPORTED: ipcfp_status = -11;
 pub const IPCFP_STORE_VERIFY_CIDS: u32 = 0x1;
 pub const IPCFP_SCAN_SKIP_TX_AMTS: u32 = 0x1;
+pub const IPCFP_SHARDED_UNION_TO_HOST: u32 = 0x2;
+pub const IPCFP_COMM_ID_BYTES: usize = 128;
 
 #[repr(C)] pub struct ipcfp_store { _p: [u8; 0] }
 #[repr(C)] pub struct ipcfp_tipset { _p: [u8; 0] }
+#[repr(C)] pub struct ipcfp_comm { _p: [u8; 0] }
 
 #[repr(C)]
 pub struct ipcfp_tipset_desc {
@@ -56,6 +59,8 @@ pub struct ipcfp_event_result {
     pub ms_total: f32, pub ms_pass1: f32, pub ms_pass2: f32, pub ms_txamt: f32, pub ms_witness: f32,
     pub pass1_bytes: u64, pub pass1_nodes: u64,
     pub shard_exec_dev: *const c_void, pub shard_exec_count: u64, pub shard_raw_total: u64,
+    pub union_cids_dev: *const c_void, pub n_union_cids: u64, pub union_cids: *const u8, pub total_matching: u64, pub total_proofs: u64,
+    pub ms_exchange: f32, pub ms_fetch: f32, pub ms_union: f32, pub _pad0: f32,
 }
 #[repr(C)]
 pub struct ipcfp_storage_proof {
@@ -114,6 +119,12 @@ extern "C" {
     pub fn ipcfp_generate_proof_bundle(s: *mut ipcfp_store, t: *const ipcfp_tipset_desc, sspecs: *const ipcfp_storage_spec, n_sspecs: u64,
                                        especs: *const ipcfp_event_spec, n_especs: u64, out: *mut *mut ipcfp_bundle) -> ipcfp_status;
     pub fn ipcfp_bundle_free(b: *mut ipcfp_bundle);
+
+    pub fn ipcfp_comm_unique_id(id: *mut u8) -> ipcfp_status;
+    pub fn ipcfp_comm_init(id: *const u8, world_size: u32, rank: u32, device: c_int, out: *mut *mut ipcfp_comm) -> ipcfp_status;
+    pub fn ipcfp_comm_destroy(c: *mut ipcfp_comm);
+    pub fn ipcfp_generate_event_proof_sharded(c: *mut ipcfp_comm, s: *mut ipcfp_store, t: *mut ipcfp_tipset, spec: *const ipcfp_event_spec,
+                                              bounds: *const u64, flags: u32, out: *mut *mut ipcfp_event_result) -> ipcfp_status;
 
     pub fn ipcfp_exec_bucketize(device: c_int, seg_dev: *const c_void, nseg: u64, pos0: u64, world: u32, cap: u64, send_dev: *mut c_void, counts: *mut u64) -> ipcfp_status;
     pub fn ipcfp_exec_dedup(device: c_int, recv_dev: *const c_void, counts: *const u64, world: u32, cap: u64, dup_pos_dev: *mut u64, cap_out: u64, n_dup: *mut u64) -> ipcfp_status;

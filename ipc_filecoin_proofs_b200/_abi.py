@@ -25,6 +25,8 @@ ERR_UNSUPPORTED = -11
 
 STORE_VERIFY_CIDS = 0x1
 SCAN_SKIP_TX_AMTS = 0x1
+SHARDED_UNION_TO_HOST = 0x2
+COMM_ID_BYTES = 128
 
 
 class TipsetDesc(C.Structure):
@@ -101,6 +103,15 @@ class EventResultC(C.Structure):
         ("shard_exec_dev", C.c_void_p),
         ("shard_exec_count", C.c_uint64),
         ("shard_raw_total", C.c_uint64),
+        ("union_cids_dev", C.c_void_p),
+        ("n_union_cids", C.c_uint64),
+        ("union_cids", C.c_void_p),
+        ("total_matching", C.c_uint64),
+        ("total_proofs", C.c_uint64),
+        ("ms_exchange", C.c_float),
+        ("ms_fetch", C.c_float),
+        ("ms_union", C.c_float),
+        ("_pad0", C.c_float),
     ]
 
 

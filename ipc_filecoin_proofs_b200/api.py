@@ -41,6 +41,7 @@ EXPORTS = [
     "ipcfp_bundle_free", "ipcfp_generate_event_proof_shard", "ipcfp_witness_cids_to_device", "ipcfp_merge_witness_cids",
     "ipcfp_tipset_upload", "ipcfp_tipset_free", "ipcfp_generate_event_proof_resident", "ipcfp_generate_event_proof_shard_resident",
     "ipcfp_store_stream", "ipcfp_exec_bucketize", "ipcfp_exec_dedup", "ipcfp_exec_fetch",
+    "ipcfp_comm_unique_id", "ipcfp_comm_init", "ipcfp_comm_destroy", "ipcfp_generate_event_proof_sharded",
 ]
 
 
@@ -116,6 +117,14 @@ def lib():
         L.ipcfp_merge_witness_cids.restype = C.c_int32
         L.ipcfp_merge_witness_cids.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                                C.POINTER(C.c_uint64)]
+        L.ipcfp_comm_unique_id.restype = C.c_int32
+        L.ipcfp_comm_unique_id.argtypes = [C.c_void_p]
+        L.ipcfp_comm_init.restype = C.c_int32
+        L.ipcfp_comm_init.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.ipcfp_comm_destroy.argtypes = [C.c_void_p]
+        L.ipcfp_generate_event_proof_sharded.restype = C.c_int32
+        L.ipcfp_generate_event_proof_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(A.EventSpec), C.c_void_p, C.c_uint32,
+                                                         C.POINTER(C.POINTER(A.EventResultC))]
         _lib = L
     return _lib
 

@@ -317,6 +317,34 @@ void ipcfp_bundle_free(ipcfp_bundle* b) {
     delete box;
 }
 
+ipcfp_status ipcfp_comm_unique_id(uint8_t id[IPCFP_COMM_ID_BYTES]) {
+    return guard([&] {
+        if (!id) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        comm_unique_id(id);
+    });
+}
+ipcfp_status ipcfp_comm_init(const uint8_t id[IPCFP_COMM_ID_BYTES], uint32_t world_size, uint32_t rank, int device, ipcfp_comm** out) {
+    return guard([&] {
+        if (!id || !out) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        *out = reinterpret_cast<ipcfp_comm*>(comm_init(id, world_size, rank, device));
+    });
+}
+void ipcfp_comm_destroy(ipcfp_comm* c) { if (c) comm_destroy(reinterpret_cast<Comm*>(c)); }
+ipcfp_status ipcfp_generate_event_proof_sharded(ipcfp_comm* c, ipcfp_store* s, ipcfp_tipset* t, const ipcfp_event_spec* spec, const uint64_t* bounds,
+                                                uint32_t flags, ipcfp_event_result** out) {
+    return guard([&] {
+        if (!c || !s || !t || !bounds || !out) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        Comm* cm = reinterpret_cast<Comm*>(c);
+        const uint32_t W = comm_world(cm), r = comm_rank(cm);
+        TipsetDev& td = *reinterpret_cast<TipsetDev*>(t);
+        for (uint32_t k = 0; k < W; k++) if (bounds[k] > bounds[k + 1]) throw Error(IPCFP_ERR_INVALID_ARG, "shard bounds must ascend");
+        if (bounds[0] != 0 || bounds[W] != td.n_receipts) throw Error(IPCFP_ERR_INVALID_ARG, "shard bounds must cover [0, n_receipts)");
+        *out = generate_event_proof(reinterpret_cast<Store*>(s), nullptr, td, spec, flags, true, bounds[r], bounds[r + 1], W, r, cm);
+    });
+}
+
 ipcfp_status ipcfp_exec_bucketize(int device, const void* seg_dev, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send_dev,
                                   uint64_t* counts) {
     return guard([&] {

@@ -87,6 +87,8 @@ struct TipsetDev {
 };
 
 struct ScopedStatus;  // capi.cu
+struct Comm;          // parallel.cu: NCCL communicator pair + exchange scratch of one rank
+struct RawCid;
 
 void set_last_error(const std::string& msg, uint64_t index);
 ipcfp_status status_from_devcode(uint32_t code);
@@ -107,13 +109,51 @@ void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint3
 // events.cu
 void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td);
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
-                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank);
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank, Comm* comm = nullptr);
 void event_result_free(ipcfp_event_result* r);
 void witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap, uint64_t* n);
 void merge_witness_cids(int device, const void* gathered, const uint64_t* counts, uint32_t world, uint64_t cap, void* out, uint64_t cap_out,
                         uint64_t* n_out);
 
-// parallel.cu
+// parallel.cu — in-library cross-shard protocol over NCCL (one process per GPU)
+void comm_unique_id(uint8_t* id128);
+Comm* comm_init(const uint8_t* id128, uint32_t world, uint32_t rank, int device);
+void comm_destroy(Comm* c);
+uint32_t comm_world(const Comm* c);
+uint32_t comm_rank(const Comm* c);
+// One sharded generate_event_proof call's share of the protocol (see the banner in parallel.cu). generate_event_proof drives it:
+//   agree_slices → start_exchange → positions_for → agree_results → fetch_and_patch → witness_union
+struct ShardExchange {
+    Comm* c;
+    Store* s;
+    uint64_t lo, hi;
+    // H0
+    std::vector<uint64_t> nseg_all;
+    uint64_t nraw = 0, max_nseg = 0, pos0 = 0, nseg = 0;
+    bool peers_ok = true;
+    // X
+    const RawCid* seg = nullptr;
+    uint64_t cap = 0, nwords = 0;
+    unsigned long long* n_exec_dev = nullptr;
+    unsigned long long* overflow_dev = nullptr;
+    // P / F
+    uint64_t M = 0;
+    const uint32_t* match_rel_dev = nullptr;
+    // H0 / H2 (global values, identical on every rank)
+    uint64_t g_tx = ~0ull, g_err = ~0ull;
+    bool g_missing_base = false, g_overflow = false;
+    uint64_t M_max = 0, nw_max = 0, M_total = 0, proofs_total = 0;
+    std::vector<uint64_t> nw_all;
+    ShardExchange(Comm* comm, Store* store, uint64_t lo_, uint64_t hi_);
+    void agree_slices(uint64_t tx_key, uint64_t err_key, uint64_t nseg_);
+    void start_exchange(const void* seg_dev, cudaEvent_t seg_ready);
+    void positions_for(cudaStream_t st, const uint32_t* match_rel, uint64_t n_match, unsigned long long* n_exec_out);
+    void agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow);
+    void fetch_and_patch(cudaStream_t st, ipcfp_event_proof* proofs_dev, uint64_t n_proofs);
+    void witness_union(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint8_t** out_dev, uint64_t* n_out_dev_word);
+    void timings(float* ms_exchange, float* ms_fetch, float* ms_union) const;   // after the call's final sync
+    uint64_t host_word(uint32_t i) const;   // the store's mapped words: 300 = exchange overflow flag, 301 = n_exec (valid after the sync that follows positions_for)
+};
 void exec_bucketize(int device, const void* seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send, uint64_t* counts_host);
 void exec_dedup(int device, const void* recv, const uint64_t* counts, uint32_t world, uint64_t cap, uint64_t* dup_dev, uint64_t cap_out, uint64_t* n_dup);
 void exec_fetch(int device, const void* seg, uint64_t nseg, uint64_t pos0, const uint64_t* req_dev, uint64_t n, void* out_dev);
@@ -143,7 +183,7 @@ struct WitnessBuilder {
     bool have_snapshot = false;
     AsyncBuf<uint32_t> idx, plen, bitsA, bitsB;
     AsyncBuf<uint64_t> offs, word_prefix, scratch;
-    AsyncBuf<uint8_t> dblobA;
+    AsyncBuf<uint8_t> dblobA, dblobB_keep;
     PinnedArray host_blob;
     explicit WitnessBuilder(Store* store);
     void snapshot(const uint32_t* wbits);        // enqueue; count → dev_words[8]
@@ -152,6 +192,8 @@ struct WitnessBuilder {
     void start_copy(uint64_t mA, uint64_t bytesA, uint64_t split_idx, uint64_t split_bytes);
     void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10]
     void finish(uint64_t mB, WitnessOut& out, bool want_sorted_idx = false);   // late blocks, Cid-order index arrays, join
+    void finish_start(uint64_t mB, WitnessOut& out, bool want_sorted_idx = false);   // … the same without the join: everything enqueued
+    void finish_join(WitnessOut& out);                                              // … wait for both streams
 };
 void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out);
 

@@ -379,6 +379,7 @@ struct EventResultBox {
     ipcfp_event_result r;  // must stay first
     PinnedArray matching, proofs, blob;
     WitnessOut wit;
+    PinnedArray union_host;       // sharded calls with IPCFP_SHARDED_UNION_TO_HOST
     AsyncBuf<RawCid> shard_exec;  // shard mode: this shard's slice of the raw execution list, kept on the device
 };
 
@@ -454,7 +455,7 @@ void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
 }
 
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*/, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
-                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/) {
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/, Comm* comm) {
     s->use();
     cudaStream_t st = s->stream;
     if (!spec || !spec->event_signature || !spec->topic_1) throw Error(IPCFP_ERR_INVALID_ARG, "event spec has null fields");
@@ -463,6 +464,26 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     const uint64_t N = hi - lo;
     const uint64_t nblk = s->n;
     const bool skip_tx = (flags & IPCFP_SCAN_SKIP_TX_AMTS) != 0;
+    // comm != nullptr: this call is one shard of a multi-GPU call and runs the cross-shard protocol itself (parallel.cu). Failures
+    // are then not thrown where they are seen: every rank keeps taking part in the collectives and all ranks fail together, with
+    // the error the reference's sequential order meets first across ALL shards.
+    std::unique_ptr<ShardExchange> xch;
+    if (comm) {
+        if (!sharded) throw Error(IPCFP_ERR_INVALID_ARG, "communicator given for an unsharded call");
+        if (s->class_prefix.size() > 1) throw Error(IPCFP_ERR_UNSUPPORTED, "sharded calls need a store with one CID prefix");
+        xch.reset(new ShardExchange(comm, s, lo, hi));
+    }
+    uint64_t pend_tx = IPCFP_NO_ERROR, pend_err = IPCFP_NO_ERROR;   // first failure seen so far (xch mode)
+    auto note_errors = [&](const uint64_t* hwp) {
+        if (!xch) { check_device_errors(hwp); return; }
+        pend_tx = std::min<uint64_t>(pend_tx, hwp[15]);
+        pend_err = std::min<uint64_t>(pend_err, hwp[0]);
+    };
+    auto throw_global = [&](uint64_t gtx, uint64_t gerr, bool gmissing) {
+        if (gtx != IPCFP_NO_ERROR) throw_tx_error(gtx);
+        if (gerr != IPCFP_NO_ERROR) throw_device_error(gerr);
+        if (gmissing) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
+    };
     unsigned long long* dw = s->dev_words.p;  // [0] err, [1..] counters
     uint64_t* hw = s->host_words.p;
 
@@ -650,6 +671,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     };
     bool dense_used = plan.ok;
     if (dense_used) run_dense(); else run_general();
+    IPCFP_CUDA(cudaEventRecord(s->ev[9], st));   // the raw message list of this call is complete (cross-shard exchange waits for it)
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
@@ -660,14 +682,23 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         dense_used = false;
         k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();   // re-seed the frontier (same outputs as before)
         run_general();
+        IPCFP_CUDA(cudaEventRecord(s->ev[9], st));
         wbuild.snapshot(wbits.p);
         publish_words(s, 0, 18);
         IPCFP_CUDA(cudaStreamSynchronize(st));
     }
     const uint32_t ccount_idx = (uint32_t)(ccount - dw);
-    check_device_errors(hw);
-    if (!dense_used && hw[ccount_idx] > raw_cap) throw Error(IPCFP_ERR_UNSUPPORTED, "unsupported input (message list longer than the walk's capacity)");
-    uint64_t nraw = dense_used ? plan.nraw : hw[ccount_idx];
+    note_errors(hw);
+    if (!dense_used && hw[ccount_idx] > raw_cap) {
+        if (!xch) throw Error(IPCFP_ERR_UNSUPPORTED, "unsupported input (message list longer than the walk's capacity)");
+        pend_tx = std::min<uint64_t>(pend_tx, tx_err_key(IPCFP_TX_EIDX_NONE, 0, 0, DC_UNSUPPORTED, 1));
+    }
+    uint64_t nraw = dense_used ? plan.nraw : std::min<uint64_t>(hw[ccount_idx], raw_cap);
+    if (xch && (pend_tx != IPCFP_NO_ERROR || pend_err != IPCFP_NO_ERROR)) {
+        // this shard has no message list: tell the peers (H0), then fail — with the first error over ALL shards, like them
+        xch->agree_slices(pend_tx, pend_err, 0);
+        throw_global(xch->g_tx, xch->g_err, false);
+    }
     wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
@@ -732,9 +763,17 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     exclusive_scan_u32(cnt.p, pbase.p, N, (uint64_t*)(dw + 7), scratch.p, st);
     exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
     publish_words(s, 0, 16);
+    if (xch) {
+        // pass 1 is running: agree on the slices with the peers (H0, one small all-gather the host waits for) and put the whole
+        // execution-order exchange on the exchange stream, underneath pass 1
+        xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
+        if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
+        xch->start_exchange(exec_raw.p, s->ev[9]);
+    }
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    check_device_errors(hw);
-    const uint64_t n_exec = hw[3], M = hw[6];
+    note_errors(hw);
+    uint64_t n_exec = hw[3];
+    const uint64_t M = hw[6];
     const uint64_t pass1_nodes = hw[4], pass1_bytes = hw[5];
     uint64_t n_proofs = hw[7], n_bytes = hw[12];
 
@@ -744,12 +783,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     AsyncBuf<ipcfp_event_proof> d_proofs(n_proofs + 1, st);
     AsyncBuf<uint8_t> d_blob(n_bytes + 16, st);
     uint32_t* any_skip_dev = misc.p + 2;
+    if (xch) xch->positions_for(st, match_rel.p, M, n_exec_dev);   // global n_exec for pass 2's exec.get(i) check; raw positions of the matches
     if (M) {
         Pass2Args p2;
         p2.store = s->view; p2.store_dev = s->view_dev.p; p2.m_dev = d_matcher; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
         p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
         p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
-        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = sharded ? 0 : 1;
+        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = xch ? 2 : (sharded ? 0 : 1);
         k_pass2<<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
@@ -757,11 +797,19 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     publish_words(s, 0, 16);
     publish_words_from(s, misc.p, 20, 2);   // misc[2] = any_skip (32-bit words 0..3 land in hw[20..21])
     IPCFP_CUDA(cudaStreamSynchronize(st));
-    check_device_errors(hw);
+    note_errors(hw);
     // base-witness CIDs (parent headers, child header, TxMeta) are only dereferenced by WitnessCollector::materialize
     // (common/witness.rs:43-56, events/generator.rs:104), i.e. AFTER every receipts-root / pass-1 / pass-2 failure
-    if (missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
+    if (!xch && missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
     const uint64_t mB = hw[10];
+    if (xch) {
+        // H2: how far did every shard get. All ranks continue or fail together, naming the same first error.
+        xch->agree_results(pend_tx, pend_err, missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300));
+        throw_global(xch->g_tx, xch->g_err, xch->g_missing_base);
+        if (xch->g_overflow) throw Error(IPCFP_ERR_UNSUPPORTED, "execution-order exchange: bucket overflow (skewed CID hash distribution)");
+        n_exec = xch->host_word(301);
+        xch->fetch_and_patch(st, d_proofs.p, n_proofs);   // EventProof.message_cid = exec[exec_index], fetched from the shards that hold them
+    }
     const bool any_skip = ((const uint32_t*)(hw + 20))[2] != 0;
     IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
 
@@ -776,7 +824,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     if (n_bytes) IPCFP_CUDA(cudaMemcpyAsync(box->blob.p, d_blob.p, n_bytes, cudaMemcpyDeviceToHost, st));
 
     // ---- witness
-    wbuild.finish(mB, box->wit);
+    wbuild.finish_start(mB, box->wit);
+    uint8_t* union_dev = nullptr;
+    if (xch) {
+        xch->witness_union(st, box->wit.cids_dev.p, box->wit.n, &union_dev, (uint64_t*)(dw + 18));
+        publish_words(s, 18, 1);
+    }
+    wbuild.finish_join(box->wit);
     IPCFP_CUDA(cudaEventRecord(s->ev[5], st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     {
@@ -805,6 +859,18 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     r.pass1_bytes = pass1_bytes; r.pass1_nodes = pass1_nodes;
     r.shard_raw_total = nraw_total;
     if (sharded) { r.n_exec = 0; r.shard_exec_count = nraw; box->shard_exec = std::move(exec_raw); r.shard_exec_dev = box->shard_exec.p; }
+    if (xch) {
+        r.n_exec = n_exec;
+        r.union_cids_dev = union_dev; r.n_union_cids = hw[18];
+        r.total_matching = xch->M_total; r.total_proofs = xch->proofs_total;
+        xch->timings(&r.ms_exchange, &r.ms_fetch, &r.ms_union);
+        if (flags & IPCFP_SHARDED_UNION_TO_HOST) {
+            box->union_host = PinnedArray(s->pool, r.n_union_cids * 38 + 64);
+            if (r.n_union_cids) IPCFP_CUDA(cudaMemcpyAsync(box->union_host.p, union_dev, r.n_union_cids * 38, cudaMemcpyDeviceToHost, st));
+            IPCFP_CUDA(cudaStreamSynchronize(st));
+            r.union_cids = box->union_host.as<uint8_t>();
+        }
+    }
     return &box.release()->r;
 }
 

@@ -185,7 +185,8 @@ struct Pass2Args {
     ipcfp_event_proof* proofs;
     uint8_t* blob;
     uint32_t* any_skip;            // set when a matching receipt is absent from the receipts AMT
-    uint32_t resolve_msg;          // 0 in shard mode: execution order is resolved across ranks afterwards
+    uint32_t resolve_msg;          // 1: exec.get(i) check + message CID from exec_cids; 0: neither (shard, execution order resolved by the
+                                   // caller afterwards); 2: the check against the GLOBAL n_exec only (in-library cross-shard protocol)
 };
 
 // One thread per matching receipt (events/generator.rs:242-301): exec.get(i), r_amt.get(i) with path
@@ -215,7 +216,7 @@ __device__ __forceinline__ void pass2_item(const Pass2Args& a, uint64_t t) {
     ec.blob = a.blob;
     ec.blob_off = a.byte_base[rel];
     ec.exec_index = i;
-    if (a.resolve_msg) ec.msg_cid = a.exec_cids[a.exec_idx[i]]; else ec.msg_cid = RawCid{};
+    if (a.resolve_msg == 1) ec.msg_cid = a.exec_cids[a.exec_idx[i]]; else ec.msg_cid = RawCid{};
     uint32_t rc = walk_events<WALK_EMIT>(a.store_dev, (uint32_t)root, a.m_dev, a.wbits, wo, &ec, &detail);
     if (rc) report_error(a.err, ST_PASS2, i, rc, detail);
 }

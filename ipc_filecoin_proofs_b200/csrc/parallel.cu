@@ -255,6 +255,7 @@ struct Comm {
     ncclComm_t cx = nullptr, cw = nullptr;   // exchange (execution order) / witness union: independent streams, independent communicators
     cudaStream_t sx = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaEvent_t tm[6] = {};                  // timing: exchange begin/end (sx), fetch begin/end, union begin/end (engine stream)
     // grow-only device scratch (allocated during warm-up, then reused)
     DevBuf<uint8_t> sendbuf, recvbuf, gather, merged, recs;
     DevBuf<unsigned long long> table, words, words2;
@@ -270,6 +271,7 @@ struct Comm {
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
         if (ev_c) cudaEventDestroy(ev_c);
+        for (auto& e : tm) if (e) cudaEventDestroy(e);
         if (sx) cudaStreamDestroy(sx);
     }
 };
@@ -290,9 +292,10 @@ Comm* comm_init(const uint8_t* id128, uint32_t world, uint32_t rank, int device)
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
-    c->host.alloc(64 + 8 * 256);
-    c->words.alloc(64 + 8 * 256);
-    c->words2.alloc(64 + 8 * 256);
+    for (auto& e : c->tm) IPCFP_CUDA(cudaEventCreate(&e));
+    c->host.alloc(4096);    // mapped: [0, 2048) gathered words of H0 / H2
+    c->words.alloc(4096);
+    c->words2.alloc(4096);
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     IPCFP_NCCL(n->CommInitRank(&c->cx, (int)world, id, (int)rank));
@@ -523,6 +526,222 @@ __global__ void k_merge_emit38(const RawCid* __restrict__ lists, const uint64_t*
     uint8_t* o = out + 38ull * outidx[pos];
     for (int q = 0; q < 6; q++) o[q] = (uint8_t)(c.w[4] >> (8 * q));
     for (int q = 0; q < 32; q++) o[6 + q] = (uint8_t)(c.w[q >> 3] >> (8 * (q & 7)));
+}
+
+}  // namespace ipcfp
+
+// ------------------------------------------------------------------------------------------ host side of the protocol
+namespace ipcfp {
+
+struct Words8 { uint64_t w[8]; };
+__global__ void k_put_words(Words8 v, uint32_t k, unsigned long long* dst) { if (threadIdx.x < k) dst[threadIdx.x] = v.w[threadIdx.x]; }
+__global__ void k_fill_words(unsigned long long* dst, uint32_t n, unsigned long long v) { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = v; }
+__global__ void k_publish_words(const unsigned long long* __restrict__ src, unsigned long long* dst_mapped, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+    __threadfence_system();
+}
+// word `field` of every rank's 8-word H2 record → dst[r]
+__global__ void k_pick_field(const unsigned long long* __restrict__ gathered, uint32_t world, uint32_t stride, uint32_t field, uint64_t* dst) {
+    for (uint32_t r = threadIdx.x; r < world; r += blockDim.x) dst[r] = gathered[(uint64_t)r * stride + field];
+}
+// Tiny all-gather of k ≤ 8 words per rank whose result the HOST needs. No copy-engine work (the D2H engine is busy with the
+// witness blob): the words go up as a kernel parameter and come back through mapped host memory.
+static void run_all_gather_host(Comm* c, const uint64_t* mine, uint32_t k, uint64_t* all /* = c->host.p */) {
+    NcclApi* n = nccl_api();
+    Words8 v{};
+    for (uint32_t i = 0; i < k && i < 8; i++) v.w[i] = mine[i];
+    k_put_words<<<1, 32, 0, c->sx>>>(v, k, c->words.p); IPCFP_LAUNCH_CHECK();
+    IPCFP_NCCL(n->AllGather(c->words.p, c->words2.p, k, ncclUint64, c->cx, c->sx));
+    k_publish_words<<<1, 256, 0, c->sx>>>(c->words2.p, (unsigned long long*)c->host.dev, c->world * k); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaStreamSynchronize(c->sx));
+    (void)all;
+}
+
+uint64_t ShardExchange::host_word(uint32_t i) const { return s->host_words.p[i]; }
+ShardExchange::ShardExchange(Comm* comm, Store* store, uint64_t lo_, uint64_t hi_) : c(comm), s(store), lo(lo_), hi(hi_) {
+    if (c->device != s->device) throw Error(IPCFP_ERR_INVALID_ARG, "communicator and store are bound to different devices");
+    if (c->world > 255) throw Error(IPCFP_ERR_UNSUPPORTED, "world too large");
+}
+
+// H0: does every shard have its slice of the message list, and how long is it. Every rank takes part, also a failing one.
+void ShardExchange::agree_slices(uint64_t tx_key, uint64_t err_key, uint64_t nseg_) {
+    const uint32_t W = c->world;
+    const bool ok = tx_key == IPCFP_NO_ERROR && err_key == IPCFP_NO_ERROR;
+    uint64_t mine[4] = {ok ? 1ull : 0ull, ok ? nseg_ : 0, tx_key, err_key};
+    uint64_t* all = c->host.p;
+    run_all_gather_host(c, mine, 4, all);
+    nseg_all.assign(W, 0);
+    bool all_ok = true;
+    nraw = 0; max_nseg = 0;
+    g_tx = g_err = IPCFP_NO_ERROR;
+    for (uint32_t r = 0; r < W; r++) {
+        if (!all[4 * r]) all_ok = false;
+        g_tx = std::min(g_tx, all[4 * r + 2]); g_err = std::min(g_err, all[4 * r + 3]);
+        nseg_all[r] = all[4 * r + 1];
+        if (r == c->rank) pos0 = nraw;
+        nraw += nseg_all[r];
+        max_nseg = std::max(max_nseg, nseg_all[r]);
+    }
+    peers_ok = all_ok;
+    nseg = nseg_;
+    if (nraw >= 0xffffffffull) throw Error(IPCFP_ERR_UNSUPPORTED, "more than 2^32 messages");
+}
+
+// X: bucketize → all-to-all → dedup → duplicate bitmap → all-reduce, all on the exchange stream (runs underneath pass 1)
+void ShardExchange::start_exchange(const void* seg_dev, cudaEvent_t seg_ready) {
+    NcclApi* n = nccl_api();
+    const uint32_t W = c->world;
+    cudaStream_t sx = c->sx;
+    seg = (const RawCid*)seg_dev;
+    IPCFP_CUDA(cudaStreamWaitEvent(sx, seg_ready, 0));
+    IPCFP_CUDA(cudaEventRecord(c->tm[0], sx));
+    cap = max_nseg / W + max_nseg / (4 * W) + 1024;
+    const uint64_t segbytes = XSEG_HDR + cap * 48;
+    c->sendbuf.ensure(segbytes * W);
+    c->recvbuf.ensure(segbytes * W);
+    nwords = (nraw + 31) / 32;
+    c->bitmap.ensure(nwords + 64);
+    c->bitmap_sum.ensure(nwords + 64);
+    c->zeros.ensure(nwords + 64);
+    c->zprefix.ensure(nwords + 64);
+    c->scan_tmp.ensure(scan_scratch_elems(nwords + 64) + 64);
+    uint64_t slots = 64;
+    while (slots < 2 * (W * cap)) slots <<= 1;
+    c->table.ensure(slots);
+    unsigned long long* small = c->words.p + 2200;        // [0, W]: first sorted position of every owner
+    unsigned long long* overflow = c->words.p + 3100;
+    IPCFP_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (nwords + 64) * 4, sx));
+    IPCFP_CUDA(cudaMemsetAsync(c->table.p, 0, slots * 8, sx));
+    IPCFP_CUDA(cudaMemsetAsync(overflow, 0, 8, sx));
+    // headers of empty segments must read 0 even when this rank has nothing to send
+    for (uint32_t r = 0; r < W; r++) IPCFP_CUDA(cudaMemsetAsync(c->sendbuf.p + r * segbytes, 0, XSEG_HDR, sx));
+    if (nseg) {
+        unsigned nb = radix_blocks(nseg);
+        AsyncBuf<uint32_t> keys(nseg, sx), vals(nseg, sx), ka(nseg, sx), va(nseg, sx), hist((size_t)256 * nb + 256, sx);
+        AsyncBuf<uint64_t> scan_tmp((size_t)256 * nb + 256, sx), scratch(scan_scratch_elems((uint64_t)256 * nb) + 8, sx);
+        k_fill_words<<<1, 256, 0, sx>>>(small, W + 1, nseg); IPCFP_LAUNCH_CHECK();
+        k_exec_owner<<<div_up(nseg, 256), 256, 0, sx>>>(seg, nseg, W, keys.p, vals.p); IPCFP_LAUNCH_CHECK();
+        if (W > 1) radix_sort_pairs(keys.p, vals.p, ka.p, va.p, nseg, 8, hist.p, scan_tmp.p, scratch.p, sx);
+        k_exec_starts<<<div_up(nseg, 256), 256, 0, sx>>>(keys.p, nseg, small); IPCFP_LAUNCH_CHECK();
+        k_exec_seg_headers<<<1, 1, 0, sx>>>(small, nseg, W, cap, c->sendbuf.p, overflow); IPCFP_LAUNCH_CHECK();
+        k_exec_scatter_seg<<<div_up(nseg, 256), 256, 0, sx>>>(seg, keys.p, vals.p, nseg, pos0, small, cap, c->sendbuf.p); IPCFP_LAUNCH_CHECK();
+    }
+    // all-to-all of whole segments (fixed size: no count round trip; the valid count travels in the segment header)
+    IPCFP_NCCL(n->GroupStart());
+    for (uint32_t p = 0; p < W; p++) {
+        IPCFP_NCCL(n->Send(c->sendbuf.p + p * segbytes, segbytes, ncclUint8, (int)p, c->cx, sx));
+        IPCFP_NCCL(n->Recv(c->recvbuf.p + p * segbytes, segbytes, ncclUint8, (int)p, c->cx, sx));
+    }
+    IPCFP_NCCL(n->GroupEnd());
+    uint64_t* seg_off = (uint64_t*)(c->words.p + 2600);   // [0, W]
+    k_recv_offsets<<<1, 1, 0, sx>>>(c->recvbuf.p, W, cap, seg_off); IPCFP_LAUNCH_CHECK();
+    const unsigned g = div_up(W * cap, 256);
+    k_exec_claim_seg<<<g, 256, 0, sx>>>(c->recvbuf.p, seg_off, W, cap, c->table.p, slots - 1); IPCFP_LAUNCH_CHECK();
+    k_exec_mark_dups<<<g, 256, 0, sx>>>(c->recvbuf.p, seg_off, W, cap, c->table.p, slots - 1, c->bitmap.p); IPCFP_LAUNCH_CHECK();
+    // the owners' bitmaps are disjoint (a position belongs to one CID, a CID to one owner): their sum is their union
+    IPCFP_NCCL(n->AllReduce(c->bitmap.p, c->bitmap_sum.p, nwords + 1, ncclUint32, ncclSum, c->cx, sx));
+    // n_exec = number of zero bits; prefix zero counts for the select
+    if (nwords) { k_zero_counts<<<div_up(nwords, 256), 256, 0, sx>>>(c->bitmap_sum.p, nraw, c->zeros.p); IPCFP_LAUNCH_CHECK(); }
+    n_exec_dev = c->words.p + 3101;
+    exclusive_scan_u32(c->zeros.p, c->zprefix.p, nwords, (uint64_t*)n_exec_dev, c->scan_tmp.p, sx);
+    IPCFP_CUDA(cudaEventRecord(c->ev_a, sx));
+    IPCFP_CUDA(cudaEventRecord(c->tm[1], sx));
+    overflow_dev = overflow;
+}
+
+// P: before pass 2 — the global n_exec for the "Missing message at index" check, raw positions of this rank's matches
+void ShardExchange::positions_for(cudaStream_t st, const uint32_t* match_rel, uint64_t n_match, unsigned long long* n_exec_out) {
+    IPCFP_CUDA(cudaStreamWaitEvent(st, c->ev_a, 0));
+    IPCFP_CUDA(cudaMemcpyAsync(n_exec_out, n_exec_dev, 8, cudaMemcpyDeviceToDevice, st));
+    publish_words_from(s, overflow_dev, 300, 2);   // host_words[300] = exchange overflow flag, [301] = n_exec: read after the caller's next sync
+    M = n_match;
+    c->req.ensure(n_match + 64);
+    if (n_match) {
+        k_select_positions<<<div_up(n_match, 128), 128, 0, st>>>(match_rel, n_match, lo, c->bitmap_sum.p, c->zprefix.p, nwords, n_exec_dev, c->req.p);
+        IPCFP_LAUNCH_CHECK();
+    }
+    match_rel_dev = match_rel;
+}
+
+// H2: every rank reports how far it got; all ranks continue or fail TOGETHER, with the same (first) error
+void ShardExchange::agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow) {
+    const uint32_t W = c->world;
+    uint64_t mine[8] = {tx_key, err_key, missing_base ? 1ull : 0ull, M, n_proofs, n_witness, exch_overflow, 0};
+    uint64_t* all = c->host.p;
+    run_all_gather_host(c, mine, 8, all);
+    k_pick_field<<<1, 256, 0, c->sx>>>(c->words2.p, W, 8, 5, (uint64_t*)(c->words2.p + 2600)); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaStreamSynchronize(c->sx));
+    g_tx = g_err = IPCFP_NO_ERROR; g_missing_base = false; g_overflow = false;
+    M_max = 0; nw_max = 0; M_total = 0; proofs_total = 0;
+    nw_all.assign(W, 0);
+    for (uint32_t r = 0; r < W; r++) {
+        const uint64_t* a = all + 8 * r;
+        g_tx = std::min(g_tx, a[0]); g_err = std::min(g_err, a[1]);
+        g_missing_base |= a[2] != 0;
+        M_max = std::max(M_max, a[3]); M_total += a[3]; proofs_total += a[4];
+        nw_all[r] = a[5]; nw_max = std::max(nw_max, a[5]);
+        g_overflow |= a[6] != 0;
+    }
+}
+
+// F: positions wanted by every rank → the owners answer → EventProof.message_cid of this rank's proofs
+void ShardExchange::fetch_and_patch(cudaStream_t st, ipcfp_event_proof* proofs_dev, uint64_t n_proofs) {
+    IPCFP_CUDA(cudaEventRecord(c->tm[2], st));
+    IPCFP_CUDA(cudaEventRecord(c->tm[3], st));
+    if (M_max == 0) return;
+    NcclApi* n = nccl_api();
+    const uint32_t W = c->world;
+    c->req_all.ensure((uint64_t)W * M_max + 64);
+    c->ans.ensure(((uint64_t)W * M_max + 8) * 5);
+    c->ans_sum.ensure(((uint64_t)W * M_max + 8) * 5);
+    // pad this rank's request list to M_max with "nobody's position"
+    if (M_max > M) IPCFP_CUDA(cudaMemsetAsync(c->req.p + M, 0xff, (M_max - M) * 8, st));
+    IPCFP_NCCL(n->AllGather(c->req.p, c->req_all.p, M_max, ncclUint64, c->cx, st));
+    const uint64_t total = (uint64_t)W * M_max;
+    k_fetch_positions<<<div_up(total, 256), 256, 0, st>>>(seg, nseg, pos0, c->req_all.p, total, (RawCid*)c->ans.p); IPCFP_LAUNCH_CHECK();
+    IPCFP_NCCL(n->AllReduce(c->ans.p, c->ans_sum.p, total * 5, ncclUint64, ncclSum, c->cx, st));
+    if (n_proofs) {
+        k_patch_message_cids<<<div_up(n_proofs, 128), 128, 0, st>>>(proofs_dev, n_proofs, match_rel_dev, M, lo, (const RawCid*)c->ans_sum.p + (uint64_t)c->rank * M_max);
+        IPCFP_LAUNCH_CHECK();
+    }
+    IPCFP_CUDA(cudaEventRecord(c->tm[3], st));
+}
+
+// W: union of the per-shard sorted witness CID lists (BTreeSet union of common/witness.rs:24-40) on every rank
+void ShardExchange::witness_union(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint8_t** out_dev, uint64_t* n_out_dev_word) {
+    NcclApi* n = nccl_api();
+    const uint32_t W = c->world;
+    IPCFP_CUDA(cudaEventRecord(c->tm[4], st));
+    const uint64_t capw = nw_max + 1;
+    const uint64_t total_cap = (uint64_t)W * capw;
+    c->recs.ensure(capw * 40 + 64);
+    c->gather.ensure(total_cap * 40 + 64);
+    c->starts.ensure((uint64_t)W * (MERGE_BUCKETS + 1) + 64);
+    c->pos_of.ensure(total_cap + 64);
+    c->flags.ensure(total_cap + 64);
+    c->fscan.ensure(total_cap + 64);
+    c->merged.ensure(total_cap * 38 + 64);
+    c->scan_tmp.ensure(scan_scratch_elems(total_cap + 64) + 64);
+    k_cids_to_recs<<<div_up(capw, 256), 256, 0, st>>>(cids_dev, n_local, capw, (RawCid*)c->recs.p); IPCFP_LAUNCH_CHECK();
+    IPCFP_NCCL(n->AllGather(c->recs.p, c->gather.p, capw * 40, ncclUint8, c->cw, st));
+    uint64_t* counts = (uint64_t*)(c->words2.p + 2600);   // per-rank list lengths, picked out of the H2 records by agree_results
+    IPCFP_CUDA(cudaMemsetAsync(c->flags.p, 0, (total_cap + 64) * 4, st));
+    const unsigned g = div_up(total_cap, 256);
+    k_merge_starts<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p); IPCFP_LAUNCH_CHECK();
+    k_merge_rank<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p, c->pos_of.p, c->flags.p); IPCFP_LAUNCH_CHECK();
+    uint64_t total_listed = 0;
+    for (uint32_t r = 0; r < W; r++) total_listed += nw_all[r];
+    unsigned long long* n_union = c->words2.p + 3000;
+    exclusive_scan_u32(c->flags.p, c->fscan.p, total_listed, (uint64_t*)n_union, c->scan_tmp.p, st);
+    k_merge_emit38<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->pos_of.p, c->flags.p, c->fscan.p, c->merged.p); IPCFP_LAUNCH_CHECK();
+    *out_dev = c->merged.p;
+    IPCFP_CUDA(cudaMemcpyAsync(n_out_dev_word, n_union, 8, cudaMemcpyDeviceToDevice, st));
+    IPCFP_CUDA(cudaEventRecord(c->tm[5], st));
+}
+void ShardExchange::timings(float* ms_exchange, float* ms_fetch, float* ms_union) const {
+    cudaEventElapsedTime(ms_exchange, c->tm[0], c->tm[1]);
+    cudaEventElapsedTime(ms_fetch, c->tm[2], c->tm[3]);
+    cudaEventElapsedTime(ms_union, c->tm[4], c->tm[5]);
 }
 
 }  // namespace ipcfp

@@ -200,6 +200,10 @@ void WitnessBuilder::finish_enqueue(const uint32_t* wbits) {
     bitmap_to_indices(bitsB.p, s->n, idx.p + mA, (uint64_t*)(dw + 10), word_prefix.p, scratch.p, st);
 }
 void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out, bool want_sorted_idx) {
+    finish_start(mB_, out, want_sorted_idx);
+    finish_join(out);
+}
+void WitnessBuilder::finish_start(uint64_t mB_, WitnessOut& out, bool want_sorted_idx) {
     mB = mB_;
     unsigned long long* dw = s->dev_words.p;
     uint64_t m = mA + mB;
@@ -245,6 +249,9 @@ void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out, bool want_sorted_idx)
         if (want_sorted_idx) IPCFP_CUDA(cudaMemcpyAsync(out.sorted_idx.p, d_idx.p, m * 4, cudaMemcpyDeviceToHost, st));
     }
     out.cids_dev = std::move(d_cids);
+    dblobB_keep = std::move(dblobB);
+}
+void WitnessBuilder::finish_join(WitnessOut& out) {
     IPCFP_CUDA(cudaStreamWaitEvent(st, s->ev[7], 0));  // the big copy on the side stream
     IPCFP_CUDA(cudaStreamSynchronize(st));
     IPCFP_CUDA(cudaStreamSynchronize(st2));

@@ -168,6 +168,92 @@ def gpu_worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
+def nccl_worker(rank, world, port, q):
+    """One rank per GPU: the library's own protocol (ipcfp_generate_event_proof_sharded over NCCL) against the oracle of the WHOLE
+    tipset — every EventProof incl. message_cid, n_exec, the local witness, the merged witness CID union — and the common failure."""
+    try:
+        import ctypes as C
+        import oracle
+        import synth
+        from ipc_filecoin_proofs_b200 import _abi as A
+        from ipc_filecoin_proofs_b200 import api
+        from ipc_filecoin_proofs_b200 import parallel as PL
+        import torch
+        dist = _init(rank, world, port, "gloo")       # carries the 128-byte id only
+        dev = rank % torch.cuda.device_count()
+        L = api.lib()
+        comm = PL.ShardedComm.from_torch_group(L, dist, dev)
+        for params in (PARAMS, dict(seed=5, n_receipts=20011, events_per_receipt=8, match_ppm=2000, dup_msgs=0, n_parents=2),
+                       dict(seed=9, n_receipts=257, events_per_receipt=3, match_ppm=500000, dup_msgs=40, n_parents=5)):
+            N = params["n_receipts"]
+            bounds = [N * r // world for r in range(world + 1)]
+            lo, hi = bounds[rank], bounds[rank + 1]
+            full = synth.Tipset(synth.default_params(**params))
+            shard = synth.Tipset(synth.default_params(shard_lo=lo, shard_hi=hi, **params)) if world > 1 else full
+            spec = A.make_event_spec(full.event_signature, full.topic1, full.actor_filter)
+            ost = oracle.Store.from_tipset(full)
+            exp = ost.generate_event_proof(full, spec)
+            exp_shard = ost.generate_event_proof_shard(full, spec, lo, hi, world, rank) if world > 1 else exp
+            store = api.BlockStore.from_tipset(shard, device=dev, verify_cids=True)
+            d, keep = A.make_tipset_desc(shard)
+            tip = C.c_void_p()
+            assert L.ipcfp_tipset_upload(store._h, C.byref(d), C.byref(tip)) == 0
+            for rep in range(2):                           # the second call reuses every buffer of the communicator
+                out = comm.generate_event_proof(store._h, tip, spec, bounds, A.SHARDED_UNION_TO_HOST)
+                r = out.contents
+                got = A.event_result_from_c(r)
+                n_union = int(r.n_union_cids)
+                union = np.frombuffer((C.c_uint8 * (n_union * 38)).from_address(r.union_cids), dtype=np.uint8).reshape(-1, 38).copy() if n_union else np.zeros((0, 38), np.uint8)
+                totals = (int(r.total_matching), int(r.total_proofs), int(r.n_exec))
+                L.ipcfp_event_result_free(out)
+                assert totals == (len(exp.matching), len(exp.proofs), exp.n_exec), (totals, len(exp.matching), len(exp.proofs), exp.n_exec)
+                assert got.matching.tolist() == exp_shard.matching.tolist()
+                mine = [p for p in exp.proofs if lo <= p.exec_index < hi]
+                assert [p.key() for p in got.proofs] == [p.key() for p in mine]                       # message_cid included
+                assert np.array_equal(got.witness.cids, exp_shard.witness.cids) and got.witness.blocks() == exp_shard.witness.blocks()
+                assert np.array_equal(union, exp.witness.cids), (union.shape, exp.witness.cids.shape)
+            # a fault on ONE rank: every rank fails, naming the same error — the one the oracle of the whole tipset names
+            if len(exp.matching):
+                victim_rcpt = int(exp.matching[len(exp.matching) // 2])
+                owner = max(r for r in range(world) if bounds[r] <= victim_rcpt)
+                bad = shard
+                if owner == rank:
+                    from tests.util import EditedTipset
+                    cid = bytes(full.events_roots[victim_rcpt])
+                    idx = next(i for i in range(shard.n_blocks) if bytes(shard.cids[i]) == cid)
+                    blob = shard.blob.copy()
+                    blob[int(shard.offsets[idx])] ^= 0xff                                              # root block no longer decodes
+                    bad = EditedTipset(shard, blob=blob)
+                fidx = next(i for i in range(full.n_blocks) if bytes(full.cids[i]) == bytes(full.events_roots[victim_rcpt]))
+                fblob = full.blob.copy()
+                fblob[int(full.offsets[fidx])] ^= 0xff
+                from tests.util import EditedTipset as ET
+                try:
+                    oracle.Store.from_tipset(ET(full, blob=fblob)).generate_event_proof(full, spec)
+                    raise AssertionError("oracle accepted a damaged block")
+                except A.IpcfpError as e:
+                    want = (e.status, e.index)
+                bstore = api.BlockStore.from_tipset(bad, device=dev)
+                btip = C.c_void_p()
+                assert L.ipcfp_tipset_upload(bstore._h, C.byref(d), C.byref(btip)) == 0
+                try:
+                    o2 = comm.generate_event_proof(bstore._h, btip, spec, bounds)
+                    L.ipcfp_event_result_free(o2)
+                    raise AssertionError("sharded call accepted a damaged block")
+                except A.IpcfpError as e:
+                    assert (e.status, e.index) == want, ((e.status, e.index), want)
+                L.ipcfp_tipset_free(btip)
+                bstore.close()
+            L.ipcfp_tipset_free(tip)
+            store.close()
+        comm.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
 def run(worker, world=2):
     import socket
     import torch.multiprocessing as mp

@@ -32,3 +32,21 @@ def test_cross_shard_protocol_gloo_cpu_world4():
 def test_cross_shard_engine_two_ranks_one_gpu():
     """2 processes sharing cuda:0 over gloo: the CUDA engine on sharded stores + ipcfp_exec_* helpers."""
     dist_worker.run(dist_worker.gpu_worker, world=2)
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_call_over_nccl(world):
+    """The in-library protocol (ipcfp_comm_init + ipcfp_generate_event_proof_sharded), one rank per GPU over NCCL, bit-exact against
+    the oracle of the whole tipset (proofs incl. message_cid, n_exec, merged witness CID list) and failing together on a fault."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} visible GPUs")
+    dist_worker.run(dist_worker.nccl_worker, world=world)
