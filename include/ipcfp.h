@@ -219,6 +219,9 @@ typedef struct ipcfp_slot_result {
     const uint8_t* values;     /* n*32, left-padded                        */
     ipcfp_witness witness;     /* blocks touched by the lookups (recorder) */
     float ms_total;
+    float ms_lookup;           /* device time of the lookup kernel alone (CUDA events on the engine stream)              */
+    uint64_t lookup_nodes;     /* HAMT nodes decoded by the lookups                                                      */
+    uint64_t lookup_bytes;     /* algorithmic bytes of the lookups: 32 per key + the bytes of every node on its path      */
 } ipcfp_slot_result;
 
 typedef struct ipcfp_bundle {

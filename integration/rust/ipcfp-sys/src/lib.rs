@@ -73,7 +73,8 @@ pub struct ipcfp_storage_result {
     pub spec_witness_offsets: *const u64, pub spec_witness_index: *const u32, pub ms_total: f32,
 }
 #[repr(C)]
-pub struct ipcfp_slot_result { pub n: u64, pub found: *const u8, pub raw_len: *const u32, pub values: *const u8, pub witness: ipcfp_witness, pub ms_total: f32 }
+pub struct ipcfp_slot_result { pub n: u64, pub found: *const u8, pub raw_len: *const u32, pub values: *const u8, pub witness: ipcfp_witness, pub ms_total: f32, pub ms_lookup: f32,
+                                pub lookup_nodes: u64, pub lookup_bytes: u64 }
 #[repr(C)]
 pub struct ipcfp_bundle { pub storage: *mut ipcfp_storage_result, pub n_event_results: u64, pub events: *mut *mut ipcfp_event_result, pub witness: ipcfp_witness }
 

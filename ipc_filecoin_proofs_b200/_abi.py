@@ -147,6 +147,9 @@ class SlotResultC(C.Structure):
         ("values", C.c_void_p),
         ("witness", Witness),
         ("ms_total", C.c_float),
+        ("ms_lookup", C.c_float),
+        ("lookup_nodes", C.c_uint64),
+        ("lookup_bytes", C.c_uint64),
     ]
 
 
@@ -327,12 +330,15 @@ class SlotResultPy:
     values: np.ndarray   # (n, 32)
     witness: WitnessPy
     ms_total: float = 0.0
+    ms_lookup: float = 0.0
+    lookup_nodes: int = 0
+    lookup_bytes: int = 0
 
 
 def slot_result_from_c(r):
     n = int(r.n)
     return SlotResultPy(_arr(r.found, n, np.uint8), _arr(r.raw_len, n, np.uint32), _arr(r.values, n * 32, np.uint8).reshape(n, 32),
-                        witness_from_c(r.witness), float(r.ms_total))
+                        witness_from_c(r.witness), float(r.ms_total), float(r.ms_lookup), int(r.lookup_nodes), int(r.lookup_bytes))
 
 
 @dataclass

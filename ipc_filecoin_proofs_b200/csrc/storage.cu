@@ -38,6 +38,7 @@ struct SlotArgs {
     uint8_t* found; uint32_t* raw_len; uint8_t* values;
     uint32_t* wbits;
     unsigned long long* err;
+    unsigned long long* stats;   // [0] HAMT nodes decoded, [1] their bytes
 };
 __global__ void __launch_bounds__(64) k_read_slots(SlotArgs a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,7 +46,10 @@ __global__ void __launch_bounds__(64) k_read_slots(SlotArgs a) {
     Recorder rec{nullptr, 0, a.wbits, false};
     SlotValue sv;
     Fail f{0, 0};
-    if (!read_storage_slot(a.store, rec, a.root_cid, a.slots + 32 * t, sv, f)) { report_error(a.err, ST_STORAGE, t, f.code, f.detail); return; }
+    const bool ok = read_storage_slot(a.store, rec, a.root_cid, a.slots + 32 * t, sv, f);
+    atomicAdd(a.stats, (unsigned long long)rec.hamt_nodes);
+    atomicAdd(a.stats + 1, (unsigned long long)rec.hamt_bytes);
+    if (!ok) { report_error(a.err, ST_STORAGE, t, f.code, f.detail); return; }
     a.found[t] = sv.found;
     a.raw_len[t] = sv.raw_len;
     for (int i = 0; i < 32; i++) a.values[32 * t + i] = sv.v32[i];
@@ -86,11 +90,15 @@ ipcfp_slot_result* read_storage_slots(Store* s, const uint8_t* root, const uint8
     if (k) IPCFP_CUDA(cudaMemcpyAsync(d_in.p + 64, slots, 32 * k, cudaMemcpyHostToDevice, st));
     SlotArgs a;
     a.store = s->view; a.root_cid = d_in.p; a.slots = d_in.p + 64; a.n = k; a.found = d_found.p; a.raw_len = d_len.p; a.values = d_vals.p;
-    a.wbits = wbits.p; a.err = dw;
+    a.wbits = wbits.p; a.err = dw; a.stats = dw + 4;
+    IPCFP_CUDA(cudaMemsetAsync(dw + 4, 0, 16, st));
+    IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
     if (k) { k_read_slots<<<div_up(k, 64), 64, 0, st>>>(a); IPCFP_LAUNCH_CHECK(); }
-    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
+    IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
+    IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 6 * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_storage_error(hw[0]);
+    const uint64_t stat_nodes = hw[4], stat_bytes = hw[5];
     std::unique_ptr<SlotResultBox> box(new SlotResultBox());
     memset(&box->r, 0, sizeof box->r);
     box->found = PinnedArray(s->pool, k + 8);
@@ -109,6 +117,10 @@ ipcfp_slot_result* read_storage_slots(Store* s, const uint8_t* root, const uint8
     float ms;
     IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
     box->r.ms_total = ms;
+    IPCFP_CUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+    box->r.ms_lookup = ms;
+    box->r.lookup_nodes = stat_nodes;
+    box->r.lookup_bytes = stat_bytes + 32 * k;
     return &box.release()->r;
 }
 void slot_result_free(ipcfp_slot_result* r) { delete reinterpret_cast<SlotResultBox*>(r); }

@@ -18,6 +18,7 @@ struct Recorder {
     uint32_t n;
     uint32_t* wbits;
     bool overflow;
+    uint32_t hamt_nodes = 0, hamt_bytes = 0;   // HAMT nodes decoded through this recorder and their bytes (measurement: K5's algorithmic bytes)
     __device__ void note(uint32_t blk) {
         witness_mark(wbits, blk);
         if (!list) return;
@@ -52,6 +53,7 @@ __device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_
     for (;;) {
         uint32_t len;
         const uint8_t* p = store_block(s, (uint32_t)blk, len);
+        rec.hamt_nodes++; rec.hamt_bytes += len;
         Rd r(p, len);
         bool depth_ok = consumed + bw <= 256;
         uint32_t idx = depth_ok ? hash_bits(h, consumed, bw) : 0;
