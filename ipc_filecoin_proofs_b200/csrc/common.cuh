@@ -33,24 +33,39 @@ void note_launch();  // counts kernel launches (ipcfp_kernel_launch_count)
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
+// Process-wide cache of large device buffers (store.cu): a caller that re-ingests per request creates and destroys a store every
+// time, and cudaMalloc / cudaFree of a GB-sized arena are slow, device-synchronising calls. A buffer goes back only after the
+// stream that used it has drained (Store::~Store synchronises first).
+void* dev_pool_take(size_t bytes, size_t* cap_out);
+void dev_pool_give(void* p, size_t cap);
+
 // RAII device buffer
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    size_t pool_cap = 0;   // > 0: the memory belongs to the device pool (alloc_pooled)
     DevBuf() {}
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_cap(o.pool_cap) { o.p = nullptr; o.n = 0; o.pool_cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; pool_cap = o.pool_cap; o.p = nullptr; o.n = 0; o.pool_cap = 0; } return *this; }
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
         n = count;
         if (count) IPCFP_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
     }
+    void alloc_pooled(size_t count) {
+        release();
+        n = count;
+        if (count) p = (T*)dev_pool_take(count * sizeof(T), &pool_cap);
+    }
     void ensure(size_t count) { if (count > n) alloc(count); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) { if (pool_cap) dev_pool_give(p, pool_cap); else cudaFree(p); }
+        p = nullptr; n = 0; pool_cap = 0;
+    }
     size_t bytes() const { return n * sizeof(T); }
 };
 

@@ -145,6 +145,14 @@ __global__ void __launch_bounds__(128, (CH * NSLOT <= 256 ? 6 : 3)) k_pass1_ring
     if ((threadIdx.x & 31) == 0 && nodes) { atomicAdd(a.stats, (unsigned long long)nodes); atomicAdd(a.stats + 1, (unsigned long long)bytes); }
 }
 
+// exec.get(i) for every matching receipt against the GLOBAL execution order length (sharded calls: the order spans shards)
+__global__ void k_check_exec(const uint32_t* __restrict__ match_rel, uint64_t n_match, uint64_t lo, const unsigned long long* __restrict__ n_exec,
+                             unsigned long long* err) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_match) return;
+    const uint64_t i = lo + match_rel[t];
+    if (i >= *n_exec) report_error(err, ST_PASS2, i, 0 /* DC_MISSING_EXEC, ranked before every other code at the same receipt */, 0);
+}
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_match) return;
@@ -391,6 +399,7 @@ static void throw_device_error(uint64_t key) {
     switch (code) {
         case DC_MISSING: st = IPCFP_ERR_MISSING_BLOCK; what = "missing block"; break;
         case DC_DECODE: st = IPCFP_ERR_DECODE; what = "decode error"; break;
+        case 0:
         case DC_MISSING_EXEC: st = IPCFP_ERR_MISSING_EXEC; what = "Missing message at index"; break;
         case DC_UNSUPPORTED: st = IPCFP_ERR_UNSUPPORTED; what = "unsupported input (frontier overflow)"; break;
         default: st = IPCFP_ERR_DECODE; what = "error"; break;
@@ -700,6 +709,13 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         throw_global(xch->g_tx, xch->g_err, false);
     }
     wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
+    if (xch) {
+        // agree on the slices with the peers (H0: one small all-gather the host waits for) and put the whole execution-order
+        // exchange on the exchange stream BEFORE pass 1 is launched, so that it runs underneath pass 1 from its first cycle
+        xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
+        if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
+        xch->start_exchange(exec_raw.p, s->ev[9]);
+    }
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
     if (sharded) IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));   // execution order is resolved across ranks by the caller
@@ -763,13 +779,6 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     exclusive_scan_u32(cnt.p, pbase.p, N, (uint64_t*)(dw + 7), scratch.p, st);
     exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
     publish_words(s, 0, 16);
-    if (xch) {
-        // pass 1 is running: agree on the slices with the peers (H0, one small all-gather the host waits for) and put the whole
-        // execution-order exchange on the exchange stream, underneath pass 1
-        xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
-        if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
-        xch->start_exchange(exec_raw.p, s->ev[9]);
-    }
     IPCFP_CUDA(cudaStreamSynchronize(st));
     note_errors(hw);
     uint64_t n_exec = hw[3];
@@ -783,14 +792,20 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     AsyncBuf<ipcfp_event_proof> d_proofs(n_proofs + 1, st);
     AsyncBuf<uint8_t> d_blob(n_bytes + 16, st);
     uint32_t* any_skip_dev = misc.p + 2;
-    if (xch) xch->positions_for(st, match_rel.p, M, n_exec_dev);   // global n_exec for pass 2's exec.get(i) check; raw positions of the matches
     if (M) {
         Pass2Args p2;
         p2.store = s->view; p2.store_dev = s->view_dev.p; p2.m_dev = d_matcher; p2.m = mh; p2.events_roots = td.events_roots.p; p2.lo = lo; p2.match_rel = match_rel.p; p2.n_match = M;
         p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
         p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
-        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = xch ? 2 : (sharded ? 0 : 1);
+        p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = sharded ? 0 : 1;
         k_pass2<<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
+    }
+    if (xch) {
+        // pass 2 did not wait for the cross-shard exchange; now that both are done: the global n_exec, the raw positions of this rank's
+        // matches, and exec.get(i) of events/generator.rs:244-246 for every match — it PRECEDES r_amt.get(i) in the reference, so at the
+        // same receipt it outranks whatever pass 2 reported (code 0 sorts first in the error word)
+        xch->positions_for(st, match_rel.p, M, n_exec_dev);
+        if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw); IPCFP_LAUNCH_CHECK(); }
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
     wbuild.finish_enqueue(wbits.p);

@@ -185,8 +185,8 @@ struct Pass2Args {
     ipcfp_event_proof* proofs;
     uint8_t* blob;
     uint32_t* any_skip;            // set when a matching receipt is absent from the receipts AMT
-    uint32_t resolve_msg;          // 1: exec.get(i) check + message CID from exec_cids; 0: neither (shard, execution order resolved by the
-                                   // caller afterwards); 2: the check against the GLOBAL n_exec only (in-library cross-shard protocol)
+    uint32_t resolve_msg;          // 1: exec.get(i) check + message CID from exec_cids; 0: neither (shard: the execution order spans shards and
+                                   // is resolved afterwards — by the caller, or by the in-library protocol with k_check_exec)
 };
 
 // One thread per matching receipt (events/generator.rs:242-301): exec.get(i), r_amt.get(i) with path

@@ -79,6 +79,49 @@ void PinnedPool::give(void* p, size_t cap) {
     free_list.push_back({p, cap});
 }
 
+// ------------------------------------------------------------------------------------------ device buffer pool
+struct DevPoolEntry { int device; void* p; size_t cap; };
+static std::mutex g_dp_mu;
+static std::vector<DevPoolEntry> g_dp;
+static const size_t DEV_POOL_MAX_ENTRIES = 24;
+void* dev_pool_take(size_t bytes, size_t* cap_out) {
+    int dev = 0;
+    IPCFP_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> g(g_dp_mu);
+        size_t best = SIZE_MAX, bi = SIZE_MAX;
+        for (size_t i = 0; i < g_dp.size(); i++)
+            if (g_dp[i].device == dev && g_dp[i].cap >= bytes && g_dp[i].cap < best) { best = g_dp[i].cap; bi = i; }
+        if (bi != SIZE_MAX && best <= bytes + bytes / 2 + (1u << 20)) {
+            void* p = g_dp[bi].p;
+            *cap_out = g_dp[bi].cap;
+            g_dp.erase(g_dp.begin() + (long)bi);
+            return p;
+        }
+    }
+    size_t cap = bytes + bytes / 16 + 4096;        // a little head-room so that the next, slightly larger store still fits
+    void* p = nullptr;
+    IPCFP_CUDA(cudaMalloc(&p, cap));
+    *cap_out = cap;
+    return p;
+}
+void dev_pool_give(void* p, size_t cap) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return; }
+    void* evict = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_dp_mu);
+        g_dp.push_back(DevPoolEntry{dev, p, cap});
+        if (g_dp.size() > DEV_POOL_MAX_ENTRIES) {   // drop the smallest: the big ones are the expensive ones to get back
+            size_t si = 0;
+            for (size_t i = 1; i < g_dp.size(); i++) if (g_dp[i].cap < g_dp[si].cap) si = i;
+            evict = g_dp[si].p;
+            g_dp.erase(g_dp.begin() + (long)si);
+        }
+    }
+    if (evict) cudaFree(evict);
+}
+
 // mapped counter blocks (host_words) are recycled per device across stores: cudaHostAlloc / cudaFreeHost are
 // slow, synchronising calls and a caller that re-ingests per request creates and destroys a store every time
 static std::mutex g_hw_mu;
@@ -106,6 +149,8 @@ static void host_words_give(int device, PinnedBuf<uint64_t>& b) {
 
 Store::~Store() {
     cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);     // nothing of this store is in flight when its buffers go back to the pools
+    if (stream2) cudaStreamSynchronize(stream2);
     host_words_give(device, host_words);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -219,7 +264,7 @@ static bool parse_prefix(const uint8_t* p, uint64_t key[4]) {
 }
 
 static void upload_view(Store* s) {
-    if (!s->view_dev.p) s->view_dev.alloc(1);
+    if (!s->view_dev.p) s->view_dev.alloc_pooled(1);
     IPCFP_CUDA(cudaMemcpyAsync(s->view_dev.p, &s->view, sizeof(StoreView), cudaMemcpyHostToDevice, s->stream));
 }
 static void fill_view(Store* s) {
@@ -266,7 +311,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     IPCFP_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) IPCFP_CUDA(cudaEventCreate(&e));
     cudaStream_t st = s->stream;
-    s->dev_words.alloc(64);
+    s->dev_words.alloc_pooled(64);
     host_words_take(device, s->host_words, 512);
     {
         cudaMemPool_t mp;
@@ -275,16 +320,18 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     IPCFP_CUDA(cudaMemsetAsync(s->dev_words.p, 0, 64 * 8, st));
 
     // device allocations
-    s->arena.alloc(blob_size + 48 + 512);   // + room for whole aligned chunks around the last block (pass-1 staging copies CH-aligned chunks)
-    s->offsets.alloc(n + 1);
-    s->lengths.alloc(n + 1);
-    s->digests.alloc(n + 1);
-    s->cls.alloc(n + 1);
-    s->recs.alloc(n + 1);
+    // (from the process-wide device pool: a store created right after one of similar size was destroyed allocates nothing)
+    s->arena.alloc_pooled(blob_size + 48 + 512);   // + room for whole aligned chunks around the last block (pass-1 staging copies CH-aligned chunks)
+    s->offsets.alloc_pooled(n + 1);
+    s->lengths.alloc_pooled(n + 1);
+    s->digests.alloc_pooled(n + 1);
+    s->cls.alloc_pooled(n + 1);
+    s->recs.alloc_pooled(n + 1);
     uint64_t slots = 64;
     while (slots < 2 * n) slots <<= 1;
-    s->table.alloc(slots);
-    DevBuf<uint8_t> cids_dev(n * 38 + 16);
+    s->table.alloc_pooled(slots);
+    DevBuf<uint8_t> cids_dev;
+    cids_dev.alloc_pooled(n * 38 + 16);
 
     // H2D. The CID array goes first so the index build overlaps the (much larger) blob copy.
     cudaStream_t st2;
@@ -296,13 +343,36 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
         IPCFP_CUDA(cudaMemcpyAsync(s->lengths.p, lengths, n * 4, cudaMemcpyHostToDevice, st));
     }
     IPCFP_CUDA(cudaMemsetAsync(s->arena.p, 0, 16, st2));
-    IPCFP_CUDA(cudaMemsetAsync(s->arena.p + 16 + blob_size, 0, 32, st2));
-    if (blob_size) IPCFP_CUDA(cudaMemcpyAsync(s->arena.p + 16, blob, blob_size, cudaMemcpyHostToDevice, st2));
+    IPCFP_CUDA(cudaMemsetAsync(s->arena.p + 16 + blob_size, 0, 32 + 512, st2));
     IPCFP_CUDA(cudaMemsetAsync(s->table.p, 0, slots * 8, st));
 
-    // validate offsets / lengths on the host (metadata only)
-    for (uint64_t i = 0; i < n; i++)
+    // validate offsets / lengths on the host (metadata only); blocks laid out in index order (the usual case) let the blob travel in
+    // CHUNKS whose blocks are Blake2b-checked while the next chunk is still on the wire
+    bool monotonic = true;
+    for (uint64_t i = 0; i < n; i++) {
         if (offsets[i] > blob_size || (uint64_t)lengths[i] > blob_size - offsets[i]) throw Error(IPCFP_ERR_INVALID_ARG, "block out of blob bounds", i);
+        if (i && offsets[i] < offsets[i - 1] + lengths[i - 1]) monotonic = false;
+    }
+    const bool verify = (flags & IPCFP_STORE_VERIFY_CIDS) && n;
+    struct Chunk { uint64_t b0, b1, byte0, byte1; };
+    std::vector<Chunk> chunks;
+    const uint64_t CHUNK_BYTES = 64ull << 20;
+    if (monotonic && verify && blob_size > 2 * CHUNK_BYTES) {
+        uint64_t b0 = 0, byte0 = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const uint64_t end = offsets[i] + lengths[i];
+            if (end - byte0 >= CHUNK_BYTES && i + 1 < n) { chunks.push_back(Chunk{b0, i + 1, byte0, offsets[i + 1]}); b0 = i + 1; byte0 = offsets[i + 1]; }
+        }
+        chunks.push_back(Chunk{b0, n, byte0, blob_size});
+    } else chunks.push_back(Chunk{0, n, 0, blob_size});
+    std::vector<cudaEvent_t> chunk_ev(chunks.size(), nullptr);
+    struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } evg{chunk_ev};
+    for (size_t k = 0; k < chunks.size(); k++) {
+        const Chunk& c = chunks[k];
+        if (c.byte1 > c.byte0) IPCFP_CUDA(cudaMemcpyAsync(s->arena.p + 16 + c.byte0, blob + c.byte0, c.byte1 - c.byte0, cudaMemcpyHostToDevice, st2));
+        IPCFP_CUDA(cudaEventCreateWithFlags(&chunk_ev[k], cudaEventDisableTiming));
+        IPCFP_CUDA(cudaEventRecord(chunk_ev[k], st2));
+    }
 
     // CID classes: the first CID's prefix is class 0; anything else is discovered by the kernel
     if (n) { std::array<uint8_t, 6> p0; memcpy(p0.data(), cids, 6); s->class_prefix.push_back(p0); }
@@ -334,11 +404,8 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
         k_build_index<<<div_up(n, 256), 256, 0, st>>>((uint32_t)n, s->digests.p, s->cls.p, (unsigned long long*)s->table.p, s->table.n - 1);
         IPCFP_LAUNCH_CHECK();
     }
-    // blob must have landed before anything reads blocks
-    IPCFP_CUDA(cudaEventRecord(s->ev[7], st2));
-    IPCFP_CUDA(cudaStreamWaitEvent(st, s->ev[7], 0));
-
-    if ((flags & IPCFP_STORE_VERIFY_CIDS) && n) {
+    upload_view(s.get());
+    if (verify) {
         uint32_t mask = 0;
         for (size_t c = 0; c < s->class_prefix.size(); c++) {
             uint64_t key[4];
@@ -347,14 +414,19 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
         }
         unsigned long long* bad = s->dev_words.p + 2;
         IPCFP_CUDA(cudaMemsetAsync(bad, 0xff, 8, st));
-        k_verify_cids<<<div_up(n, 128), 128, 0, st>>>(s->view, 0, (uint32_t)n, mask, bad);
-        IPCFP_LAUNCH_CHECK();
-        IPCFP_CUDA(cudaMemcpyAsync(s->host_words.p, bad, 8, cudaMemcpyDeviceToHost, st));
+        for (size_t k = 0; k < chunks.size(); k++) {   // chunk k is checked while chunk k+1 is on the wire
+            const Chunk& c = chunks[k];
+            IPCFP_CUDA(cudaStreamWaitEvent(st, chunk_ev[k], 0));
+            if (c.b1 > c.b0) { k_verify_cids<<<div_up(c.b1 - c.b0, 128), 128, 0, st>>>(s->view, (uint32_t)c.b0, (uint32_t)c.b1, mask, bad); IPCFP_LAUNCH_CHECK(); }
+        }
+        publish_words(s.get(), 2, 1);
         IPCFP_CUDA(cudaStreamSynchronize(st));
-        s->first_bad = s->host_words.p[0];  // reported by the C ABI as IPCFP_ERR_CID_MISMATCH (handle stays valid)
+        s->first_bad = s->host_words.p[2];  // reported by the C ABI as IPCFP_ERR_CID_MISMATCH (handle stays valid)
+    } else {
+        // the blob must have landed before anything reads blocks
+        IPCFP_CUDA(cudaStreamWaitEvent(st, chunk_ev.back(), 0));
+        IPCFP_CUDA(cudaStreamSynchronize(st));
     }
-    upload_view(s.get());
-    IPCFP_CUDA(cudaStreamSynchronize(st));
     return s.release();
 }
 
