@@ -288,7 +288,11 @@ Comm* comm_init(const uint8_t* id128, uint32_t world, uint32_t rank, int device)
     NcclApi* n = nccl_api();
     std::unique_ptr<Comm> c(new Comm());
     c->device = device; c->world = world; c->rank = rank;
-    IPCFP_CUDA(cudaStreamCreateWithFlags(&c->sx, cudaStreamNonBlocking));
+    {   // the exchange must not queue behind the full-grid scan kernels of the engine stream
+        int lo_p = 0, hi_p = 0;
+        IPCFP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        IPCFP_CUDA(cudaStreamCreateWithPriority(&c->sx, cudaStreamNonBlocking, hi_p));
+    }
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));

@@ -58,7 +58,7 @@ __device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_
         bool depth_ok = consumed + bw <= 256;
         uint32_t idx = depth_ok ? hash_bits(h, consumed, bw) : 0;
         HamtHit hit;
-        hamt_node_lookup(r, vkind, idx, key, keylen, hit);
+        if (!hamt_node_lookup_fast(p, len, vkind, idx, key, keylen, hit)) hamt_node_lookup(r, vkind, idx, key, keylen, hit);   // strict decoder: exact errors
         if (r.err) SFAIL(DC_DECODE, r.err);
         if (!depth_ok) SFAIL(DC_DECODE, CE_HAMT);  // HashBits::next → MaxDepth
         consumed += bw;

@@ -347,7 +347,7 @@ static int fuzz_receipt_nodes(uint64_t iters) {
 
 // ---- sixth property: one HAMT node (state tree / EVM storage, csrc/storage.cu hamt_get's unit) vs the oracle --------------
 static int fuzz_hamt_nodes(uint64_t iters) {
-    uint64_t okn = 0, bad = 0, hits = 0, links = 0;
+    uint64_t okn = 0, bad = 0, hits = 0, links = 0, fast_ok = 0;
     std::vector<uint8_t> buf;
     for (uint64_t it = 0; it < iters; it++) {
         int vkind = (int)(rnd() % 2);
@@ -419,6 +419,18 @@ static int fuzz_hamt_nodes(uint64_t iters) {
         Rd r(p, len);
         HamtHit hit;
         hamt_node_lookup(r, vkind, idx, key.data(), (uint32_t)key.size(), hit);
+        {   // the fast node decoder may only accept what the strict one accepts, with the same hit
+            HamtHit fh;
+            if (hamt_node_lookup_fast(p, len, vkind, idx, key.data(), (uint32_t)key.size(), fh)) {
+                fast_ok++;
+                if (r.err || fh.kind != hit.kind || (fh.kind == 1 && fh.val_off != hit.val_off) || (fh.kind == 2 && fh.link_off != hit.link_off)) {
+                    fprintf(stderr, "HAMT FAST/STRICT MISMATCH at iteration %llu: strict err %u kind %d, fast kind %d\nnode:", (unsigned long long)it, r.err, hit.kind, fh.kind);
+                    for (size_t k = 0; k < node.size(); k++) fprintf(stderr, " %02x", node[k]);
+                    fprintf(stderr, "\n");
+                    return 1;
+                }
+            } else if (!r.err && nmut == 0 && bf.size() <= 32) { fprintf(stderr, "HAMT FAST: a generated, unmutated node was not taken (iteration %llu)\n", (unsigned long long)it); return 1; }
+        }
         int32_t okind = 0;
         uint8_t oout[4096];
         uint64_t olen = 0;
@@ -450,8 +462,8 @@ static int fuzz_hamt_nodes(uint64_t iters) {
         }
         if (r.err) bad++; else { okn++; hits += hit.kind == 1; links += hit.kind == 2; }
     }
-    printf("ok: %llu HAMT nodes agree with the oracle (%llu decoded: %llu values found, %llu links; %llu decode errors)\n", (unsigned long long)iters,
-           (unsigned long long)okn, (unsigned long long)hits, (unsigned long long)links, (unsigned long long)bad);
+    printf("ok: %llu HAMT nodes agree with the oracle (%llu decoded: %llu values found, %llu links; %llu decode errors; %llu taken by the fast node decoder)\n", (unsigned long long)iters,
+           (unsigned long long)okn, (unsigned long long)hits, (unsigned long long)links, (unsigned long long)bad, (unsigned long long)fast_ok);
     return 0;
 }
 
