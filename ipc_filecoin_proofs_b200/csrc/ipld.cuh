@@ -430,28 +430,32 @@ __device__ __forceinline__ void hamt_node_lookup(Rd& r, int vkind, uint32_t idx,
 // same hit; anything else returns false and the caller runs the strict decoder, which also names the error.
 __device__ __forceinline__ bool skip_u8vec_fast(const uint8_t* p, uint32_t len, uint32_t& pos) {
     if (pos >= len) return false;
-    uint64_t w = load_u64_any(p + pos);
-    uint32_t b = (uint32_t)w & 0xff, n;
+    uint64_t w0 = load_u64_any(p + pos);
+    uint32_t b = (uint32_t)w0 & 0xff, n;
     if (b >= 0x80 && b < 0x98) { n = b - 0x80; pos += 1; }
-    else if (b == 0x98) { n = (uint32_t)(w >> 8) & 0xff; if (n < 24 || len - pos < 2) return false; pos += 2; }
+    else if (b == 0x98) { n = (uint32_t)(w0 >> 8) & 0xff; if (n < 24 || len - pos < 2) return false; pos += 2; }
     else return false;                                   // longer arrays: strict path
     if (n > len - pos) return false;                     // (rd_array's bound: every element takes ≥ 1 byte)
+    // One loop body for every lane (lanes of a warp walk different nodes: data-dependent branches would serialise them): a 16-byte
+    // register window [base, base + 16) refilled every 8 bytes; an element is 1 byte (uint < 24) or `18 xx` with xx ≥ 24 (minimal
+    // encoding); four two-byte elements in a row — the common run for random byte values — go in one step. Reads may run up to 24
+    // bytes past `len` (every block buffer is padded by ≥ 32); a value that ends past the block is rejected after the loop.
+    uint32_t base = pos;
+    uint64_t w1 = load_u64_any(p + pos + 8);
+    w0 = load_u64_any(p + pos);
     while (n) {
-        if (pos >= len) return false;
-        w = load_u64_any(p + pos);
-        const uint32_t avail = len - pos < 8 ? len - pos : 8;
-        uint32_t used = 0;
-        while (n && used < avail) {
-            const uint32_t e = (uint32_t)(w >> (8 * used)) & 0xff;
-            if (e < 0x18) used += 1;                     // uint 0..23
-            else if (e == 0x18) {                        // uint8 argument: must be ≥ 24 (minimal encoding), ≤ 255 by construction
-                if (used + 1 >= avail) { if (used == 0) return false; break; }   // the argument byte is in the next window
-                if (((uint32_t)(w >> (8 * used + 8)) & 0xff) < 24) return false;
-                used += 2;
-            } else return false;                         // > 255, another major type, …: strict path decides
-            n--;
-        }
-        pos += used;
+        uint32_t off = pos - base;
+        if (off >= 8) { base = pos; w0 = load_u64_any(p + pos); w1 = load_u64_any(p + pos + 8); off = 0; }
+        const uint32_t sh = 8 * off;                     // 0..56
+        const uint64_t x = (w0 >> sh) | ((w1 << 1) << (63 - sh));
+        const bool four = n >= 4 && (x & 0x00ff00ff00ff00ffull) == 0x0018001800180018ull &&
+                          ((((x >> 8) & 0x00ff00ff00ff00ffull) + 0x00e800e800e800e8ull) & 0x0100010001000100ull) == 0x0100010001000100ull;
+        const uint32_t e = (uint32_t)x & 0xff, e2 = (uint32_t)(x >> 8) & 0xff;
+        if (four) { pos += 8; n -= 4; }
+        else if (e < 0x18) { pos += 1; n -= 1; }
+        else if (e == 0x18 && e2 >= 24) { pos += 2; n -= 1; }
+        else return false;                               // > 255, non-minimal, another major type: the strict path decides
+        if (pos > len) return false;
     }
     return true;
 }

@@ -7,6 +7,7 @@
 //   reference src/proofs/common/decode.rs:17-124      get_actor_state, parse_evm_state, HeaderLite
 //   fvm_ipld_hamt 0.10 [UPSTREAM]                     Hamt::get with SHA-256 key hashing (K2b)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -18,9 +19,12 @@
 
 namespace ipcfp {
 
-__global__ void __launch_bounds__(64) k_storage_proofs(StorageArgs a) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
+// One WARP per proof / lookup, lane 0 walks. The walk is a chain of data-dependent branches over a different node in every lane:
+// 32 lookups in one warp execute one lane at a time (measured: 1.5 active lanes per instruction, 0.85 ms for ANY batch up to 64 k
+// lookups), so a lookup per warp costs the same issue slots, finishes 32 lookups' worth earlier and spreads a small batch over all SMs.
+__global__ void __launch_bounds__(128) k_storage_proofs(StorageArgs a) {
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= a.n || (threadIdx.x & 31)) return;
     Recorder rec{a.rec_list + t * REC_CAP, 0, a.wbits, false};
     ipcfp_storage_proof q;
     Fail f{0, 0};
@@ -39,11 +43,17 @@ struct SlotArgs {
     uint32_t* wbits;
     unsigned long long* err;
     unsigned long long* stats;   // [0] HAMT nodes decoded, [1] their bytes
+    uint32_t strict_only;
+    uint32_t per_warp;
 };
-__global__ void __launch_bounds__(64) k_read_slots(SlotArgs a) {
+// a.per_warp: one lookup per warp (small and medium batches: latency); else one per thread with the strict decoder, whose uniform
+// head-by-head loop keeps the lanes of a warp closer together (large batches: 60 M lookups/s at 64 k, measured)
+__global__ void __launch_bounds__(128) k_read_slots(SlotArgs a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.per_warp) { if (threadIdx.x & 31) return; t >>= 5; }
     if (t >= a.n) return;
     Recorder rec{nullptr, 0, a.wbits, false};
+    rec.strict_only = a.strict_only != 0;
     SlotValue sv;
     Fail f{0, 0};
     const bool ok = read_storage_slot(a.store, rec, a.root_cid, a.slots + 32 * t, sv, f);
@@ -90,10 +100,12 @@ ipcfp_slot_result* read_storage_slots(Store* s, const uint8_t* root, const uint8
     if (k) IPCFP_CUDA(cudaMemcpyAsync(d_in.p + 64, slots, 32 * k, cudaMemcpyHostToDevice, st));
     SlotArgs a;
     a.store = s->view; a.root_cid = d_in.p; a.slots = d_in.p + 64; a.n = k; a.found = d_found.p; a.raw_len = d_len.p; a.values = d_vals.p;
-    a.wbits = wbits.p; a.err = dw; a.stats = dw + 4;
+    a.wbits = wbits.p; a.err = dw; a.stats = dw + 4; a.strict_only = getenv("IPCFP_HAMT_STRICT") ? 1 : 0;
     IPCFP_CUDA(cudaMemsetAsync(dw + 4, 0, 16, st));
     IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
-    if (k) { k_read_slots<<<div_up(k, 64), 64, 0, st>>>(a); IPCFP_LAUNCH_CHECK(); }
+    a.per_warp = k <= 16384 ? 1 : 0;
+    if (!a.per_warp) a.strict_only = 1;
+    if (k) { k_read_slots<<<div_up(a.per_warp ? k * 32 : k, 128), 128, 0, st>>>(a); IPCFP_LAUNCH_CHECK(); }
     IPCFP_CUDA(cudaEventRecord(s->ev[3], st));
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 6 * 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
@@ -152,7 +164,7 @@ ipcfp_storage_result* generate_storage_proofs(Store* s, const ipcfp_tipset_desc*
     StorageArgs a;
     a.store = s->view; a.child_cid = d_in.p; a.state_root_json = d_in.p + 64; a.specs = d_specs.p; a.n = n; a.out = d_out.p;
     a.rec_list = d_rec.p; a.rec_n = d_recn.p; a.wbits = wbits.p; a.err = dw;
-    if (n) { k_storage_proofs<<<div_up(n, 64), 64, 0, st>>>(a); IPCFP_LAUNCH_CHECK(); }
+    if (n) { k_storage_proofs<<<div_up(n * 32, 128), 128, 0, st>>>(a); IPCFP_LAUNCH_CHECK(); }
     IPCFP_CUDA(cudaMemcpyAsync(hw, dw, 8, cudaMemcpyDeviceToHost, st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (hw[0] != IPCFP_NO_ERROR) throw_storage_error(hw[0]);

@@ -19,6 +19,7 @@ struct Recorder {
     uint32_t* wbits;
     bool overflow;
     uint32_t hamt_nodes = 0, hamt_bytes = 0;   // HAMT nodes decoded through this recorder and their bytes (measurement: K5's algorithmic bytes)
+    bool strict_only = false;                  // A/B switch (IPCFP_HAMT_STRICT=1): skip the fast node decoder
     __device__ void note(uint32_t blk) {
         witness_mark(wbits, blk);
         if (!list) return;
@@ -58,7 +59,7 @@ __device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_
         bool depth_ok = consumed + bw <= 256;
         uint32_t idx = depth_ok ? hash_bits(h, consumed, bw) : 0;
         HamtHit hit;
-        if (!hamt_node_lookup_fast(p, len, vkind, idx, key, keylen, hit)) hamt_node_lookup(r, vkind, idx, key, keylen, hit);   // strict decoder: exact errors
+        if (rec.strict_only || !hamt_node_lookup_fast(p, len, vkind, idx, key, keylen, hit)) hamt_node_lookup(r, vkind, idx, key, keylen, hit);   // strict decoder: exact errors
         if (r.err) SFAIL(DC_DECODE, r.err);
         if (!depth_ok) SFAIL(DC_DECODE, CE_HAMT);  // HashBits::next → MaxDepth
         consumed += bw;

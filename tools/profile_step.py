@@ -86,10 +86,14 @@ def main():
         st3 = api.BlockStore.from_tipset(ts3, verify_cids=args.verify)
         keys = [ts3.storage_entry(k)[0] for k in range(args.storage)]
         slots = np.frombuffer(b"".join(api.compute_mapping_slots(keys, [0] * len(keys))), dtype=np.uint8)
-        for k in range(3):
-            t = time.time()
-            r = st3.read_storage_slots(ts3.storage_root, slots)
-            log(f"storage lookups x{args.storage}: wall {1e3 * (time.time() - t):.2f} ms device {r.ms_total:.3f} ms found {int(r.found.sum())}")
+        for mode in ("fast", "strict", "fast"):
+            os.environ.pop("IPCFP_HAMT_STRICT", None)
+            if mode == "strict":
+                os.environ["IPCFP_HAMT_STRICT"] = "1"
+            for k in range(4):
+                t = time.time()
+                r = st3.read_storage_slots(ts3.storage_root, slots)
+                print(f"STORAGE {mode} x{args.storage}: wall {1e3 * (time.time() - t):.2f} ms device {r.ms_total:.3f} ms lookup kernel {r.ms_lookup:.4f} ms nodes {r.lookup_nodes} found {int(r.found.sum())}", flush=True)
     log("done")
 
 
