@@ -709,6 +709,14 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         throw_global(xch->g_tx, xch->g_err, false);
     }
     wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
+    if (xch) {
+        // The witness gather is on its way: agree on the slices with the peers (H0: one small all-gather the host waits for) and put the
+        // whole execution-order exchange on the exchange stream — a HIGH-PRIORITY stream, so that its blocks are scheduled ahead of
+        // pass 1's (launched right below) instead of behind them, and the exchange is over long before pass 2 is
+        xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
+        if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
+        xch->start_exchange(exec_raw.p, s->ev[9]);
+    }
     AsyncBuf<uint32_t> exec_idx(nraw + 32, st), keep_bits((nraw + 31) / 32 + 8, st);
     unsigned long long* n_exec_dev = dw + 3;
     if (sharded) IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));   // execution order is resolved across ranks by the caller
@@ -772,14 +780,6 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     exclusive_scan_u32(cnt.p, pbase.p, N, (uint64_t*)(dw + 7), scratch.p, st);
     exclusive_scan_u32(nby.p, bbase.p, N, (uint64_t*)(dw + 12), scratch.p, st);
     publish_words(s, 0, 16);
-    if (xch) {
-        // pass 1 is on its way: agree on the slices with the peers (H0: one small all-gather the host waits for) and put the whole
-        // execution-order exchange on the exchange stream — a HIGH-PRIORITY stream, so its blocks are scheduled between pass 1's
-        // instead of behind them
-        xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
-        if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
-        xch->start_exchange(exec_raw.p, s->ev[9]);
-    }
     IPCFP_CUDA(cudaStreamSynchronize(st));
     note_errors(hw);
     uint64_t n_exec = hw[3];
