@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 CSRC      := ipc_filecoin_proofs_b200/csrc
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr
-CU_SRCS   := $(CSRC)/store.cu $(CSRC)/events.cu $(CSRC)/storage.cu $(CSRC)/witness.cu $(CSRC)/prims.cu $(CSRC)/parallel.cu $(CSRC)/capi.cu
+CU_SRCS   := $(CSRC)/store.cu $(CSRC)/events.cu $(CSRC)/storage.cu $(CSRC)/witness.cu $(CSRC)/prims.cu $(CSRC)/parallel.cu $(CSRC)/verify.cu $(CSRC)/capi.cu
 CU_OBJS   := $(CU_SRCS:.cu=.o)
 CU_HDRS   := $(wildcard $(CSRC)/*.cuh) include/ipcfp.h
 LIB       := ipc_filecoin_proofs_b200/libipcfp.so

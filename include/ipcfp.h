@@ -276,6 +276,21 @@ ipcfp_status ipcfp_generate_proof_bundle(ipcfp_store* s, const ipcfp_tipset_desc
 void ipcfp_bundle_free(ipcfp_bundle* b);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched verifiers (src/proofs/events/verifier.rs:51-290, src/proofs/storage/verifier.rs:24-170): replay every proof against a
+ * store that holds ONLY the witness blocks. Create that store with IPCFP_STORE_VERIFY_CIDS: this is the Blake2b-256 check of every
+ * witness block the reference's load_witness_store leaves out (`put_keyed`, events/verifier.rs:79-89). results[i] = the reference's
+ * Ok(bool) for proof i; an Err of the reference (missing witness block, decode failure, TxMeta mismatch) fails the call, index =
+ * the first proof that meets it. Trust anchors (:124-144) are host-side policy closures and stay with the caller; `filter` (may
+ * be NULL) plays check_event: the event must satisfy matches_log of that spec (events/generator.rs:38-40).
+ * t: parent_cids / n_parents / epochs / child_cid (events), child_cid / child_parent_state_root (storage) — the fields every
+ * proof of one bundle shares (EventProof.parent_tipset_cids …, StorageProof.parent_state_root).
+ * ------------------------------------------------------------------------------------------ */
+ipcfp_status ipcfp_verify_event_proofs(ipcfp_store* witness_store, const ipcfp_tipset_desc* t, const ipcfp_event_proof* proofs, uint64_t n_proofs,
+                                       const uint8_t* data_blob, uint64_t data_blob_size, const ipcfp_event_spec* filter, uint8_t* results);
+ipcfp_status ipcfp_verify_storage_proofs(ipcfp_store* witness_store, const ipcfp_tipset_desc* t, const ipcfp_storage_proof* proofs, uint64_t n_proofs,
+                                         uint8_t* results);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU; the caller owns the communicator — torch.distributed / NCCL).
  * Receipts shard by index range; each rank scans its shard, then the per-shard witness CID sets
  * are all-gathered and merged (the BTreeSet union of src/proofs/common/witness.rs:24-40).

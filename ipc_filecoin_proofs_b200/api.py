@@ -42,6 +42,7 @@ EXPORTS = [
     "ipcfp_tipset_upload", "ipcfp_tipset_free", "ipcfp_generate_event_proof_resident", "ipcfp_generate_event_proof_shard_resident",
     "ipcfp_store_stream", "ipcfp_exec_bucketize", "ipcfp_exec_dedup", "ipcfp_exec_fetch",
     "ipcfp_comm_unique_id", "ipcfp_comm_init", "ipcfp_comm_destroy", "ipcfp_generate_event_proof_sharded",
+    "ipcfp_verify_event_proofs", "ipcfp_verify_storage_proofs",
 ]
 
 
@@ -125,6 +126,10 @@ def lib():
         L.ipcfp_generate_event_proof_sharded.restype = C.c_int32
         L.ipcfp_generate_event_proof_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(A.EventSpec), C.c_void_p, C.c_uint32,
                                                          C.POINTER(C.POINTER(A.EventResultC))]
+        L.ipcfp_verify_event_proofs.restype = C.c_int32
+        L.ipcfp_verify_event_proofs.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ipcfp_verify_storage_proofs.restype = C.c_int32
+        L.ipcfp_verify_storage_proofs.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.c_void_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -297,6 +302,38 @@ class BlockStore:
             self.close()
         except Exception:
             pass
+
+
+def verify_event_proofs(witness, ts, result, filter_spec=None, device=0):
+    """verify_event_proof (events/verifier.rs:51-74) batched on the GPU: the witness (WitnessPy) becomes a store with every block
+    Blake2b-checked against its CID, then every proof of `result` (EventResultPy) is replayed. → list of bools."""
+    store = BlockStore(witness.cids, witness.offsets, witness.lengths, witness.blob, device, verify_cids=True)
+    try:
+        d, keep = A.make_tipset_desc(ts)
+        n = len(result.proofs)
+        res = np.zeros(max(n, 1), dtype=np.uint8)
+        raw = np.ascontiguousarray(result.raw_proofs)
+        blob = np.ascontiguousarray(result.data_blob)
+        fs = filter_spec.as_c() if isinstance(filter_spec, EventProofSpec) else filter_spec
+        _check(lib().ipcfp_verify_event_proofs(store._h, C.byref(d), raw.ctypes.data if n else None, n, blob.ctypes.data if blob.size else None, blob.size,
+                                               C.addressof(fs) if fs is not None else None, res.ctypes.data))
+        return [bool(x) for x in res[:n]]
+    finally:
+        store.close()
+
+
+def verify_storage_proofs(witness, ts, result, device=0):
+    """verify_storage_proof (storage/verifier.rs:24-63) batched on the GPU over a CID-checked witness store."""
+    store = BlockStore(witness.cids, witness.offsets, witness.lengths, witness.blob, device, verify_cids=True)
+    try:
+        d, keep = A.make_tipset_desc(ts)
+        n = len(result.proofs)
+        res = np.zeros(max(n, 1), dtype=np.uint8)
+        raw = np.ascontiguousarray(result.raw_proofs)
+        _check(lib().ipcfp_verify_storage_proofs(store._h, C.byref(d), raw.ctypes.data if n else None, n, res.ctypes.data))
+        return [bool(x) for x in res[:n]]
+    finally:
+        store.close()
 
 
 def _hash_batch(fn, messages, device=0):

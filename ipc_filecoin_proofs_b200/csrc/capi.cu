@@ -317,6 +317,20 @@ void ipcfp_bundle_free(ipcfp_bundle* b) {
     delete box;
 }
 
+ipcfp_status ipcfp_verify_event_proofs(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_event_proof* proofs, uint64_t n, const uint8_t* blob,
+                                       uint64_t blob_size, const ipcfp_event_spec* filter, uint8_t* results) {
+    return guard([&] {
+        if (!s) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        verify_event_proofs(reinterpret_cast<Store*>(s), t, proofs, n, blob, blob_size, filter, results);
+    });
+}
+ipcfp_status ipcfp_verify_storage_proofs(ipcfp_store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_proof* proofs, uint64_t n, uint8_t* results) {
+    return guard([&] {
+        if (!s) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");
+        verify_storage_proofs(reinterpret_cast<Store*>(s), t, proofs, n, results);
+    });
+}
+
 ipcfp_status ipcfp_comm_unique_id(uint8_t id[IPCFP_COMM_ID_BYTES]) {
     return guard([&] {
         if (!id) throw Error(IPCFP_ERR_INVALID_ARG, "null argument");

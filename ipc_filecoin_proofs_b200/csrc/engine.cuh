@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "store.cuh"
+#include "rawcid.cuh"
 
 namespace ipcfp {
 
@@ -88,7 +89,6 @@ struct TipsetDev {
 
 struct ScopedStatus;  // capi.cu
 struct Comm;          // parallel.cu: NCCL communicator pair + exchange scratch of one rank
-struct RawCid;
 
 void set_last_error(const std::string& msg, uint64_t index);
 ipcfp_status status_from_devcode(uint32_t code);
@@ -108,8 +108,19 @@ void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint3
 
 // events.cu
 void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td);
+// the reconstructed execution order of a tipset on the device (reconstruct_execution_order, events/utils.rs:16-30): exec[i] = exec_raw[exec_idx[i]]
+struct ExecOrderOut {
+    uint64_t n_exec = 0, nraw = 0;
+    AsyncBuf<RawCid> exec_raw;
+    AsyncBuf<uint32_t> exec_idx;
+};
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
-                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank, Comm* comm = nullptr);
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank, Comm* comm = nullptr,
+                                         ExecOrderOut* exo = nullptr);
+// verify.cu — batched verifiers over a witness store
+void verify_event_proofs(Store* s, const ipcfp_tipset_desc* t, const ipcfp_event_proof* proofs, uint64_t n, const uint8_t* data_blob, uint64_t blob_size,
+                         const ipcfp_event_spec* filter, uint8_t* results);
+void verify_storage_proofs(Store* s, const ipcfp_tipset_desc* t, const ipcfp_storage_proof* proofs, uint64_t n, uint8_t* results);
 void event_result_free(ipcfp_event_result* r);
 void witness_cids_to_device(const ipcfp_event_result* r, void* dev_ptr, uint64_t cap, uint64_t* n);
 void merge_witness_cids(int device, const void* gathered, const uint64_t* counts, uint32_t world, uint64_t cap, void* out, uint64_t cap_out,

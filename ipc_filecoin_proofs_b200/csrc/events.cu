@@ -169,6 +169,7 @@ struct SetupArgs {
     const uint8_t* child_cid;      // 38
     const uint8_t* receipts_root;  // 38
     uint32_t skip_tx;
+    uint32_t skip_receipts;        // execution-order-only mode: the receipts root is not part of the call
     uint32_t* wbits;
     unsigned long long* err;
     unsigned long long* txerr;     // message-AMT fault word (tx_err_key)
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
     }
     if (t != 0) return;
     *a.f_count = 2 * P;
+    if (a.skip_receipts) return;
     // Amtv0::<MessageReceipt>::load(&receipts_root, &rec_receipts) (events/generator.rs:195-196)
     int32_t rb = store_lookup(s, a.receipts_root);
     if (rb < 0) { report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_MISSING, 0); return; }
@@ -464,7 +466,7 @@ void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
 }
 
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*/, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
-                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/, Comm* comm) {
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/, Comm* comm, ExecOrderOut* exo) {
     s->use();
     cudaStream_t st = s->stream;
     if (!spec || !spec->event_signature || !spec->topic_1) throw Error(IPCFP_ERR_INVALID_ARG, "event spec has null fields");
@@ -554,7 +556,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     sa.store = s->view; sa.n_parents = td.n_parents;
     sa.parent_cids = d_cids; sa.txmeta_cids = d_cids + 38ull * td.n_parents;
     sa.child_cid = d_cids + 76ull * td.n_parents; sa.receipts_root = sa.child_cid + 38;
-    sa.skip_tx = skip_tx; sa.wbits = wbits.p; sa.err = dw; sa.txerr = dw + 15;
+    sa.skip_tx = skip_tx; sa.skip_receipts = exo ? 1 : 0; sa.wbits = wbits.p; sa.err = dw; sa.txerr = dw + 15;
     sa.receipts_root_blk = misc.p; sa.missing_base = misc.p + 1; sa.amt_height = misc.p + 64;
     sa.f_blk = fA_blk.p; sa.f_meta = fA_meta.p; sa.f_base = fA_base.p; sa.f_count = dw + 1;
     sa.amt_count = amt_count.p;
@@ -684,7 +686,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
-    wbuild.snapshot(wbits.p);
+    if (!exo) wbuild.snapshot(wbits.p);
     publish_words(s, 0, 18);   // error word, frontier counters (dw[1]/dw[2]), witness counts (dw[8], dw[9]), dense-walk flag (dw[14]), gather split (dw[16], dw[17])
     IPCFP_CUDA(cudaStreamSynchronize(st));
     if (dense_used && hw[14] != 0) {   // the AMTs are not what the dense walk assumes: redo the walk with the general kernels
@@ -692,7 +694,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         k_setup<<<1, 256, 0, st>>>(sa); IPCFP_LAUNCH_CHECK();   // re-seed the frontier (same outputs as before)
         run_general();
         IPCFP_CUDA(cudaEventRecord(s->ev[9], st));
-        wbuild.snapshot(wbits.p);
+        if (!exo) wbuild.snapshot(wbits.p);
         publish_words(s, 0, 18);
         IPCFP_CUDA(cudaStreamSynchronize(st));
     }
@@ -708,7 +710,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         xch->agree_slices(pend_tx, pend_err, 0);
         throw_global(xch->g_tx, xch->g_err, false);
     }
-    wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
+    if (!exo) wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
     if (xch) {
         // The witness gather is on its way: agree on the slices with the peers (H0: one small all-gather the host waits for) and put the
         // whole execution-order exchange on the exchange stream — a HIGH-PRIORITY stream, so that its blocks are scheduled ahead of
@@ -731,6 +733,16 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         bitmap_to_indices(keep_bits.p, nraw, exec_idx.p, (uint64_t*)n_exec_dev, wp2.p, scratch.p, st);
     } else IPCFP_CUDA(cudaMemsetAsync(n_exec_dev, 0, 8, st));
     IPCFP_CUDA(cudaEventRecord(s->ev[2], st));
+    if (exo) {
+        // execution-order-only mode (the batched verifier, verify.cu): hand the order over and stop before the scan
+        publish_words(s, 3, 1);
+        IPCFP_CUDA(cudaStreamSynchronize(st));
+        exo->n_exec = hw[3];
+        exo->nraw = nraw;
+        exo->exec_raw = std::move(exec_raw);
+        exo->exec_idx = std::move(exec_idx);
+        return nullptr;
+    }
 
     // ---- PASS 1
     AsyncBuf<uint32_t> match_bits((N + 31) / 32 + 8, st), cnt(N + 8, st), nby(N + 8, st);

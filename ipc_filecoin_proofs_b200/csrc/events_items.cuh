@@ -130,7 +130,7 @@ struct Pass1Args {
 
 // ------------------------------------------------------------------------------------------ receipts AMT
 // Amtv0<Receipt>::get(i) with recording (events/generator.rs:249). 1 = Some, 0 = None, <0 = -DevCode.
-__device__ int receipts_get(const StoreView& s, uint32_t root_blk, uint64_t i, uint32_t* wbits, uint32_t* detail) {
+static __device__ int receipts_get(const StoreView& s, uint32_t root_blk, uint64_t i, uint32_t* wbits, uint32_t* detail) {
     uint32_t len;
     const uint8_t* p = store_block(s, root_blk, len);
     Rd r(p, len);

@@ -21,7 +21,7 @@ struct Recorder {
     uint32_t hamt_nodes = 0, hamt_bytes = 0;   // HAMT nodes decoded through this recorder and their bytes (measurement: K5's algorithmic bytes)
     bool strict_only = false;                  // A/B switch (IPCFP_HAMT_STRICT=1): skip the fast node decoder
     __device__ void note(uint32_t blk) {
-        witness_mark(wbits, blk);
+        if (wbits) witness_mark(wbits, blk);   // (the verifiers walk without recording)
         if (!list) return;
         for (uint32_t i = 0; i < n; i++) if (list[i] == blk) return;
         if (n < REC_CAP) list[n++] = blk; else overflow = true;
@@ -41,7 +41,7 @@ __device__ __forceinline__ int32_t rec_get(const StoreView& s, Recorder& rec, co
 struct ValueRef { uint32_t blk; uint32_t off; };
 
 // Hamt::get. key: keylen bytes. Returns true on success; found/val describe the outcome.
-__device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_cid, uint64_t bw64, int vkind, const uint8_t* key,
+static __device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_cid, uint64_t bw64, int vkind, const uint8_t* key,
                          uint32_t keylen, bool& found, ValueRef& val, Fail& f) {
     found = false;
     if (bw64 < 1 || bw64 > 8) SFAIL(DC_DECODE, CE_HAMT);
@@ -71,7 +71,7 @@ __device__ bool hamt_get(const StoreView& s, Recorder& rec, const uint8_t* root_
 }
 
 // struct SmallMap { v: Vec<(ByteBuf, ByteBuf)> } from a CBOR map; remembers the first pair whose key == slot
-__device__ void dec_small_map(Rd& r, const uint8_t* slot, bool search, bool& hit, uint32_t& voff, uint32_t& vlen) {
+static __device__ void dec_small_map(Rd& r, const uint8_t* slot, bool search, bool& hit, uint32_t& voff, uint32_t& vlen) {
     uint32_t n = rd_map(r);
     bool have = false;
     for (uint32_t i = 0; i < n && !r.err; i++) {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void value_from_bytes(const uint8_t* p, uint32_t len,
     uint32_t take = len < 32 ? len : 32;
     for (uint32_t i = 0; i < take; i++) out.v32[32 - take + i] = p[len - take + i];
 }
-__device__ void value_from_u8vec(const uint8_t* p, uint32_t blen, uint32_t off, SlotValue& out) {
+static __device__ void value_from_u8vec(const uint8_t* p, uint32_t blen, uint32_t off, SlotValue& out) {
     Rd r(p, blen);
     r.pos = off;
     uint32_t n = rd_array(r);
@@ -120,7 +120,7 @@ __device__ void value_from_u8vec(const uint8_t* p, uint32_t blen, uint32_t off, 
 }
 
 // read_storage_slot (storage/decode.rs:36-97)
-__device__ bool read_storage_slot(const StoreView& s, Recorder& rec, const uint8_t* root_cid, const uint8_t* slot, SlotValue& out, Fail& f) {
+static __device__ bool read_storage_slot(const StoreView& s, Recorder& rec, const uint8_t* root_cid, const uint8_t* slot, SlotValue& out, Fail& f) {
     out.found = false; out.raw_len = 0;
     for (int i = 0; i < 32; i++) out.v32[i] = 0;
     int32_t blk = rec_get(s, rec, root_cid);
@@ -199,7 +199,7 @@ do_hamt:
 }
 
 // HeaderLite (common/decode.rs:100-124): returns offset of parent_state_root CID bytes
-__device__ uint32_t header_parent_state_root(Rd& r) {
+static __device__ uint32_t header_parent_state_root(Rd& r) {
     rd_array_exact(r, 16);
     for (int i = 0; i < 5; i++) rd_skip_any(r);
     uint32_t np = rd_array(r);
@@ -218,7 +218,7 @@ __device__ uint32_t header_parent_state_root(Rd& r) {
     return psr;
 }
 // EvmStateV6 / V5 (common/decode.rs:48-97): offset of contract_state CID bytes
-__device__ bool try_evm_state(const uint8_t* p, uint32_t len, int fields, uint32_t& cs_off) {
+static __device__ bool try_evm_state(const uint8_t* p, uint32_t len, int fields, uint32_t& cs_off) {
     Rd r(p, len);
     rd_array_exact(r, (uint32_t)fields);
     (void)rd_cid(r);
@@ -246,7 +246,7 @@ struct StorageArgs {
     unsigned long long* err;
 };
 
-__device__ bool storage_proof_one(const StorageArgs& a, uint64_t t, Recorder& rec, ipcfp_storage_proof& q, Fail& f) {
+static __device__ bool storage_proof_one(const StorageArgs& a, uint64_t t, Recorder& rec, ipcfp_storage_proof& q, Fail& f) {
     const StoreView& s = a.store;
     // extract_and_verify_parent_state (storage/generator.rs:72-103); the header recorder is dropped (:80-83)
     int32_t hb = store_lookup(s, a.child_cid);

@@ -420,3 +420,93 @@ def test_full_size_config3(api, oracle_mod, synth_mod):
     for i, k in enumerate(ks):
         v = ts.storage_entry(k)[1]
         assert bytes(got.values[i][32 - len(v):]) == v
+
+
+# ------------------------------------------------------------------ GPU-batched verifiers (events/verifier.rs, storage/verifier.rs)
+def _verify_both(api, oracle_mod, w, ts, r, spec):
+    """GPU verdicts == oracle verdicts, or both raise the same status."""
+    try:
+        exp = oracle_mod.verify_event_proofs(w, ts, r, spec)
+    except A.IpcfpError as e:
+        with pytest.raises(A.IpcfpError) as ei:
+            api.verify_event_proofs(w, ts, r, spec)
+        assert ei.value.status == e.status, (ei.value.status, ei.value.msg, e.status, e.msg)
+        return None
+    got = api.verify_event_proofs(w, ts, r, spec)
+    assert got == exp
+    return got
+
+
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_verify_event_proofs_gpu(api, oracle_mod, synth_mod, cfg):
+    ts = synth_mod.Tipset(synth_mod.config_params(cfg))
+    spec = spec_of(ts)
+    r = api.BlockStore.from_tipset(ts, verify_cids=True).generate_event_proof(ts, spec)
+    assert len(r.proofs) > 0
+    assert all(_verify_both(api, oracle_mod, r.witness, ts, r, spec))
+    assert all(_verify_both(api, oracle_mod, r.witness, ts, r, None))
+    # a different predicate: nothing satisfies it
+    other = A.make_event_spec("SomethingElse(uint256)", ts.topic1, None)
+    assert not any(_verify_both(api, oracle_mod, r.witness, ts, r, other))
+    w = r.witness
+    # drop-one-block minimality probe: same verdicts / same failure as the restated verifier, and every block is needed
+    step = 1 if cfg == 1 else max(1, w.n_blocks // 60)
+    for drop in range(0, w.n_blocks, step):
+        keep = [i for i in range(w.n_blocks) if i != drop]
+        w2 = A.WitnessPy(w.cids[keep], w.offsets[keep], w.lengths[keep], w.blob)
+        got = _verify_both(api, oracle_mod, w2, ts, r, spec)
+        if cfg == 1:
+            assert got is None or not all(got), f"witness block {drop} is not needed"
+    # tampered claims: event index, exec index, a topic byte, the message CID, the emitter
+    import copy
+    for off, what in ((8, "event_index"), (0, "exec_index"), (16, "emitter"), (48, "message_cid")):
+        r2 = copy.copy(r)
+        r2.raw_proofs = r.raw_proofs.copy()
+        r2.raw_proofs[off] ^= 1
+        got = _verify_both(api, oracle_mod, w, ts, r2, spec)
+        assert got is None or not got[0], what
+    r3 = copy.copy(r)
+    r3.data_blob = r.data_blob.copy()
+    r3.data_blob[5] ^= 0x80
+    got = _verify_both(api, oracle_mod, w, ts, r3, spec)
+    assert not got[0]
+    # a witness block whose bytes do not hash to its CID never gets in (the check the reference's load_witness_store lacks)
+    blob = w.blob.copy()
+    blob[int(w.offsets[3]) + 1] ^= 0x10
+    with pytest.raises(A.IpcfpError) as ei:
+        api.verify_event_proofs(A.WitnessPy(w.cids, w.offsets, w.lengths, blob), ts, r, spec)
+    assert ei.value.status == A.ERR_CID_MISMATCH and ei.value.index == 3
+
+
+def test_verify_storage_proofs_gpu(api, oracle_mod, ts3_small):
+    ts = ts3_small
+    n = int(ts.params.hamt_entries)
+    slots = [oracle_mod.compute_mapping_slot(ts.storage_entry(k)[0], 0) for k in (0, 5, n)] + [oracle_mod.compute_mapping_slot(ts.storage_absent_key(3), 0)]
+    specs = [(a, s) for a in (1001, 1002, 1003, 1004, 1005, 1006) for s in slots]
+    r = api.BlockStore.from_tipset(ts, verify_cids=True).generate_storage_proofs(ts, specs)
+    exp = oracle_mod.verify_storage_proofs(r.witness, ts, r)
+    got = api.verify_storage_proofs(r.witness, ts, r)
+    assert got == exp and all(got)
+    # tampered claims: value, storage root, actor state CID
+    import copy
+    sz = r.raw_proofs.size // len(r.proofs)
+    for off in (8 + 38 + 38 + 32 + 31, 8 + 38 + 5, 8 + 5):
+        r2 = copy.copy(r)
+        r2.raw_proofs = r.raw_proofs.copy()
+        r2.raw_proofs[sz * 2 + off] ^= 1
+        exp2 = oracle_mod.verify_storage_proofs(r.witness, ts, r2)
+        got2 = api.verify_storage_proofs(r.witness, ts, r2)
+        assert got2 == exp2 and not got2[2] and got2[0]
+    # a dropped witness block: same verdicts or the same failure
+    w = r.witness
+    for drop in range(0, w.n_blocks, max(1, w.n_blocks // 40)):
+        keep = [i for i in range(w.n_blocks) if i != drop]
+        w2 = A.WitnessPy(w.cids[keep], w.offsets[keep], w.lengths[keep], w.blob)
+        try:
+            e2 = oracle_mod.verify_storage_proofs(w2, ts, r)
+        except A.IpcfpError as e:
+            with pytest.raises(A.IpcfpError) as ei:
+                api.verify_storage_proofs(w2, ts, r)
+            assert ei.value.status == e.status
+            continue
+        assert api.verify_storage_proofs(w2, ts, r) == e2
