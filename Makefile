@@ -14,8 +14,11 @@ all: $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
 $(CSRC)/%.o: $(CSRC)/%.cu $(CU_HDRS)
 	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c $< -o $@
 
-$(LIB): $(CU_OBJS)
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) -lcudart -ldl
+$(CSRC)/bundle_json.o: $(CSRC)/bundle_json.cpp include/ipcfp.h
+	$(CXX) -O2 -std=c++17 -fPIC -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(CSRC)/bundle_json.o
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) $(CSRC)/bundle_json.o -lcudart -ldl
 
 synth/libipcfp_synth.so: synth/synth.cpp synth/synth.h synth/cpu_crypto.h
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ synth/synth.cpp
@@ -24,6 +27,6 @@ oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h synth/cpu_crypto.h includ
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ oracle/oracle.cpp
 
 clean:
-	rm -f $(CU_OBJS) $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
+	rm -f $(CU_OBJS) $(CSRC)/bundle_json.o $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
 
 .PHONY: all clean

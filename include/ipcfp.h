@@ -276,6 +276,17 @@ ipcfp_status ipcfp_generate_proof_bundle(ipcfp_store* s, const ipcfp_tipset_desc
 void ipcfp_bundle_free(ipcfp_bundle* b);
 
 /* ------------------------------------------------------------------------------------------
+ * Wire format (src/proofs/common/bundle.rs:10-45, src/proofs/events/bundle.rs:5-30, src/proofs/storage/bundle.rs:5-14): the JSON
+ * `serde_json::to_string` gives for UnifiedProofBundle / EventProofBundle — struct field order, compact, CIDs as "bafy2bzace…"
+ * strings, "0x" lower-case hex, base64 block data (ProofBlock.cid as the byte array cid 0.11's Serialize emits). t supplies the
+ * fields every proof of the bundle shares (epochs, parent tipset CIDs, child block CID, parent state root). Host-side rendering:
+ * no device is needed. *out is a NUL-terminated string of *out_len bytes, released with ipcfp_json_free.
+ * ------------------------------------------------------------------------------------------ */
+ipcfp_status ipcfp_bundle_to_json(const ipcfp_bundle* b, const ipcfp_tipset_desc* t, char** out, uint64_t* out_len);
+ipcfp_status ipcfp_event_result_to_json(const ipcfp_event_result* r, const ipcfp_tipset_desc* t, char** out, uint64_t* out_len);
+void ipcfp_json_free(char* p);
+
+/* ------------------------------------------------------------------------------------------
  * Batched verifiers (src/proofs/events/verifier.rs:51-290, src/proofs/storage/verifier.rs:24-170): replay every proof against a
  * store that holds ONLY the witness blocks. Create that store with IPCFP_STORE_VERIFY_CIDS: this is the Blake2b-256 check of every
  * witness block the reference's load_witness_store leaves out (`put_keyed`, events/verifier.rs:79-89). results[i] = the reference's

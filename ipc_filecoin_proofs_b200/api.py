@@ -42,7 +42,7 @@ EXPORTS = [
     "ipcfp_tipset_upload", "ipcfp_tipset_free", "ipcfp_generate_event_proof_resident", "ipcfp_generate_event_proof_shard_resident",
     "ipcfp_store_stream", "ipcfp_exec_bucketize", "ipcfp_exec_dedup", "ipcfp_exec_fetch",
     "ipcfp_comm_unique_id", "ipcfp_comm_init", "ipcfp_comm_destroy", "ipcfp_generate_event_proof_sharded",
-    "ipcfp_verify_event_proofs", "ipcfp_verify_storage_proofs",
+    "ipcfp_verify_event_proofs", "ipcfp_verify_storage_proofs", "ipcfp_bundle_to_json", "ipcfp_event_result_to_json", "ipcfp_json_free",
 ]
 
 
@@ -130,6 +130,11 @@ def lib():
         L.ipcfp_verify_event_proofs.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.ipcfp_verify_storage_proofs.restype = C.c_int32
         L.ipcfp_verify_storage_proofs.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.c_void_p, C.c_uint64, C.c_void_p]
+        for name in ("ipcfp_bundle_to_json", "ipcfp_event_result_to_json"):
+            f = getattr(L, name)
+            f.restype = C.c_int32
+            f.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.ipcfp_json_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -302,6 +307,26 @@ class BlockStore:
             self.close()
         except Exception:
             pass
+
+
+def _to_json(fn, obj_ptr, ts):
+    d, keep = A.make_tipset_desc(ts)
+    out, n = C.c_void_p(), C.c_uint64()
+    _check(getattr(lib(), fn)(obj_ptr, C.byref(d), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out.value, n.value).decode()
+    finally:
+        lib().ipcfp_json_free(out)
+
+
+def bundle_to_json(bundle_c_ptr, ts):
+    """`serde_json::to_string(&UnifiedProofBundle)` of an ipcfp_bundle (POINTER(BundleC) or its address)."""
+    return _to_json("ipcfp_bundle_to_json", C.cast(bundle_c_ptr, C.c_void_p), ts)
+
+
+def event_result_to_json(result_c_ptr, ts):
+    """`serde_json::to_string(&EventProofBundle)` of an ipcfp_event_result."""
+    return _to_json("ipcfp_event_result_to_json", C.cast(result_c_ptr, C.c_void_p), ts)
 
 
 def verify_event_proofs(witness, ts, result, filter_spec=None, device=0):

@@ -82,3 +82,39 @@ def test_unified_bundle_json_round_trip(oracle_mod, ts3_small):
     # the other CID spellings consumers use are accepted on input
     alt = [{"cid": {"/": J.cid_to_string(bytes(x["cid"]))}, "data": x["data"]} for x in doc["blocks"][:3]]
     assert np.array_equal(J.witness_from_blocks(alt).cids, w.cids[:3])
+
+
+def test_c_abi_json_equals_python_rendering(oracle_mod, ts3_small, ts1):
+    """ipcfp_bundle_to_json / ipcfp_event_result_to_json (csrc/bundle_json.cpp: host-side rendering behind the C ABI, no device) give
+    byte for byte what bundle_json.py gives — on PODs produced by the oracle, which have exactly the layout the engine returns."""
+    import ctypes as C
+    from ipc_filecoin_proofs_b200 import api
+    ts = ts3_small
+    slot = oracle_mod.compute_mapping_slot((b"calib-subnet-1" + bytes(32))[:32], 0)
+    sspecs = [(1001, slot), (1003, slot)]
+    especs = [A.make_event_spec(ts.event_signature, ts.topic1, ts.actor_filter)]
+    OL = oracle_mod.lib()
+    ost = oracle_mod.Store.from_tipset(ts)
+    d, keep = A.make_tipset_desc(ts)
+    sarr = A.make_storage_specs(sspecs)
+    earr = (A.EventSpec * len(especs))(*especs)
+    out = C.POINTER(A.BundleC)()
+    assert OL.oracle_generate_proof_bundle(ost._h, C.byref(d), sarr, len(sspecs), earr, len(especs), C.byref(out)) == 0
+    try:
+        text = api.bundle_to_json(out, ts)
+        want = J.dumps(J.unified_bundle(ts, A.bundle_from_c(out.contents)))
+        assert text == want
+        assert json.loads(text)["storage_proofs"][0]["slot"] == "0x" + bytes(slot).hex()
+    finally:
+        OL.oracle_bundle_free(out)
+    # EventProofBundle of one result
+    spec = spec_of(ts1)
+    ost1 = oracle_mod.Store.from_tipset(ts1)
+    d1, keep1 = A.make_tipset_desc(ts1)
+    eo = C.POINTER(A.EventResultC)()
+    assert OL.oracle_generate_event_proof(ost1._h, C.byref(d1), C.byref(spec), 0, 1, C.byref(eo)) == 0
+    try:
+        text = api.event_result_to_json(eo, ts1)
+        assert text == J.dumps(J.event_bundle(ts1, A.event_result_from_c(eo.contents)))
+    finally:
+        OL.oracle_event_result_free(eo)
