@@ -317,3 +317,40 @@ def test_product_does_not_link_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/__init__.py", ""), f
+
+
+def test_oracle_vs_python_oracle_config4_shape(oracle_mod, synth_mod):
+    """The two independent oracle implementations on a config-4-SHAPED tipset at 100 k receipts (0.1 % match, events-AMT bit widths 3/5
+    mixed, duplicate messages, 5-level receipts AMT) — VERDICT r1: the cross-check used to stop at configs 1-2."""
+    from oracle import pyoracle as P
+    ts = synth_mod.Tipset(synth_mod.config_params(4, n_receipts=100_000))
+    r = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec_of(ts), threads=4)
+    pr = P.generate_event_proof(ts.as_dict(), ts, ts.event_signature, ts.topic1, ts.actor_filter)
+    assert pr["matching"] == r.matching.tolist() == ts.selected.tolist() and len(pr["matching"]) > 20
+    assert [bytes(c) for c in r.witness.cids] == pr["witness"]
+    assert [(p.exec_index, p.event_index, p.emitter, tuple(p.topics), p.data, p.message_cid) for p in r.proofs] == pr["proofs"]
+    assert r.n_exec == len(pr["exec_order"])
+
+
+def test_oracle_vs_python_oracle_full_size_hamt(oracle_mod, synth_mod):
+    """Both oracles on the FULL-SIZE storage tree of configs[2] (1 M slots): 300 lookups (present, absent, the six root shapes)."""
+    from oracle import pyoracle as P
+    ts = synth_mod.Tipset(synth_mod.config_params(3))
+    st = oracle_mod.Store.from_tipset(ts)
+    store = ts.as_dict()
+    rng = np.random.default_rng(11)
+    keys = [ts.storage_entry(int(k))[0] for k in rng.choice(1_000_000, size=270, replace=False)] + [ts.storage_absent_key(k) for k in range(30)]
+    slots = [oracle_mod.compute_mapping_slot(k, 0) for k in keys]
+    got = st.read_storage_slots(ts.storage_root, np.frombuffer(b"".join(slots), dtype=np.uint8))
+    rec = P.Recorder(store)
+    for i, s in enumerate(slots):
+        v = P.read_storage_slot(rec, bytes(ts.storage_root), s)
+        assert bool(got.found[i]) == (v is not None)
+        if v is not None:
+            assert bytes(got.values[i]) == bytes(32 - len(v)) + v if len(v) <= 32 else v[-32:]
+    assert sorted(rec.seen) == sorted(bytes(c) for c in got.witness.cids)
+    specs = [(a, slots[k]) for k, a in enumerate((1001, 1002, 1003, 1004, 1005, 1006))]
+    r = st.generate_storage_proofs(ts, specs)
+    for (a, s), p in zip(specs, r.proofs):
+        pp = P.generate_storage_proof(store, ts, a, s)
+        assert (p.actor_state_cid, p.storage_root, p.value) == (pp["actor_state_cid"], pp["storage_root"], pp["value"])
