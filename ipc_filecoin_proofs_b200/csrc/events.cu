@@ -769,7 +769,11 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
             kern<<<div_up(N, 128), 128, smem, st>>>(p1, (const uint8_t*)s->arena.p + s->arena.n);
         };
         auto is = [](const char* e, const char* v) { return e && !strcmp(e, v); };
-        if (is(stage_env, "128x4x1")) launch_stage(k_pass1_stage<128, 4, 1, 4, 3>, 4, StageGeom<128, 4, 1>::WARP_BYTES);
+        if (is(stage_env, "lean128x4x1")) launch_stage(k_pass1_stage<128, 4, 1, 4, 3, 1>, 4, StageGeom<128, 4, 1>::WARP_BYTES);
+        else if (is(stage_env, "lean128x4x1w2")) launch_stage(k_pass1_stage<128, 4, 1, 2, 6, 1>, 2, StageGeom<128, 4, 1>::WARP_BYTES);
+        else if (is(stage_env, "lean64x8x2")) launch_stage(k_pass1_stage<64, 8, 2, 4, 3, 1>, 4, StageGeom<64, 8, 2>::WARP_BYTES);
+        else if (is(stage_env, "lean128x4x2")) launch_stage(k_pass1_stage<128, 4, 2, 4, 3, 1>, 4, StageGeom<128, 4, 2>::WARP_BYTES);
+        else if (is(stage_env, "128x4x1")) launch_stage(k_pass1_stage<128, 4, 1, 4, 3>, 4, StageGeom<128, 4, 1>::WARP_BYTES);
         else if (is(stage_env, "128x4x1w2")) launch_stage(k_pass1_stage<128, 4, 1, 2, 6>, 2, StageGeom<128, 4, 1>::WARP_BYTES);
         else if (is(stage_env, "128x4x2")) launch_stage(k_pass1_stage<128, 4, 2, 4, 3>, 4, StageGeom<128, 4, 2>::WARP_BYTES);
         else if (is(stage_env, "64x8x2")) launch_stage(k_pass1_stage<64, 8, 2, 4, 3>, 4, StageGeom<64, 8, 2>::WARP_BYTES);

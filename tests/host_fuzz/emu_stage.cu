@@ -101,7 +101,7 @@ static std::vector<uint8_t> make_root(bool& wellformed_single) {
 }
 
 
-template <int CH, int NSLOT, int CPP>
+template <int CH, int NSLOT, int CPP, int LEAN = 0>
 static int run(uint64_t warps, uint64_t* taken_out, uint64_t* wf_out, uint64_t* slow_out) {
     using GEO = StageGeom<CH, NSLOT, CPP>;
     uint64_t taken_n = 0, wf = 0;
@@ -168,7 +168,7 @@ static int run(uint64_t warps, uint64_t* taken_out, uint64_t* wf_out, uint64_t* 
             for (uint32_t l = 0; l < 32; l++) { L[l].landed = L[l].front; alive |= L[l].state != 0; }
             if (!alive) break;
             fill();
-            for (uint32_t l = 0; l < 32; l++) L[l].step(m);
+            for (uint32_t l = 0; l < 32; l++) { if (LEAN) L[l].step_lean(m); else L[l].step(m); }
             g_stage_iters++;
             if (++guard > 100000) { fprintf(stderr, "STAGE <%d,%d,%d>: no progress (warp %llu)\n", CH, NSLOT, CPP, (unsigned long long)w); return 1; }
         }
@@ -216,7 +216,7 @@ int main(int argc, char** argv) {
     if (argc > 3) {   // canonical-shape statistics per geometry: iterations per warp and events that left the fast path
         g_canonical = true;
         auto one = [&](const char* name, int rc) { printf("  %s: %llu warp iterations, %llu events, %llu through the arena decoder\n", name, g_stage_iters, g_stage_events, g_stage_slow_events); g_stage_iters = g_stage_events = g_stage_slow_events = 0; return rc; };
-        if (one("128x4x1", run<128, 4, 1>(warps, &taken, &wf, &slow)) || one("64x4x2", run<64, 4, 2>(warps, &taken, &wf, &slow)) || one("64x8x2", run<64, 8, 2>(warps, &taken, &wf, &slow)) ||
+        if (one("lean128x4x1", run<128, 4, 1, 1>(warps, &taken, &wf, &slow)) || one("lean64x8x2", run<64, 8, 2, 1>(warps, &taken, &wf, &slow)) || one("128x4x1", run<128, 4, 1>(warps, &taken, &wf, &slow)) || one("64x4x2", run<64, 4, 2>(warps, &taken, &wf, &slow)) || one("64x8x2", run<64, 8, 2>(warps, &taken, &wf, &slow)) ||
             one("128x4x2", run<128, 4, 2>(warps, &taken, &wf, &slow)) || one("256x2x1", run<256, 2, 1>(warps, &taken, &wf, &slow)))
             return 1;
         g_canonical = false;
@@ -224,6 +224,11 @@ int main(int argc, char** argv) {
     if (run<128, 4, 1>(warps, &taken, &wf, &slow) || run<64, 4, 2>(warps, &taken, &wf, &slow) || run<64, 8, 2>(warps, &taken, &wf, &slow) || run<128, 4, 2>(warps, &taken, &wf, &slow) ||
         run<256, 2, 1>(warps, &taken, &wf, &slow))
         return 1;
+    {   // the lean decoder of pass 1's count mode
+        const unsigned long long e0 = g_stage_events, s0 = g_stage_slow_events;
+        if (run<128, 4, 1, 1>(warps, &taken, &wf, &slow) || run<64, 8, 2, 1>(warps, &taken, &wf, &slow) || run<128, 4, 2, 1>(warps, &taken, &wf, &slow) || run<64, 4, 2, 1>(warps, &taken, &wf, &slow)) return 1;
+        printf("ok: lean decoder: %llu events, %llu of them through the arena decoder\n", g_stage_events - e0, g_stage_slow_events - s0);
+    }
     printf("ok: staged pass 1 == arena pass 1 for 5 geometries x %llu warps: %llu nodes taken by the staged path, %llu well-formed single-node blocks (all taken); %llu events, %llu of them through the arena decoder; %llu warp iterations\n",
            (unsigned long long)warps, (unsigned long long)taken, (unsigned long long)wf, g_stage_events, g_stage_slow_events, g_stage_iters);
     return 0;
