@@ -31,6 +31,7 @@ namespace ipcfp {
 // One thread per receipt: resolve its events root CID, decode the root node of its events AMT,
 // test every StampedEvent. The common single-node AMT (≤ 2^bw events) never leaves this
 // function; taller AMTs fall through to the generic walker.
+template <int WINMODE = 0>
 __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
     uint64_t i = a.lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool matched = false;
@@ -62,7 +63,7 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
         amt_node_begin(r, bw, h);
         uint32_t nv = rd_array(r);
         WalkOut wo{0, 0, false};
-        node_events<WALK_COUNT>(r, p, h, nv, 0, a.m, wo, nullptr, a.tune);
+        node_events<WALK_COUNT, WINMODE>(r, p, h, nv, 0, a.m, wo, nullptr, a.tune);
         amt_node_finish(r, h, nv, height);
         if (r.err) report_error(a.err, ST_PASS1, i, DC_DECODE, r.err);
         else if (h.nl) {
@@ -86,6 +87,9 @@ __device__ __forceinline__ void pass1_body(const Pass1Args& a) {
 __global__ void __launch_bounds__(128, 6) k_pass1(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 8) k_pass1_occ8(Pass1Args a) { pass1_body(a); }
 __global__ void __launch_bounds__(128, 10) k_pass1_occ10(Pass1Args a) { pass1_body(a); }
+// windows through two 16-byte loads (2/3 of the L1 wavefronts of three 8-byte loads)
+__global__ void __launch_bounds__(128, 8) k_pass1_w16(Pass1Args a) { pass1_body<1>(a); }
+__global__ void __launch_bounds__(128, 6) k_pass1_w16_occ6(Pass1Args a) { pass1_body<1>(a); }
 
 // ---- EXPERIMENT (round 2): pass 1 through per-lane shared-memory rings, see pass1_ring.cuh. Same outputs as k_pass1;
 // a node the ring path cannot take (malformed head, links = taller AMT) is re-decoded by the arena path below.
@@ -783,6 +787,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         else if (is(ring_env, "128x2")) launch_ring(k_pass1_ring<128, 2>, 128 * (128 * 2 + 16));
         else if (is(ring_env, "128x4")) launch_ring(k_pass1_ring<128, 4>, 128 * (128 * 4 + 16));
         else if (is(ring_env, "256x2")) launch_ring(k_pass1_ring<256, 2>, 128 * (256 * 2 + 16));
+        else if (getenv("IPCFP_PASS1_W16") && atoi(getenv("IPCFP_PASS1_W16")) == 6) k_pass1_w16_occ6<<<div_up(N, 128), 128, 0, st>>>(p1);
+        else if (getenv("IPCFP_PASS1_W16")) k_pass1_w16<<<div_up(N, 128), 128, 0, st>>>(p1);
         else if (minb >= 10) k_pass1_occ10<<<div_up(N, 128), 128, 0, st>>>(p1);
         else if (minb >= 8) k_pass1_occ8<<<div_up(N, 128), 128, 0, st>>>(p1);
         else k_pass1<<<div_up(N, 128), 128, 0, st>>>(p1);

@@ -46,7 +46,7 @@ __device__ __forceinline__ void emit_proof(const uint8_t* p, const EvLog& ev, ui
 }
 
 // Decodes the values of one events-AMT node. Returns false on a decode error (r.err set).
-template <int MODE>
+template <int MODE, int WINMODE = 0>
 __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNodeHdr& h, uint32_t nv, uint64_t base, const Matcher& m,
                                             WalkOut& wo, EmitCtx* ec, uint32_t tune = 0) {
     for (uint32_t v = 0; v < nv && !r.err; v++) {
@@ -56,7 +56,7 @@ __device__ __forceinline__ void node_events(Rd& r, const uint8_t* p, const AmtNo
         if (!(tune & 2) && r.pos + ahead < r.n) prefetch_l2(r.p + r.pos + ahead);
         if ((tune & 1) && r.pos + 128 < r.n) prefetch_l1(r.p + r.pos + 128);  // experiment: next line into L1
         EvLog ev;
-        decode_stamped_event(r, ev);
+        decode_stamped_event<WINMODE>(r, ev);
         if (r.err) break;
         if (event_matches(p, ev, m)) {
             wo.any = true;

@@ -470,6 +470,18 @@ static int fuzz_hamt_nodes(uint64_t iters) {
 int main(int argc, char** argv) {
     uint64_t iters = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
     rng_state = argc > 2 ? strtoull(argv[2], nullptr, 10) : 0x1FC0FFEEull;
+    {   // the two window loaders give the same 16 bytes at every alignment
+        alignas(16) uint8_t buf[128];
+        for (int k = 0; k < 128; k++) buf[k] = (uint8_t)rnd();
+        for (int off = 16; off < 64; off++) {
+            uint64_t a0, a1, b0, b1;
+            win_load(buf + off, a0, a1);
+            win_load16(buf + off, b0, b1);
+            uint64_t e0, e1;
+            memcpy(&e0, buf + off, 8); memcpy(&e1, buf + off + 8, 8);
+            if (a0 != e0 || a1 != e1 || b0 != e0 || b1 != e1) { fprintf(stderr, "WINDOW LOADERS DISAGREE at offset %d\n", off); return 1; }
+        }
+    }
     uint64_t accepted = 0, rejected = 0, strict_ok = 0, oracle_checked = 0;
     std::vector<uint8_t> buf;
     for (uint64_t it = 0; it < iters; it++) {

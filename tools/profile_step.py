@@ -48,7 +48,7 @@ def main():
         import numpy as np
         ref = None
         for var in args.sweep.split(","):
-            for k in ("IPCFP_PASS1_STAGE", "IPCFP_PASS1_RING", "IPCFP_PASS1_MINB", "IPCFP_PASS1_TUNE"):
+            for k in ("IPCFP_PASS1_STAGE", "IPCFP_PASS1_RING", "IPCFP_PASS1_MINB", "IPCFP_PASS1_TUNE", "IPCFP_PASS1_W16"):
                 os.environ.pop(k, None)
             for kv in var.split("+"):
                 name, val = kv.split("=")
