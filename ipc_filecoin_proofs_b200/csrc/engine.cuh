@@ -142,6 +142,7 @@ struct ShardExchange {
     std::vector<uint64_t> nseg_all;
     uint64_t nraw = 0, max_nseg = 0, pos0 = 0, nseg = 0;
     bool peers_ok = true;
+    bool all_early = false;          // early H0: every shard promised its slice before its walk was over
     // X
     const RawCid* seg = nullptr;
     uint64_t cap = 0, nwords = 0;
@@ -152,14 +153,15 @@ struct ShardExchange {
     const uint32_t* match_rel_dev = nullptr;
     // H0 / H2 (global values, identical on every rank)
     uint64_t g_tx = ~0ull, g_err = ~0ull;
-    bool g_missing_base = false, g_overflow = false;
+    bool g_missing_base = false, g_overflow = false, g_stale = false;
     uint64_t M_max = 0, nw_max = 0, M_total = 0, proofs_total = 0;
     std::vector<uint64_t> nw_all;
     ShardExchange(Comm* comm, Store* store, uint64_t lo_, uint64_t hi_);
+    void agree_early(bool can_promise, uint64_t planned_nseg, uint64_t nraw_total);
     void agree_slices(uint64_t tx_key, uint64_t err_key, uint64_t nseg_);
     void start_exchange(const void* seg_dev, cudaEvent_t seg_ready);
     void positions_for(cudaStream_t st, const uint32_t* match_rel, uint64_t n_match, unsigned long long* n_exec_out);
-    void agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow);
+    void agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow, bool stale);
     void fetch_and_patch(cudaStream_t st, ipcfp_event_proof* proofs_dev, uint64_t n_proofs);
     void witness_union(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint8_t** out_dev, uint64_t* n_out_dev_word);
     void timings(float* ms_exchange, float* ms_fetch, float* ms_union) const;   // after the call's final sync

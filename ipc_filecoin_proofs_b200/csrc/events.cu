@@ -687,6 +687,17 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     bool dense_used = plan.ok;
     if (dense_used) run_dense(); else run_general();
     IPCFP_CUDA(cudaEventRecord(s->ev[9], st));   // the raw message list of this call is complete (cross-shard exchange waits for it)
+    bool xch_early = false;
+    if (xch) {
+        // EARLY H0: with dense message AMTs the length of this shard's slice is known from the roots alone (plan.nraw), so the peers can
+        // agree on the slices while the walk is still running and the whole execution-order exchange goes onto the (high-priority)
+        // exchange stream right behind it — it then runs under the witness snapshot, the host's sync and pass 1 instead of after them.
+        // A shard that cannot promise its slice yet (sparse AMTs → general walk, a fault in the prologue) says so and EVERY shard takes
+        // the late path below; a promise that turns out wrong (the dense walk raised its flag) is repaired after pass 2 (`stale`).
+        xch->agree_early(plan.ok && !early_fault, plan.ok ? plan.nraw : 0, nraw_total);
+        xch_early = xch->all_early;
+        if (xch_early) xch->start_exchange(exec_raw.p, s->ev[9]);
+    }
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
@@ -709,16 +720,16 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         pend_tx = std::min<uint64_t>(pend_tx, tx_err_key(IPCFP_TX_EIDX_NONE, 0, 0, DC_UNSUPPORTED, 1));
     }
     uint64_t nraw = dense_used ? plan.nraw : std::min<uint64_t>(hw[ccount_idx], raw_cap);
-    if (xch && (pend_tx != IPCFP_NO_ERROR || pend_err != IPCFP_NO_ERROR)) {
+    // early mode: the exchange that is running was fed the PLANNED slice; if the dense walk gave up, the list was rewritten underneath it
+    bool xch_stale = xch_early && (!dense_used || nraw != plan.nraw);
+    if (xch && !xch_early && (pend_tx != IPCFP_NO_ERROR || pend_err != IPCFP_NO_ERROR)) {
         // this shard has no message list: tell the peers (H0), then fail — with the first error over ALL shards, like them
         xch->agree_slices(pend_tx, pend_err, 0);
         throw_global(xch->g_tx, xch->g_err, false);
     }
     if (!exo) wbuild.start_copy(hw[8], hw[9], hw[16], hw[17]);
-    if (xch) {
-        // The witness gather is on its way: agree on the slices with the peers (H0: one small all-gather the host waits for) and put the
-        // whole execution-order exchange on the exchange stream — a HIGH-PRIORITY stream, so that its blocks are scheduled ahead of
-        // pass 1's (launched right below) instead of behind them, and the exchange is over long before pass 2 is
+    if (xch && !xch_early) {
+        // LATE H0 (some shard could not promise its slice before its walk was over): agree on the slices now and start the exchange
         xch->agree_slices(IPCFP_NO_ERROR, IPCFP_NO_ERROR, nraw);
         if (!xch->peers_ok) { IPCFP_CUDA(cudaStreamSynchronize(st)); throw_global(xch->g_tx, xch->g_err, false); }
         xch->start_exchange(exec_raw.p, s->ev[9]);
@@ -828,11 +839,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         // matches, and exec.get(i) of events/generator.rs:244-246 for every match — it PRECEDES r_amt.get(i) in the reference, so at the
         // same receipt it outranks whatever pass 2 reported (code 0 sorts first in the error word)
         xch->positions_for(st, match_rel.p, M, n_exec_dev);
-        if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw); IPCFP_LAUNCH_CHECK(); }
+        IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, st));   // the check has its own word: it may have to be repeated (stale exchange)
+        if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
     wbuild.finish_enqueue(wbits.p);
-    publish_words(s, 0, 16);
+    publish_words(s, 0, 20);
     publish_words_from(s, misc.p, 20, 2);   // misc[2] = any_skip (32-bit words 0..3 land in hw[20..21])
     IPCFP_CUDA(cudaStreamSynchronize(st));
     note_errors(hw);
@@ -842,7 +854,23 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     const uint64_t mB = hw[10];
     if (xch) {
         // H2: how far did every shard get. All ranks continue or fail together, naming the same first error.
-        xch->agree_results(pend_tx, pend_err, missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300));
+        uint64_t pend_chk = hw[19];
+        xch->agree_results(pend_tx, std::min(pend_err, pend_chk), missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300), xch_stale);
+        if (xch->g_stale && xch->g_tx == IPCFP_NO_ERROR) {
+            // some shard's early promise was wrong: its slice differs from what the running exchange used. Every shard repeats the
+            // exchange with the slices as they really are (late H0), then the positions, the exec.get check and H2.
+            xch->agree_slices(pend_tx, pend_err, nraw);
+            if (xch->peers_ok) {
+                xch->start_exchange(exec_raw.p, s->ev[9]);
+                xch->positions_for(st, match_rel.p, M, n_exec_dev);
+                IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, st));
+                if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
+                publish_words(s, 19, 1);
+                IPCFP_CUDA(cudaStreamSynchronize(st));
+                pend_chk = hw[19];
+            }
+            xch->agree_results(pend_tx, std::min(pend_err, pend_chk), missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300), false);
+        }
         throw_global(xch->g_tx, xch->g_err, xch->g_missing_base);
         if (xch->g_overflow) throw Error(IPCFP_ERR_UNSUPPORTED, "execution-order exchange: bucket overflow (skewed CID hash distribution)");
         n_exec = xch->host_word(301);

@@ -198,6 +198,7 @@ void exec_fetch(int device, const void* seg, uint64_t nseg, uint64_t pos0, const
 // NCCL is resolved with dlopen at ipcfp_comm_init (libnccl.so.2: the copy already in the process — e.g. PyTorch's — or the
 // system one), so the library itself keeps linking only cudart and loads on machines without NCCL.
 // =====================================================================================================================
+#include <cstdio>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -255,7 +256,7 @@ struct Comm {
     ncclComm_t cx = nullptr, cw = nullptr;   // exchange (execution order) / witness union: independent streams, independent communicators
     cudaStream_t sx = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
-    cudaEvent_t tm[6] = {};                  // timing: exchange begin/end (sx), fetch begin/end, union begin/end (engine stream)
+    cudaEvent_t tm[10] = {};                 // timing: exchange begin/end (sx), fetch begin/end, union begin/end (engine stream); [6..8] inside the exchange: bucketize | all-to-all | dedup done
     // grow-only device scratch (allocated during warm-up, then reused)
     DevBuf<uint8_t> sendbuf, recvbuf, gather, merged, recs;
     DevBuf<unsigned long long> table, words, words2;
@@ -343,6 +344,67 @@ __global__ void k_exec_scatter_seg(const RawCid* __restrict__ seg, const uint32_
         *(ExecEntry*)(send + (uint64_t)owner * (XSEG_HDR + cap * 48) + XSEG_HDR + slot * 48) = e;
     }
 }
+// ---- order-preserving partition by owner in three kernels (count per warp run → one scan → scatter), no key / value arrays ----
+#define XB_RUN 256u   // consecutive entries one warp handles (8 chunks of 32)
+__device__ __forceinline__ uint32_t exec_owner_of(const RawCid& c, uint32_t world) { return (uint32_t)((rawcid_hash(c) >> 32) % world); }
+// cnt[owner * nruns + run] = entries of that owner in run `run` of the slice
+__global__ void __launch_bounds__(128) k_xb_count(const RawCid* __restrict__ seg, uint64_t nseg, uint32_t world, uint32_t nruns, uint32_t* cnt) {
+    const uint32_t run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (run >= nruns) return;
+    const uint64_t base = (uint64_t)run * XB_RUN;
+    uint32_t mine = 0;                                   // lane o (< 32) accumulates owner o; world > 32: lanes take owners o, o+32, … in turn
+    for (uint32_t c = 0; c < XB_RUN / 32; c++) {
+        const uint64_t i = base + c * 32 + lane;
+        const uint32_t o = i < nseg ? exec_owner_of(seg[i], world) : 0xffffffffu;
+        for (uint32_t ob = 0; ob < world; ob += 32) {
+            uint32_t add = 0;
+            for (uint32_t k = 0; k < 32 && ob + k < world; k++) { uint32_t b = __ballot_sync(0xffffffffu, o == ob + k); if (lane == k) add = (uint32_t)__popc(b); }
+            if (ob == 0) mine += add;
+            else if (ob + lane < world && add) atomicAdd(&cnt[(uint64_t)(ob + lane) * nruns + run], add);   // rare: world > 32
+        }
+    }
+    if (lane < world) cnt[(uint64_t)lane * nruns + run] = mine + (world > 32 ? cnt[(uint64_t)lane * nruns + run] : 0u);
+}
+// segment headers: count per owner from the scan (scan[o * nruns] = entries of all owners before o)
+__global__ void k_xb_headers(const uint64_t* __restrict__ scan, const uint64_t* __restrict__ total, uint32_t world, uint32_t nruns, uint64_t cap, uint8_t* send,
+                             unsigned long long* overflow) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= world) return;
+    const uint64_t a = scan[(uint64_t)o * nruns], b = o + 1 < world ? scan[(uint64_t)(o + 1) * nruns] : *total;
+    unsigned long long c = b - a;
+    if (c > cap) { *overflow = 1; c = cap; }
+    *(unsigned long long*)(send + (uint64_t)o * (XSEG_HDR + cap * 48)) = c;
+}
+// entries leave in (owner, position) order: slot = entries of that owner in earlier runs + earlier ones of this run
+__global__ void __launch_bounds__(128) k_xb_scatter(const RawCid* __restrict__ seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint32_t nruns,
+                                                   const uint64_t* __restrict__ scan, uint64_t cap, uint8_t* send) {
+    __shared__ uint32_t s_run[4][256];
+    const uint32_t run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (run >= nruns) return;
+    for (uint32_t o = lane; o < world; o += 32) s_run[wib][o] = 0;
+    __syncwarp();
+    const uint64_t base = (uint64_t)run * XB_RUN;
+    for (uint32_t c = 0; c < XB_RUN / 32; c++) {
+        const uint64_t i = base + c * 32 + lane;
+        const bool valid = i < nseg;
+        RawCid rc{};
+        uint32_t o = 0xffffffffu;
+        if (valid) { rc = seg[i]; o = exec_owner_of(rc, world); }
+        const unsigned m = __match_any_sync(0xffffffffu, o);
+        if (valid) {
+            const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+            const uint64_t slot = scan[(uint64_t)o * nruns + run] - scan[(uint64_t)o * nruns] + s_run[wib][o] + rank;
+            if (slot < cap) {
+                ExecEntry e; e.c = rc; e.pos = pos0 + i;
+                *(ExecEntry*)(send + (uint64_t)o * (XSEG_HDR + cap * 48) + XSEG_HDR + slot * 48) = e;
+            }
+        }
+        __syncwarp();
+        if (valid && (m & ((1u << lane) - 1u)) == 0) s_run[wib][o] += (uint32_t)__popc(m);   // first lane of every owner group
+        __syncwarp();
+    }
+}
+
 // seg_off[0..world] from the received segment headers
 __global__ void k_recv_offsets(const uint8_t* __restrict__ recv, uint32_t world, uint64_t cap, uint64_t* seg_off) {
     if (threadIdx.x || blockIdx.x) return;
@@ -567,6 +629,29 @@ ShardExchange::ShardExchange(Comm* comm, Store* store, uint64_t lo_, uint64_t hi
     if (c->world > 255) throw Error(IPCFP_ERR_UNSUPPORTED, "world too large");
 }
 
+// EARLY H0: can every shard promise the length of its slice already (dense message AMTs: known from the roots), and do all shards see the
+// same message list. all_early ⇒ the slices (nseg_all, pos0, nraw) are set as for agree_slices.
+void ShardExchange::agree_early(bool can_promise, uint64_t planned_nseg, uint64_t nraw_total) {
+    const uint32_t W = c->world;
+    uint64_t mine[4] = {can_promise ? 1ull : 0ull, planned_nseg, nraw_total, 0};
+    uint64_t* all = c->host.p;
+    run_all_gather_host(c, mine, 4, all);
+    bool ok = true;
+    nseg_all.assign(W, 0);
+    nraw = 0; max_nseg = 0;
+    for (uint32_t r = 0; r < W; r++) {
+        if (!all[4 * r] || all[4 * r + 2] != all[2]) ok = false;
+        nseg_all[r] = all[4 * r + 1];
+        if (r == c->rank) pos0 = nraw;
+        nraw += nseg_all[r];
+        max_nseg = std::max(max_nseg, nseg_all[r]);
+    }
+    if (ok && nraw != all[2]) ok = false;                 // the promised slices must tile the whole list
+    if (nraw >= 0xffffffffull) ok = false;
+    all_early = ok;
+    peers_ok = true;
+    nseg = planned_nseg;
+}
 // H0: does every shard have its slice of the message list, and how long is it. Every rank takes part, also a failing one.
 void ShardExchange::agree_slices(uint64_t tx_key, uint64_t err_key, uint64_t nseg_) {
     const uint32_t W = c->world;
@@ -612,7 +697,6 @@ void ShardExchange::start_exchange(const void* seg_dev, cudaEvent_t seg_ready) {
     uint64_t slots = 64;
     while (slots < 2 * (W * cap)) slots <<= 1;
     c->table.ensure(slots);
-    unsigned long long* small = c->words.p + 2200;        // [0, W]: first sorted position of every owner
     unsigned long long* overflow = c->words.p + 3100;
     IPCFP_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (nwords + 64) * 4, sx));
     IPCFP_CUDA(cudaMemsetAsync(c->table.p, 0, slots * 8, sx));
@@ -620,16 +704,16 @@ void ShardExchange::start_exchange(const void* seg_dev, cudaEvent_t seg_ready) {
     // headers of empty segments must read 0 even when this rank has nothing to send
     for (uint32_t r = 0; r < W; r++) IPCFP_CUDA(cudaMemsetAsync(c->sendbuf.p + r * segbytes, 0, XSEG_HDR, sx));
     if (nseg) {
-        unsigned nb = radix_blocks(nseg);
-        AsyncBuf<uint32_t> keys(nseg, sx), vals(nseg, sx), ka(nseg, sx), va(nseg, sx), hist((size_t)256 * nb + 256, sx);
-        AsyncBuf<uint64_t> scan_tmp((size_t)256 * nb + 256, sx), scratch(scan_scratch_elems((uint64_t)256 * nb) + 8, sx);
-        k_fill_words<<<1, 256, 0, sx>>>(small, W + 1, nseg); IPCFP_LAUNCH_CHECK();
-        k_exec_owner<<<div_up(nseg, 256), 256, 0, sx>>>(seg, nseg, W, keys.p, vals.p); IPCFP_LAUNCH_CHECK();
-        if (W > 1) radix_sort_pairs(keys.p, vals.p, ka.p, va.p, nseg, 8, hist.p, scan_tmp.p, scratch.p, sx);
-        k_exec_starts<<<div_up(nseg, 256), 256, 0, sx>>>(keys.p, nseg, small); IPCFP_LAUNCH_CHECK();
-        k_exec_seg_headers<<<1, 1, 0, sx>>>(small, nseg, W, cap, c->sendbuf.p, overflow); IPCFP_LAUNCH_CHECK();
-        k_exec_scatter_seg<<<div_up(nseg, 256), 256, 0, sx>>>(seg, keys.p, vals.p, nseg, pos0, small, cap, c->sendbuf.p); IPCFP_LAUNCH_CHECK();
+        const uint32_t nruns = div_up(nseg, XB_RUN);
+        AsyncBuf<uint32_t> cnt((uint64_t)W * nruns + 64, sx);
+        AsyncBuf<uint64_t> scan((uint64_t)W * nruns + 64, sx), scratch(scan_scratch_elems((uint64_t)W * nruns) + 8, sx), total(1, sx);
+        if (W > 32) cnt.zero();
+        k_xb_count<<<div_up((uint64_t)nruns * 32, 128), 128, 0, sx>>>(seg, nseg, W, nruns, cnt.p); IPCFP_LAUNCH_CHECK();
+        exclusive_scan_u32(cnt.p, scan.p, (uint64_t)W * nruns, total.p, scratch.p, sx);
+        k_xb_headers<<<div_up(W, 64), 64, 0, sx>>>(scan.p, total.p, W, nruns, cap, c->sendbuf.p, overflow); IPCFP_LAUNCH_CHECK();
+        k_xb_scatter<<<div_up((uint64_t)nruns * 32, 128), 128, 0, sx>>>(seg, nseg, pos0, W, nruns, scan.p, cap, c->sendbuf.p); IPCFP_LAUNCH_CHECK();
     }
+    IPCFP_CUDA(cudaEventRecord(c->tm[6], sx));
     // all-to-all of whole segments (fixed size: no count round trip; the valid count travels in the segment header)
     IPCFP_NCCL(n->GroupStart());
     for (uint32_t p = 0; p < W; p++) {
@@ -637,11 +721,13 @@ void ShardExchange::start_exchange(const void* seg_dev, cudaEvent_t seg_ready) {
         IPCFP_NCCL(n->Recv(c->recvbuf.p + p * segbytes, segbytes, ncclUint8, (int)p, c->cx, sx));
     }
     IPCFP_NCCL(n->GroupEnd());
+    IPCFP_CUDA(cudaEventRecord(c->tm[7], sx));
     uint64_t* seg_off = (uint64_t*)(c->words.p + 2600);   // [0, W]
     k_recv_offsets<<<1, 1, 0, sx>>>(c->recvbuf.p, W, cap, seg_off); IPCFP_LAUNCH_CHECK();
     const unsigned g = div_up(W * cap, 256);
     k_exec_claim_seg<<<g, 256, 0, sx>>>(c->recvbuf.p, seg_off, W, cap, c->table.p, slots - 1); IPCFP_LAUNCH_CHECK();
     k_exec_mark_dups<<<g, 256, 0, sx>>>(c->recvbuf.p, seg_off, W, cap, c->table.p, slots - 1, c->bitmap.p); IPCFP_LAUNCH_CHECK();
+    IPCFP_CUDA(cudaEventRecord(c->tm[8], sx));
     // the owners' bitmaps are disjoint (a position belongs to one CID, a CID to one owner): their sum is their union
     IPCFP_NCCL(n->AllReduce(c->bitmap.p, c->bitmap_sum.p, nwords + 1, ncclUint32, ncclSum, c->cx, sx));
     // n_exec = number of zero bits; prefix zero counts for the select
@@ -668,14 +754,14 @@ void ShardExchange::positions_for(cudaStream_t st, const uint32_t* match_rel, ui
 }
 
 // H2: every rank reports how far it got; all ranks continue or fail TOGETHER, with the same (first) error
-void ShardExchange::agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow) {
+void ShardExchange::agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow, bool stale) {
     const uint32_t W = c->world;
-    uint64_t mine[8] = {tx_key, err_key, missing_base ? 1ull : 0ull, M, n_proofs, n_witness, exch_overflow, 0};
+    uint64_t mine[8] = {tx_key, err_key, missing_base ? 1ull : 0ull, M, n_proofs, n_witness, exch_overflow, stale ? 1ull : 0ull};
     uint64_t* all = c->host.p;
     run_all_gather_host(c, mine, 8, all);
     k_pick_field<<<1, 256, 0, c->sx>>>(c->words2.p, W, 8, 5, (uint64_t*)(c->words2.p + 2600)); IPCFP_LAUNCH_CHECK();
     IPCFP_CUDA(cudaStreamSynchronize(c->sx));
-    g_tx = g_err = IPCFP_NO_ERROR; g_missing_base = false; g_overflow = false;
+    g_tx = g_err = IPCFP_NO_ERROR; g_missing_base = false; g_overflow = false; g_stale = false;
     M_max = 0; nw_max = 0; M_total = 0; proofs_total = 0;
     nw_all.assign(W, 0);
     for (uint32_t r = 0; r < W; r++) {
@@ -685,6 +771,7 @@ void ShardExchange::agree_results(uint64_t tx_key, uint64_t err_key, bool missin
         M_max = std::max(M_max, a[3]); M_total += a[3]; proofs_total += a[4];
         nw_all[r] = a[5]; nw_max = std::max(nw_max, a[5]);
         g_overflow |= a[6] != 0;
+        g_stale |= a[7] != 0;
     }
 }
 
@@ -744,6 +831,12 @@ void ShardExchange::witness_union(cudaStream_t st, const uint8_t* cids_dev, uint
 }
 void ShardExchange::timings(float* ms_exchange, float* ms_fetch, float* ms_union) const {
     cudaEventElapsedTime(ms_exchange, c->tm[0], c->tm[1]);
+    if (getenv("IPCFP_XCH_TRACE")) {
+        float a = 0, b = 0, d = 0, e = 0;
+        cudaEventElapsedTime(&a, c->tm[0], c->tm[6]); cudaEventElapsedTime(&b, c->tm[6], c->tm[7]); cudaEventElapsedTime(&d, c->tm[7], c->tm[8]); cudaEventElapsedTime(&e, c->tm[8], c->tm[1]);
+        fprintf(stderr, "[ipcfp rank %u] exchange: bucketize %.3f ms | all-to-all %.3f ms | dedup %.3f ms | all-reduce + scan %.3f ms (cap %llu entries/segment)\n", c->rank, a, b, d, e,
+                (unsigned long long)cap);
+    }
     cudaEventElapsedTime(ms_fetch, c->tm[2], c->tm[3]);
     cudaEventElapsedTime(ms_union, c->tm[4], c->tm[5]);
 }

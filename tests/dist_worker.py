@@ -246,6 +246,77 @@ def nccl_worker(rank, world, port, q):
                 bstore.close()
             L.ipcfp_tipset_free(tip)
             store.close()
+
+        def outcome_sharded(shard_ts, N):
+            bounds = [N * r // world for r in range(world + 1)]
+            spec = A.make_event_spec(shard_ts.event_signature, shard_ts.topic1, shard_ts.actor_filter)
+            st_ = api.BlockStore.from_tipset(shard_ts, device=dev)
+            d_, k_ = A.make_tipset_desc(shard_ts)
+            tp = C.c_void_p()
+            assert L.ipcfp_tipset_upload(st_._h, C.byref(d_), C.byref(tp)) == 0
+            try:
+                o = comm.generate_event_proof(st_._h, tp, spec, bounds, A.SHARDED_UNION_TO_HOST)
+                r_ = o.contents
+                g = A.event_result_from_c(r_)
+                nu = int(r_.n_union_cids)
+                un = np.frombuffer((C.c_uint8 * (nu * 38)).from_address(r_.union_cids), dtype=np.uint8).reshape(-1, 38).copy() if nu else np.zeros((0, 38), np.uint8)
+                res = ("ok", g, int(r_.n_exec), un)
+                L.ipcfp_event_result_free(o)
+                return res
+            except A.IpcfpError as e:
+                return ("err", e.status, e.index)
+            finally:
+                L.ipcfp_tipset_free(tp)
+                st_.close()
+
+        def outcome_oracle(full_ts):
+            spec = A.make_event_spec(full_ts.event_signature, full_ts.topic1, full_ts.actor_filter)
+            try:
+                return ("ok", oracle.Store.from_tipset(full_ts).generate_event_proof(full_ts, spec))
+            except A.IpcfpError as e:
+                return ("err", e.status, e.index)
+
+        def compare(got, exp, lo, hi):
+            assert got[0] == exp[0], (got[:3] if got[0] == "err" else got[0], exp[:3] if exp[0] == "err" else exp[0])
+            if got[0] == "err":
+                assert got[1:] == exp[1:], (got, exp)
+                return
+            g, n_exec, union = got[1], got[2], got[3]
+            e = exp[1]
+            assert n_exec == e.n_exec
+            assert g.matching.tolist() == [int(i) for i in e.matching if lo <= i < hi]
+            assert [p.key() for p in g.proofs] == [p.key() for p in e.proofs if lo <= p.exec_index < hi]
+            assert np.array_equal(union, e.witness.cids)
+
+        # ---- the LATE path of the protocol: no shard promises its slice early (general walk forced)
+        N = PARAMS["n_receipts"]
+        lo, hi = N * rank // world, N * (rank + 1) // world
+        full = synth.Tipset(synth.default_params(**PARAMS))
+        shard = synth.Tipset(synth.default_params(shard_lo=lo, shard_hi=hi, **PARAMS)) if world > 1 else full
+        os.environ["IPCFP_BFS_GENERAL"] = "1"
+        compare(outcome_sharded(shard, N), outcome_oracle(full), lo, hi)
+        del os.environ["IPCFP_BFS_GENERAL"]
+        # ---- the STALE path: a message AMT with a hole (its root still promises a dense list): the dense walk of the shard that owns the
+        # hole gives up AFTER the early exchange has started; every shard then repeats the exchange with the real slices
+        import cbor2
+        from tests.test_oracle_cpu import _patched
+        dct = full.as_dict()
+        tm = cbor2.loads(dct[bytes(full.parent_txmeta_cids[0])])
+        root_cid = tm[0].value[1:]
+        height, count, node = cbor2.loads(dct[root_cid])
+        cur_cid, cur, is_root = root_cid, node, True
+        while cur[1]:
+            cur_cid = cur[1][0].value[1:]
+            cur, is_root = cbor2.loads(dct[cur_cid]), False
+        bmap, links, vals = cur
+        if len(vals) >= 2:
+            slots = [b for b in range(8) if bmap[0] >> b & 1]
+            node2 = [bytes([bmap[0] & ~(1 << slots[-1])]), [], vals[:-1]]
+            new = cbor2.dumps([height, count, node2]) if is_root else cbor2.dumps(node2)
+            full2 = _patched(full, cur_cid, new)
+            has = any(bytes(shard.cids[i]) == bytes(cur_cid) for i in range(shard.n_blocks))
+            shard2 = _patched(shard, cur_cid, new) if has else shard
+            compare(outcome_sharded(shard2, N), outcome_oracle(full2), lo, hi)
         comm.close()
         dist.barrier()
         dist.destroy_process_group()
