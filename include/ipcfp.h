@@ -180,9 +180,13 @@ typedef struct ipcfp_event_result {
     uint64_t shard_exec_count;
     uint64_t shard_raw_total;         /* total length of the concatenated message list (all shards) */
     /* ipcfp_generate_event_proof_sharded only: proofs[].message_cid and n_exec are final (resolved across shards inside the
-     * call); the union of ALL shards' witness CID sets (the BTreeSet union of src/proofs/common/witness.rs:24-40), sorted in
-     * `Cid` order, in DEVICE memory (n_union_cids*38 bytes, valid until the next sharded call on the same communicator) and —
-     * with IPCFP_SHARDED_UNION_TO_HOST — on the host; matches / proofs summed over all shards. */
+     * call). The union of ALL shards' witness CID sets (the BTreeSet union of src/proofs/common/witness.rs:24-40) has
+     * n_union_cids entries in `Cid` order and is left DISTRIBUTED: this rank holds entries [union_part_first, union_part_first +
+     * n_union_part) — the CIDs whose first two digest bytes fall into its 1/world share of the 65 536 buckets — so the
+     * concatenation of the ranks' parts in rank order is the whole sorted set. With IPCFP_SHARDED_UNION_FULL every rank holds the
+     * whole set instead (union_part_first = 0, n_union_part = n_union_cids). union_cids_dev: DEVICE memory, n_union_part*38 bytes,
+     * valid until the next sharded call on the same communicator; union_cids: the same on the host with
+     * IPCFP_SHARDED_UNION_TO_HOST. total_matching / total_proofs: summed over all shards. */
     const void* union_cids_dev;
     uint64_t n_union_cids;
     const uint8_t* union_cids;
@@ -190,6 +194,8 @@ typedef struct ipcfp_event_result {
     uint64_t total_proofs;
     float ms_exchange, ms_fetch, ms_union; /* device time of the execution-order exchange (its own stream, under pass 1), the message-CID fetch, the witness union */
     float _pad0;
+    uint64_t union_part_first;
+    uint64_t n_union_part;
 } ipcfp_event_result;
 
 typedef struct ipcfp_storage_proof {
@@ -236,7 +242,8 @@ typedef struct ipcfp_bundle {
  * ------------------------------------------------------------------------------------------ */
 #define IPCFP_SCAN_SKIP_TX_AMTS 0x1u  /* find_matching_events only: no record_transaction_amts / base witness;
                                          execution order still built                                          */
-#define IPCFP_SHARDED_UNION_TO_HOST 0x2u /* ipcfp_generate_event_proof_sharded: also copy the merged witness CID list to the host */
+#define IPCFP_SHARDED_UNION_TO_HOST 0x2u /* ipcfp_generate_event_proof_sharded: also copy this rank's part of the merged witness CID list to the host */
+#define IPCFP_SHARDED_UNION_FULL 0x4u    /* … every rank receives the WHOLE merged list (all-gather + merge of `world` lists on every rank) instead of its partition */
 
 /* generate_event_proof (src/proofs/events/generator.rs:60-107): base witness, message-AMT
  * recording, execution order, two-pass scan (find_matching_events :180-307), materialise. */
@@ -313,8 +320,8 @@ ipcfp_status ipcfp_verify_storage_proofs(ipcfp_store* witness_store, const ipcfp
  * receipts are split by index range bounds[rank] .. bounds[rank+1] (bounds: world+1 ascending values, bounds[0] = 0,
  * bounds[world] = n_receipts); every rank's store holds the blocks its range needs (events blocks, receipts-AMT paths, its share
  * of the message AMTs, the shared top levels). Inside the call: all-to-all + all-reduce for the first-seen dedup of the
- * execution order (src/proofs/events/utils.rs:48-94), exec index → message CID fetch for the rank's proofs, and ONE all-gather of
- * the per-shard witness CID sets merged on every rank. All ranks must make the call; they succeed or fail together and a
+ * execution order (src/proofs/events/utils.rs:48-94), exec index → message CID fetch for the rank's proofs, and the union of the
+ * per-shard witness CID sets (range-partitioned all-to-all + merge; see ipcfp_event_result.union_*). All ranks must make the call; they succeed or fail together and a
  * failure names the same (status, index) everywhere — the one the reference's sequential order meets first over all shards.
  * Errors: IPCFP_ERR_NCCL (library missing / communicator failure). */
 #define IPCFP_COMM_ID_BYTES 128

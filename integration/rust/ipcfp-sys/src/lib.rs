@@ -21,6 +21,7 @@ pub const IPCFP_ERR_UNSUPPORTED: ipcfp_status = -11;
 pub const IPCFP_STORE_VERIFY_CIDS: u32 = 0x1;
 pub const IPCFP_SCAN_SKIP_TX_AMTS: u32 = 0x1;
 pub const IPCFP_SHARDED_UNION_TO_HOST: u32 = 0x2;
+pub const IPCFP_SHARDED_UNION_FULL: u32 = 0x4;
 pub const IPCFP_COMM_ID_BYTES: usize = 128;
 
 #[repr(C)] pub struct ipcfp_store { _p: [u8; 0] }
@@ -61,6 +62,7 @@ pub struct ipcfp_event_result {
     pub shard_exec_dev: *const c_void, pub shard_exec_count: u64, pub shard_raw_total: u64,
     pub union_cids_dev: *const c_void, pub n_union_cids: u64, pub union_cids: *const u8, pub total_matching: u64, pub total_proofs: u64,
     pub ms_exchange: f32, pub ms_fetch: f32, pub ms_union: f32, pub _pad0: f32,
+    pub union_part_first: u64, pub n_union_part: u64,
 }
 #[repr(C)]
 pub struct ipcfp_storage_proof {

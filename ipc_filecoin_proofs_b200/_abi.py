@@ -26,6 +26,7 @@ ERR_UNSUPPORTED = -11
 STORE_VERIFY_CIDS = 0x1
 SCAN_SKIP_TX_AMTS = 0x1
 SHARDED_UNION_TO_HOST = 0x2
+SHARDED_UNION_FULL = 0x4
 COMM_ID_BYTES = 128
 
 
@@ -112,6 +113,8 @@ class EventResultC(C.Structure):
         ("ms_fetch", C.c_float),
         ("ms_union", C.c_float),
         ("_pad0", C.c_float),
+        ("union_part_first", C.c_uint64),
+        ("n_union_part", C.c_uint64),
     ]
 
 

@@ -60,6 +60,7 @@ struct Store {
     DevBuf<uint8_t> cls;
     DevBuf<uint64_t> table;
     DevBuf<BlockRec> recs;
+    DevBuf<uint32_t> rank_of, block_at_rank;   // `Cid` Ord rank of every block and its inverse (witness bitmaps are indexed by rank)
     StoreView view{};
     DevBuf<StoreView> view_dev;   // device copy, for out-of-line device functions (keeps kernel params off the stack)
     std::vector<std::array<uint8_t, 6>> class_prefix;  // distinct CID prefixes in this store
@@ -105,6 +106,7 @@ void check_device(int device);
 // instead of a D2H copy, so the read-back never queues behind a large copy on the copy engine
 void publish_words(Store* s, uint32_t first, uint32_t count);
 void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint32_t n_words);
+void publish_words_on(Store* s, cudaStream_t stream, const void* src_dev, uint32_t dst_first, uint32_t n_words);   // the same on another stream
 
 // events.cu
 void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td);
@@ -164,7 +166,15 @@ struct ShardExchange {
     void agree_results(uint64_t tx_key, uint64_t err_key, bool missing_base, uint64_t n_proofs, uint64_t n_witness, uint64_t exch_overflow, bool stale);
     void fetch_and_patch(cudaStream_t st, ipcfp_event_proof* proofs_dev, uint64_t n_proofs);
     void witness_union(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint8_t** out_dev, uint64_t* n_out_dev_word);
+    // the same union left distributed: this rank's partition (sorted) in *out_dev; every rank's [partition size, overflow flag] lands in
+    // the store's mapped words [host_word_first, +2·world) with the next sync of `st`. Any overflow flag set: repeat with
+    // union_piece_cap(true).
+    uint64_t union_piece_cap(bool cannot_overflow) const;
+    void witness_union_partitioned(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint64_t cap, uint8_t** out_dev, uint32_t host_word_first);
     void timings(float* ms_exchange, float* ms_fetch, float* ms_union) const;   // after the call's final sync
+    void trace_timeline(cudaEvent_t origin, const char* engine_part) const;
+    cudaStream_t stream() const;            // the exchange stream
+    cudaStream_t union_stream() const;      // the witness union's own stream (its communicator is independent of the exchange's)
     uint64_t host_word(uint32_t i) const;   // the store's mapped words: 300 = exchange overflow flag, 301 = n_exec (valid after the sync that follows positions_for)
 };
 void exec_bucketize(int device, const void* seg, uint64_t nseg, uint64_t pos0, uint32_t world, uint64_t cap, void* send, uint64_t* counts_host);
@@ -195,7 +205,7 @@ struct WitnessBuilder {
     uint64_t nwords = 0, mA = 0, mB = 0, bytesA = 0, bytesB = 0, host_cap = 0;
     bool have_snapshot = false;
     AsyncBuf<uint32_t> idx, plen, bitsA, bitsB;
-    AsyncBuf<uint64_t> offs, word_prefix, scratch;
+    AsyncBuf<uint64_t> offs, word_prefix, word_prefixB, scratch;
     AsyncBuf<uint8_t> dblobA, dblobB_keep;
     PinnedArray host_blob;
     explicit WitnessBuilder(Store* store);
@@ -203,11 +213,15 @@ struct WitnessBuilder {
     // host knows the counts: gather in two parts (the first split_idx blocks = split_bytes bytes, then the rest) so that the D2H of
     // the first part is on the wire while the second is still being gathered
     void start_copy(uint64_t mA, uint64_t bytesA, uint64_t split_idx, uint64_t split_bytes);
-    void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10]
-    void finish(uint64_t mB, WitnessOut& out, bool want_sorted_idx = false);   // late blocks, Cid-order index arrays, join
-    void finish_start(uint64_t mB, WitnessOut& out, bool want_sorted_idx = false);   // … the same without the join: everything enqueued
+    void finish_enqueue(const uint32_t* wbits);  // enqueue; late-block count → dev_words[10], their padded bytes → dev_words[11]
+    // late blocks (mB of them, bytesB padded bytes: dev_words[10] and [11] after finish_enqueue), Cid-order index arrays, join
+    void finish(uint64_t mB, uint64_t bytesB, WitnessOut& out, bool want_sorted_idx = false);
+    void finish_start(uint64_t mB, uint64_t bytesB, WitnessOut& out, bool want_sorted_idx = false);   // … the same without the join: everything enqueued
     void finish_join(WitnessOut& out);                                              // … wait for both streams
 };
 void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out);
+// ord[0..m) = the permutation that sorts the blocks idx[0..m) in `Cid` Ord (stable); runs on the store's stream (ingest: the ranks)
+size_t sort_by_cid_ws_bytes(uint64_t m);
+void sort_by_cid(Store* s, const uint32_t* idx_dev, uint32_t* ord, uint64_t m, void* workspace);
 
 }  // namespace ipcfp

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <chrono>
 #include "engine.cuh"
 #include "hashes.cuh"
 #include "ipld.cuh"
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
         for (uint32_t i = t - 128; i < 2 * P + 2; i += 128) {
             const uint8_t* cid = i < P ? a.parent_cids + 38 * i : (i == P ? a.child_cid : (i == P + 1 ? a.receipts_root : a.txmeta_cids + 38 * (i - P - 2)));
             int32_t b = store_lookup(s, cid);
-            if (b < 0) *a.missing_base = 1; else witness_mark(a.wbits, (uint32_t)b);
+            if (b < 0) *a.missing_base = 1; else witness_mark(s, a.wbits, (uint32_t)b);
         }
     }
     if (t == 96) {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
         for (uint32_t k = 0; k < 2; k++) { a.f_meta[2 * b + k] = AMT_SENTINEL; a.f_blk[2 * b + k] = 0; a.f_base[2 * b + k] = 0; a.amt_height[2 * b + k] = 0; a.amt_count[2 * b + k] = 0; }
         int32_t tb = store_lookup(s, a.txmeta_cids + 38 * b);
         if (tb < 0) { report_tx_error(a.txerr, 3 * b, 0, 31, DC_MISSING, 0); continue; }
-        if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)tb);
+        if (!a.skip_tx) witness_mark(s, a.wbits, (uint32_t)tb);
         uint32_t len;
         const uint8_t* p = store_block(s, (uint32_t)tb, len);
         Rd r(p, len);
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
         for (uint32_t k = 0; k < 2; k++) {
             int32_t rb = store_lookup(s, p + (k ? c1 : c0));
             if (rb < 0) { report_tx_error(a.txerr, 3 * b + 1 + k, 0, 31, DC_MISSING, 0); break; }
-            if (!a.skip_tx) witness_mark(a.wbits, (uint32_t)rb);
+            if (!a.skip_tx) witness_mark(s, a.wbits, (uint32_t)rb);
             uint32_t rl;
             const uint8_t* rp = store_block(s, (uint32_t)rb, rl);
             Rd rr(rp, rl);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupArgs a) {
     // Amtv0::<MessageReceipt>::load(&receipts_root, &rec_receipts) (events/generator.rs:195-196)
     int32_t rb = store_lookup(s, a.receipts_root);
     if (rb < 0) { report_error(a.err, ST_RECEIPTS_ROOT, 0, DC_MISSING, 0); return; }
-    witness_mark(a.wbits, (uint32_t)rb);
+    witness_mark(s, a.wbits, (uint32_t)rb);
     *a.receipts_root_blk = (uint32_t)rb;
     uint32_t len;
     const uint8_t* p = store_block(s, (uint32_t)rb, len);
@@ -470,9 +471,11 @@ void tipset_upload(Store* s, const ipcfp_tipset_desc* t, TipsetDev& td) {
 }
 
 ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*/, TipsetDev& td, const ipcfp_event_spec* spec, uint32_t flags,
-                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t /*world*/, uint32_t /*rank*/, Comm* comm, ExecOrderOut* exo) {
+                                         bool sharded, uint64_t lo, uint64_t hi, uint32_t world, uint32_t rank, Comm* comm, ExecOrderOut* exo) {
     s->use();
     cudaStream_t st = s->stream;
+    const auto t_enter = std::chrono::steady_clock::now();
+    static thread_local std::chrono::steady_clock::time_point t_last_exit = t_enter;
     if (!spec || !spec->event_signature || !spec->topic_1) throw Error(IPCFP_ERR_INVALID_ARG, "event spec has null fields");
     if (!sharded) { lo = 0; hi = td.n_receipts; }
     if (lo > hi || hi > td.n_receipts) throw Error(IPCFP_ERR_INVALID_ARG, "receipt range out of bounds");
@@ -838,9 +841,12 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         // pass 2 did not wait for the cross-shard exchange; now that both are done: the global n_exec, the raw positions of this rank's
         // matches, and exec.get(i) of events/generator.rs:244-246 for every match — it PRECEDES r_amt.get(i) in the reference, so at the
         // same receipt it outranks whatever pass 2 reported (code 0 sorts first in the error word)
-        xch->positions_for(st, match_rel.p, M, n_exec_dev);
-        IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, st));   // the check has its own word: it may have to be repeated (stale exchange)
-        if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
+        // (all of it on the EXCHANGE stream, behind the exchange: the engine stream goes on with the witness and never waits for a peer)
+        cudaStream_t sx = xch->stream();
+        xch->positions_for(sx, match_rel.p, M, n_exec_dev);
+        IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, sx));   // the check has its own word: it may have to be repeated (stale exchange)
+        if (M) { k_check_exec<<<div_up(M, 128), 128, 0, sx>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
+        publish_words_on(s, sx, dw + 19, 19, 1);
     }
     // blocks recorded by pass 2 (receipt paths + events AMTs of the matches): the late part of the witness
     wbuild.finish_enqueue(wbits.p);
@@ -852,8 +858,26 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // (common/witness.rs:43-56, events/generator.rs:104), i.e. AFTER every receipts-root / pass-1 / pass-2 failure
     if (!xch && missing_base && !skip_tx) throw Error(IPCFP_ERR_MISSING_BLOCK, "missing block (base witness CID not in the store)");
     const uint64_t mB = hw[10];
+    const bool any_skip = ((const uint32_t*)(hw + 20))[2] != 0;
+    IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
+
+    // ---- results to the host
+    box->matching = PinnedArray(s->pool, (M + 1) * 8);
+    box->proofs = PinnedArray(s->pool, (n_proofs + 1) * sizeof(ipcfp_event_proof));
+    box->blob = PinnedArray(s->pool, n_bytes + 16);
+    PinnedArray rel(s->pool, (M + 1) * 4);
+    if (M) IPCFP_CUDA(cudaMemcpyAsync(rel.p, match_rel.p, M * 4, cudaMemcpyDeviceToHost, st));
+    if (n_proofs && !xch) IPCFP_CUDA(cudaMemcpyAsync(box->proofs.p, d_proofs.p, n_proofs * sizeof(ipcfp_event_proof), cudaMemcpyDeviceToHost, st));
+    if (n_bytes) IPCFP_CUDA(cudaMemcpyAsync(box->blob.p, d_blob.p, n_bytes, cudaMemcpyDeviceToHost, st));
+
+    // ---- witness: late blocks, sort in Cid order, index arrays (engine stream; the sharded protocol's tail runs beside it)
+    wbuild.finish_start(mB, hw[11], box->wit);
+    uint8_t* union_dev = nullptr;
     if (xch) {
-        // H2: how far did every shard get. All ranks continue or fail together, naming the same first error.
+        cudaStream_t sx = xch->stream();
+        // H2: how far did every shard get. All ranks continue or fail together, naming the same first error. (The host waits for its
+        // peers here while its own GPU sorts the witness.)
+        IPCFP_CUDA(cudaStreamSynchronize(sx));
         uint64_t pend_chk = hw[19];
         xch->agree_results(pend_tx, std::min(pend_err, pend_chk), missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300), xch_stale);
         if (xch->g_stale && xch->g_tx == IPCFP_NO_ERROR) {
@@ -862,41 +886,46 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
             xch->agree_slices(pend_tx, pend_err, nraw);
             if (xch->peers_ok) {
                 xch->start_exchange(exec_raw.p, s->ev[9]);
-                xch->positions_for(st, match_rel.p, M, n_exec_dev);
-                IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, st));
-                if (M) { k_check_exec<<<div_up(M, 128), 128, 0, st>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
-                publish_words(s, 19, 1);
-                IPCFP_CUDA(cudaStreamSynchronize(st));
+                xch->positions_for(sx, match_rel.p, M, n_exec_dev);
+                IPCFP_CUDA(cudaMemsetAsync(dw + 19, 0xff, 8, sx));
+                if (M) { k_check_exec<<<div_up(M, 128), 128, 0, sx>>>(match_rel.p, M, lo, n_exec_dev, dw + 19); IPCFP_LAUNCH_CHECK(); }
+                publish_words_on(s, sx, dw + 19, 19, 1);
+                IPCFP_CUDA(cudaStreamSynchronize(sx));
                 pend_chk = hw[19];
             }
             xch->agree_results(pend_tx, std::min(pend_err, pend_chk), missing_base && !skip_tx, n_proofs, hw[8] + mB, xch->host_word(300), false);
         }
-        throw_global(xch->g_tx, xch->g_err, xch->g_missing_base);
-        if (xch->g_overflow) throw Error(IPCFP_ERR_UNSUPPORTED, "execution-order exchange: bucket overflow (skewed CID hash distribution)");
+        if (xch->g_tx != IPCFP_NO_ERROR || xch->g_err != IPCFP_NO_ERROR || xch->g_missing_base || xch->g_overflow) {
+            wbuild.finish_join(box->wit);   // nothing of this call may be in flight when its buffers go
+            throw_global(xch->g_tx, xch->g_err, xch->g_missing_base);
+            throw Error(IPCFP_ERR_UNSUPPORTED, "execution-order exchange: bucket overflow (skewed CID hash distribution)");
+        }
         n_exec = xch->host_word(301);
-        xch->fetch_and_patch(st, d_proofs.p, n_proofs);   // EventProof.message_cid = exec[exec_index], fetched from the shards that hold them
-    }
-    const bool any_skip = ((const uint32_t*)(hw + 20))[2] != 0;
-    IPCFP_CUDA(cudaEventRecord(s->ev[4], st));
-
-    // ---- results to the host
-    box->matching = PinnedArray(s->pool, (M + 1) * 8);
-    box->proofs = PinnedArray(s->pool, (n_proofs + 1) * sizeof(ipcfp_event_proof));
-    box->blob = PinnedArray(s->pool, n_bytes + 16);
-    AsyncBuf<uint32_t> tmp_rel;  // match_rel → absolute u64 on the host below
-    PinnedArray rel(s->pool, (M + 1) * 4);
-    if (M) IPCFP_CUDA(cudaMemcpyAsync(rel.p, match_rel.p, M * 4, cudaMemcpyDeviceToHost, st));
-    if (n_proofs) IPCFP_CUDA(cudaMemcpyAsync(box->proofs.p, d_proofs.p, n_proofs * sizeof(ipcfp_event_proof), cudaMemcpyDeviceToHost, st));
-    if (n_bytes) IPCFP_CUDA(cudaMemcpyAsync(box->blob.p, d_blob.p, n_bytes, cudaMemcpyDeviceToHost, st));
-
-    // ---- witness
-    wbuild.finish_start(mB, box->wit);
-    uint8_t* union_dev = nullptr;
-    if (xch) {
-        xch->witness_union(st, box->wit.cids_dev.p, box->wit.n, &union_dev, (uint64_t*)(dw + 18));
-        publish_words(s, 18, 1);
+        // EventProof.message_cid = exec[exec_index], fetched from the shards that hold them (pass 2 is complete: the host synchronised on it)
+        xch->fetch_and_patch(sx, d_proofs.p, n_proofs);
+        if (n_proofs) IPCFP_CUDA(cudaMemcpyAsync(box->proofs.p, d_proofs.p, n_proofs * sizeof(ipcfp_event_proof), cudaMemcpyDeviceToHost, sx));
+        // union of the shards' witness CID sets as soon as this shard's sorted list exists (event after k_witness_emit), on its own
+        // stream and communicator: it runs beside the message-CID fetch
+        cudaStream_t sw = xch->union_stream();
+        IPCFP_CUDA(cudaStreamWaitEvent(sw, s->ev[6], 0));
+        if (flags & IPCFP_SHARDED_UNION_FULL) {
+            xch->witness_union(sw, box->wit.cids_dev.p, box->wit.n, &union_dev, (uint64_t*)(dw + 18));
+            publish_words_on(s, sw, dw + 18, 18, 1);
+        } else xch->witness_union_partitioned(sw, box->wit.cids_dev.p, box->wit.n, xch->union_piece_cap(false), &union_dev, 320);   // [size, overflow] per rank → hw[320 ..)
     }
     wbuild.finish_join(box->wit);
+    if (xch) {
+        IPCFP_CUDA(cudaStreamSynchronize(xch->stream()));
+        IPCFP_CUDA(cudaStreamSynchronize(xch->union_stream()));
+        if (!(flags & IPCFP_SHARDED_UNION_FULL)) {
+            bool overflow = false;
+            for (uint32_t q = 0; q < world; q++) overflow |= hw[320 + 2 * q + 1] != 0;
+            if (overflow) {   // a piece did not fit its slot on some rank (every rank sees the same words): once more with slots that cannot overflow
+                xch->witness_union_partitioned(xch->union_stream(), box->wit.cids_dev.p, box->wit.n, xch->union_piece_cap(true), &union_dev, 320);
+                IPCFP_CUDA(cudaStreamSynchronize(xch->union_stream()));
+            }
+        }
+    }
     IPCFP_CUDA(cudaEventRecord(s->ev[5], st));
     IPCFP_CUDA(cudaStreamSynchronize(st));
     {
@@ -927,12 +956,30 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     if (sharded) { r.n_exec = 0; r.shard_exec_count = nraw; box->shard_exec = std::move(exec_raw); r.shard_exec_dev = box->shard_exec.p; }
     if (xch) {
         r.n_exec = n_exec;
-        r.union_cids_dev = union_dev; r.n_union_cids = hw[18];
+        r.union_cids_dev = union_dev;
+        if (flags & IPCFP_SHARDED_UNION_FULL) { r.n_union_cids = r.n_union_part = hw[18]; r.union_part_first = 0; }
+        else {
+            r.n_union_cids = 0;
+            for (uint32_t q = 0; q < world; q++) { if (q == rank) r.union_part_first = r.n_union_cids; r.n_union_cids += hw[320 + 2 * q]; }
+            r.n_union_part = hw[320 + 2 * rank];
+        }
         r.total_matching = xch->M_total; r.total_proofs = xch->proofs_total;
         xch->timings(&r.ms_exchange, &r.ms_fetch, &r.ms_union);
+        if (getenv("IPCFP_XCH_TRACE")) {
+            float t[6]; char buf[384];
+            const int evs[6] = {2, 3, 4, 6, 7, 5};   // walk+snapshot done, pass 1 done, pass 2 done, sorted CID list, 51 MB copy done, end
+            for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], s->ev[0], s->ev[evs[i]]);
+            const auto t_now = std::chrono::steady_clock::now();
+            const double host_call = std::chrono::duration<double, std::milli>(t_now - t_enter).count();
+            const double host_gap = std::chrono::duration<double, std::milli>(t_enter - t_last_exit).count();
+            snprintf(buf, sizeof buf, "host: gap since last call %.3f, in call %.3f | walk %.3f pass1 %.3f pass2 %.3f sorted %.3f blobD2H %.3f end %.3f", host_gap, host_call,
+                     t[0], t[1], t[2], t[3], t[4], t[5]);
+            t_last_exit = std::chrono::steady_clock::now();
+            xch->trace_timeline(s->ev[0], buf);
+        }
         if (flags & IPCFP_SHARDED_UNION_TO_HOST) {
-            box->union_host = PinnedArray(s->pool, r.n_union_cids * 38 + 64);
-            if (r.n_union_cids) IPCFP_CUDA(cudaMemcpyAsync(box->union_host.p, union_dev, r.n_union_cids * 38, cudaMemcpyDeviceToHost, st));
+            box->union_host = PinnedArray(s->pool, r.n_union_part * 38 + 64);
+            if (r.n_union_part) IPCFP_CUDA(cudaMemcpyAsync(box->union_host.p, union_dev, r.n_union_part * 38, cudaMemcpyDeviceToHost, st));
             IPCFP_CUDA(cudaStreamSynchronize(st));
             r.union_cids = box->union_host.as<uint8_t>();
         }

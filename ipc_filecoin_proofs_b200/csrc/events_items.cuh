@@ -102,7 +102,7 @@ static __device__ __noinline__ uint32_t walk_events(const StoreView* sp, uint32_
         uint32_t slot = bm_select(h.bm, f.k);
         int32_t child = store_lookup(s, p + h.links_off + 43 * f.k + 5);
         if (child < 0) { *detail = 0; return DC_MISSING; }
-        if (wbits) witness_mark(wbits, (uint32_t)child);
+        if (wbits) witness_mark(s, wbits, (uint32_t)child);
         uint64_t cbase = f.base + (uint64_t)slot * pow_sat(bw, lvl);
         f.k++;
         depth++;
@@ -156,7 +156,7 @@ static __device__ int receipts_get(const StoreView& s, uint32_t root_blk, uint64
         uint32_t k = bm_rank(h.bm, idx);
         int32_t child = store_lookup(s, p + h.links_off + 43 * k + 5);
         if (child < 0) { *detail = 0; return -(int)DC_MISSING; }
-        witness_mark(wbits, (uint32_t)child);
+        witness_mark(s, wbits, (uint32_t)child);
         p = store_block(s, (uint32_t)child, len);
         r = Rd(p, len);
         lvl--;
@@ -209,7 +209,7 @@ __device__ __forceinline__ void pass2_item(const Pass2Args& a, uint64_t t) {
     }
     int32_t root = store_lookup(a.store, a.events_roots + 38 * i);
     if (root < 0) { report_error(a.err, ST_PASS2, i, DC_MISSING, 0); return; }
-    witness_mark(a.wbits, (uint32_t)root);
+    witness_mark(a.store, a.wbits, (uint32_t)root);
     WalkOut wo{0, 0, false};
     EmitCtx ec;
     ec.proofs = out;

@@ -254,15 +254,16 @@ struct Comm {
     int device = 0;
     uint32_t world = 1, rank = 0;
     ncclComm_t cx = nullptr, cw = nullptr;   // exchange (execution order) / witness union: independent streams, independent communicators
-    cudaStream_t sx = nullptr;
+    cudaStream_t sx = nullptr, sw = nullptr;   // exchange / fetch stream (communicator cx); witness-union stream (communicator cw)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     cudaEvent_t tm[10] = {};                 // timing: exchange begin/end (sx), fetch begin/end, union begin/end (engine stream); [6..8] inside the exchange: bucketize | all-to-all | dedup done
     // grow-only device scratch (allocated during warm-up, then reused)
-    DevBuf<uint8_t> sendbuf, recvbuf, gather, merged, recs;
+    DevBuf<uint8_t> sendbuf, recvbuf, gather, merged, recs, part_send;
     DevBuf<unsigned long long> table, words, words2;
     DevBuf<uint32_t> bitmap, bitmap_sum, zeros, flags, starts;
-    DevBuf<uint64_t> zprefix, scan_tmp, req, req_all, ans, ans_sum, fscan;
+    DevBuf<uint64_t> zprefix, scan_tmp, req, req_pad, req_all, ans, ans_sum, fscan;
     DevBuf<uint32_t> pos_of;
+    DevBuf<unsigned long long> part_words;   // partitioned union: [0, W] piece bounds | [W+1, 2W+1) received piece lengths | [n_part, overflow] | the same of all ranks
     PinnedBuf<uint64_t> host;                // mapped: H0 / H2 read-backs
     ~Comm() {
         cudaSetDevice(device);
@@ -274,6 +275,7 @@ struct Comm {
         if (ev_c) cudaEventDestroy(ev_c);
         for (auto& e : tm) if (e) cudaEventDestroy(e);
         if (sx) cudaStreamDestroy(sx);
+        if (sw) cudaStreamDestroy(sw);
     }
 };
 
@@ -293,6 +295,7 @@ Comm* comm_init(const uint8_t* id128, uint32_t world, uint32_t rank, int device)
         int lo_p = 0, hi_p = 0;
         IPCFP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
         IPCFP_CUDA(cudaStreamCreateWithPriority(&c->sx, cudaStreamNonBlocking, hi_p));
+        IPCFP_CUDA(cudaStreamCreateWithPriority(&c->sw, cudaStreamNonBlocking, hi_p));
     }
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     IPCFP_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
@@ -536,35 +539,37 @@ __device__ __forceinline__ int rec_cmp(const RawCid& a, const RawCid& b) {
 }
 __device__ __forceinline__ uint32_t rec_bucket(const RawCid& a) { return (uint32_t)((a.w[0] & 0xff) << 8 | ((a.w[0] >> 8) & 0xff)); }
 #define MERGE_BUCKETS 65536u
-// starts[b][B] = first index of list b whose bucket is >= B (B = 0..65536); lists are sorted, so every element fills the gap it closes
-__global__ void k_merge_starts(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap, uint32_t* starts) {
+// starts[b][B - b0] = first index of list b whose bucket is >= B (B = b0..b0+nb); lists are sorted and hold buckets of [b0, b0+nb) only,
+// so every element fills the gap it closes
+__global__ void k_merge_starts(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap, uint32_t* starts,
+                               uint32_t b0, uint32_t nb) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (uint64_t)world * cap) return;
     uint32_t b = (uint32_t)(g / cap);
     uint64_t k = g % cap, n = counts[b];
-    uint32_t* st = starts + (uint64_t)b * (MERGE_BUCKETS + 1);
-    if (n == 0) { if (k == 0) for (uint32_t B = 0; B <= MERGE_BUCKETS; B++) st[B] = 0; return; }
+    uint32_t* st = starts + (uint64_t)b * (nb + 1);
+    if (n == 0) { if (k == 0) for (uint32_t B = 0; B <= nb; B++) st[B] = 0; return; }
     if (k >= n) return;
     const RawCid* L = lists + (uint64_t)b * cap;
-    uint32_t Bk = rec_bucket(L[k]);
-    uint32_t from = k == 0 ? 0 : rec_bucket(L[k - 1]) + 1;
+    uint32_t Bk = rec_bucket(L[k]) - b0;
+    uint32_t from = k == 0 ? 0 : rec_bucket(L[k - 1]) - b0 + 1;
     for (uint32_t B = from; B <= Bk; B++) st[B] = (uint32_t)k;
-    if (k == n - 1) for (uint32_t B = Bk + 1; B <= MERGE_BUCKETS; B++) st[B] = (uint32_t)n;
+    if (k == n - 1) for (uint32_t B = Bk + 1; B <= nb; B++) st[B] = (uint32_t)n;
 }
 // position of every element in the merged (still non-unique) order + is it the first of its CID
 __global__ void k_merge_rank(const RawCid* __restrict__ lists, const uint64_t* __restrict__ counts, uint32_t world, uint64_t cap,
-                             const uint32_t* __restrict__ starts, uint32_t* pos_of, uint32_t* keep) {
+                             const uint32_t* __restrict__ starts, uint32_t* pos_of, uint32_t* keep, uint32_t b0, uint32_t nb) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (uint64_t)world * cap) return;
     uint32_t b = (uint32_t)(g / cap);
     uint64_t k = g % cap;
     if (k >= counts[b]) return;
     const RawCid e = lists[(uint64_t)b * cap + k];
-    const uint32_t B = rec_bucket(e);
+    const uint32_t B = rec_bucket(e) - b0;
     uint64_t pos = 0;
     bool dup = false;
     for (uint32_t q = 0; q < world; q++) {
-        const uint32_t* st = starts + (uint64_t)q * (MERGE_BUCKETS + 1);
+        const uint32_t* st = starts + (uint64_t)q * (nb + 1);
         uint32_t s0 = st[B], s1 = st[B + 1];
         pos += s0;
         if (q == b) { pos += k - s0; continue; }
@@ -594,6 +599,42 @@ __global__ void k_merge_emit38(const RawCid* __restrict__ lists, const uint64_t*
     for (int q = 0; q < 32; q++) o[6 + q] = (uint8_t)(c.w[q >> 3] >> (8 * (q & 7)));
 }
 
+// ---- partitioned union: rank r owns the CIDs whose bucket (first two digest bytes) lies in [part_lo(r), part_lo(r+1))
+__host__ __device__ __forceinline__ uint32_t part_lo(uint32_t r, uint32_t world) { return (uint32_t)(((uint64_t)r * MERGE_BUCKETS + world - 1) / world); }
+// One CTA: bounds[r] = first index of the sorted local list whose bucket is >= part_lo(r) (r = 0..world); the header record of piece r
+// in the send buffer (piece stride = cap + 1 records) receives min(piece length, cap); *overflow = 1 when a piece does not fit.
+__global__ void k_part_bounds(const RawCid* __restrict__ list, uint64_t n, uint32_t world, uint64_t cap, uint64_t* bounds, RawCid* send, unsigned long long* overflow) {
+    __shared__ uint64_t b[1025];
+    for (uint32_t r = threadIdx.x; r <= world; r += blockDim.x) {
+        const uint32_t want = part_lo(r, world);
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (rec_bucket(list[mid]) < want) lo = mid + 1; else hi = mid; }
+        b[r] = r == world ? n : lo;
+        bounds[r] = b[r];
+    }
+    if (threadIdx.x == 0) *overflow = 0;
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < world; r += blockDim.x) {
+        const uint64_t cnt = b[r + 1] - b[r];
+        RawCid h{};
+        h.w[0] = cnt < cap ? cnt : cap;
+        send[(uint64_t)r * (cap + 1)] = h;
+        if (cnt > cap) *overflow = 1;
+    }
+}
+// entry i of the sorted local list → its place in the piece of the rank that owns its bucket
+__global__ void k_part_pack(const RawCid* __restrict__ list, uint64_t n, uint32_t world, uint64_t cap, const uint64_t* __restrict__ bounds, RawCid* send) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawCid e = list[i];
+    const uint32_t dst = (uint32_t)(((uint64_t)rec_bucket(e) * world) >> 16);
+    const uint64_t j = i - bounds[dst];
+    if (j < cap) send[(uint64_t)dst * (cap + 1) + 1 + j] = e;
+}
+// piece lengths out of the received headers
+__global__ void k_part_counts(const RawCid* __restrict__ recv, uint32_t world, uint64_t cap, uint64_t* counts) {
+    for (uint32_t r = threadIdx.x; r < world; r += blockDim.x) counts[r] = recv[(uint64_t)r * (cap + 1)].w[0];
+}
 }  // namespace ipcfp
 
 // ------------------------------------------------------------------------------------------ host side of the protocol
@@ -624,6 +665,8 @@ static void run_all_gather_host(Comm* c, const uint64_t* mine, uint32_t k, uint6
 }
 
 uint64_t ShardExchange::host_word(uint32_t i) const { return s->host_words.p[i]; }
+cudaStream_t ShardExchange::stream() const { return c->sx; }
+cudaStream_t ShardExchange::union_stream() const { return c->sw; }
 ShardExchange::ShardExchange(Comm* comm, Store* store, uint64_t lo_, uint64_t hi_) : c(comm), s(store), lo(lo_), hi(hi_) {
     if (c->device != s->device) throw Error(IPCFP_ERR_INVALID_ARG, "communicator and store are bound to different devices");
     if (c->world > 255) throw Error(IPCFP_ERR_UNSUPPORTED, "world too large");
@@ -743,7 +786,7 @@ void ShardExchange::start_exchange(const void* seg_dev, cudaEvent_t seg_ready) {
 void ShardExchange::positions_for(cudaStream_t st, const uint32_t* match_rel, uint64_t n_match, unsigned long long* n_exec_out) {
     IPCFP_CUDA(cudaStreamWaitEvent(st, c->ev_a, 0));
     IPCFP_CUDA(cudaMemcpyAsync(n_exec_out, n_exec_dev, 8, cudaMemcpyDeviceToDevice, st));
-    publish_words_from(s, overflow_dev, 300, 2);   // host_words[300] = exchange overflow flag, [301] = n_exec: read after the caller's next sync
+    publish_words_on(s, st, overflow_dev, 300, 2);   // host_words[300] = exchange overflow flag, [301] = n_exec: read after the next sync of that stream
     M = n_match;
     c->req.ensure(n_match + 64);
     if (n_match) {
@@ -785,9 +828,11 @@ void ShardExchange::fetch_and_patch(cudaStream_t st, ipcfp_event_proof* proofs_d
     c->req_all.ensure((uint64_t)W * M_max + 64);
     c->ans.ensure(((uint64_t)W * M_max + 8) * 5);
     c->ans_sum.ensure(((uint64_t)W * M_max + 8) * 5);
-    // pad this rank's request list to M_max with "nobody's position"
-    if (M_max > M) IPCFP_CUDA(cudaMemsetAsync(c->req.p + M, 0xff, (M_max - M) * 8, st));
-    IPCFP_NCCL(n->AllGather(c->req.p, c->req_all.p, M_max, ncclUint64, c->cx, st));
+    // this rank's request list, padded to M_max with "nobody's position" (req itself holds M entries: M_max was not known when it was sized)
+    c->req_pad.ensure(M_max + 64);
+    IPCFP_CUDA(cudaMemsetAsync(c->req_pad.p, 0xff, M_max * 8, st));
+    if (M) IPCFP_CUDA(cudaMemcpyAsync(c->req_pad.p, c->req.p, M * 8, cudaMemcpyDeviceToDevice, st));
+    IPCFP_NCCL(n->AllGather(c->req_pad.p, c->req_all.p, M_max, ncclUint64, c->cx, st));
     const uint64_t total = (uint64_t)W * M_max;
     k_fetch_positions<<<div_up(total, 256), 256, 0, st>>>(seg, nseg, pos0, c->req_all.p, total, (RawCid*)c->ans.p); IPCFP_LAUNCH_CHECK();
     IPCFP_NCCL(n->AllReduce(c->ans.p, c->ans_sum.p, total * 5, ncclUint64, ncclSum, c->cx, st));
@@ -818,8 +863,8 @@ void ShardExchange::witness_union(cudaStream_t st, const uint8_t* cids_dev, uint
     uint64_t* counts = (uint64_t*)(c->words2.p + 2600);   // per-rank list lengths, picked out of the H2 records by agree_results
     IPCFP_CUDA(cudaMemsetAsync(c->flags.p, 0, (total_cap + 64) * 4, st));
     const unsigned g = div_up(total_cap, 256);
-    k_merge_starts<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p); IPCFP_LAUNCH_CHECK();
-    k_merge_rank<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p, c->pos_of.p, c->flags.p); IPCFP_LAUNCH_CHECK();
+    k_merge_starts<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p, 0, MERGE_BUCKETS); IPCFP_LAUNCH_CHECK();
+    k_merge_rank<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->starts.p, c->pos_of.p, c->flags.p, 0, MERGE_BUCKETS); IPCFP_LAUNCH_CHECK();
     uint64_t total_listed = 0;
     for (uint32_t r = 0; r < W; r++) total_listed += nw_all[r];
     unsigned long long* n_union = c->words2.p + 3000;
@@ -827,6 +872,63 @@ void ShardExchange::witness_union(cudaStream_t st, const uint8_t* cids_dev, uint
     k_merge_emit38<<<g, 256, 0, st>>>((const RawCid*)c->gather.p, counts, W, capw, c->pos_of.p, c->flags.p, c->fscan.p, c->merged.p); IPCFP_LAUNCH_CHECK();
     *out_dev = c->merged.p;
     IPCFP_CUDA(cudaMemcpyAsync(n_out_dev_word, n_union, 8, cudaMemcpyDeviceToDevice, st));
+    IPCFP_CUDA(cudaEventRecord(c->tm[5], st));
+}
+// W, partitioned: the union is left DISTRIBUTED — rank r ends up with the sorted, duplicate-free CIDs whose first two digest bytes
+// fall into its 1/world share of the 65 536 buckets, so the concatenation of the partitions in rank order is the BTreeSet order. Every
+// rank sends each peer the piece of its sorted list that belongs to it and merges the `world` sorted pieces it receives: bytes on the
+// wire and merge work per rank are those of about TWO shard lists, whatever the world size (the all-gather variant above moves and
+// merges `world` lists on every rank). Pieces travel in fixed-size slots of `cap` records behind a count header, so that no size has
+// to come back to the host in the middle of the protocol; a piece that does not fit raises this rank's overflow word, every rank
+// sees every word after the call's last synchronisation, and the caller repeats the union with cap = the longest list (cannot
+// overflow). No host synchronisation inside.
+uint64_t ShardExchange::union_piece_cap(bool cannot_overflow) const {
+    const uint32_t W = c->world;
+    if (cannot_overflow) return nw_max + 1;
+    if (const char* e = getenv("IPCFP_UNION_CAP")) return (uint64_t)std::max(1, atoi(e));   // tests: force the overflow path
+    return std::min<uint64_t>(nw_max + 1, 2 * ((nw_max + W - 1) / W) + 1024);
+}
+void ShardExchange::witness_union_partitioned(cudaStream_t st, const uint8_t* cids_dev, uint64_t n_local, uint64_t cap, uint8_t** out_dev, uint32_t host_word_first) {
+    NcclApi* n = nccl_api();
+    const uint32_t W = c->world, me = c->rank;
+    IPCFP_CUDA(cudaEventRecord(c->tm[4], st));
+    const uint64_t stride = cap + 1, total_cap = (uint64_t)W * stride;
+    const uint32_t b0 = part_lo(me, W), nb = part_lo(me + 1, W) - b0;
+    c->recs.ensure((n_local + 1) * 40 + 64);
+    c->part_send.ensure(total_cap * 40 + 64);
+    c->gather.ensure(total_cap * 40 + 64);
+    c->part_words.ensure(4ull * W + 16);
+    c->starts.ensure((uint64_t)W * (nb + 1) + 64);
+    c->pos_of.ensure(total_cap + 64);
+    c->flags.ensure(total_cap + 64);
+    c->fscan.ensure(total_cap + 64);
+    c->merged.ensure(total_cap * 38 + 64);
+    c->scan_tmp.ensure(scan_scratch_elems(total_cap + 64) + 64);
+    unsigned long long* pw = c->part_words.p;
+    unsigned long long *bounds_d = pw, *col_d = pw + W + 1, *mine_d = pw + 2 * W + 2 /* [n_part, overflow] */, *all_d = pw + 2 * W + 4 /* 2 words per rank */;
+    RawCid* send = (RawCid*)c->part_send.p;
+    RawCid* recv = (RawCid*)c->gather.p;
+    k_cids_to_recs<<<div_up(n_local + 1, 256), 256, 0, st>>>(cids_dev, n_local, n_local + 1, (RawCid*)c->recs.p); IPCFP_LAUNCH_CHECK();
+    k_part_bounds<<<1, 256, 0, st>>>((const RawCid*)c->recs.p, n_local, W, cap, (uint64_t*)bounds_d, send, mine_d + 1); IPCFP_LAUNCH_CHECK();
+    if (n_local) { k_part_pack<<<div_up(n_local, 256), 256, 0, st>>>((const RawCid*)c->recs.p, n_local, W, cap, (const uint64_t*)bounds_d, send); IPCFP_LAUNCH_CHECK(); }
+    IPCFP_NCCL(n->GroupStart());
+    for (uint32_t r = 0; r < W; r++) {
+        IPCFP_NCCL(n->Send(send + (uint64_t)r * stride, stride * 40, ncclUint8, (int)r, c->cw, st));
+        IPCFP_NCCL(n->Recv(recv + (uint64_t)r * stride, stride * 40, ncclUint8, (int)r, c->cw, st));
+    }
+    IPCFP_NCCL(n->GroupEnd());
+    IPCFP_CUDA(cudaMemsetAsync(c->flags.p, 0, (total_cap + 64) * 4, st));
+    k_part_counts<<<1, 256, 0, st>>>(recv, W, cap, (uint64_t*)col_d); IPCFP_LAUNCH_CHECK();
+    const unsigned g = div_up(total_cap, 256);
+    const RawCid* lists = recv + 1;   // piece r's entries start one record behind its header: same stride
+    k_merge_starts<<<g, 256, 0, st>>>(lists, (const uint64_t*)col_d, W, stride, c->starts.p, b0, nb); IPCFP_LAUNCH_CHECK();
+    k_merge_rank<<<g, 256, 0, st>>>(lists, (const uint64_t*)col_d, W, stride, c->starts.p, c->pos_of.p, c->flags.p, b0, nb); IPCFP_LAUNCH_CHECK();
+    exclusive_scan_u32(c->flags.p, c->fscan.p, total_cap, (uint64_t*)mine_d, c->scan_tmp.p, st);
+    k_merge_emit38<<<g, 256, 0, st>>>(lists, (const uint64_t*)col_d, W, stride, c->pos_of.p, c->flags.p, c->fscan.p, c->merged.p); IPCFP_LAUNCH_CHECK();
+    // [partition size, overflow] of all ranks → the store's mapped words [host_word_first, +2·world): read after the caller's next sync of this stream
+    IPCFP_NCCL(n->AllGather(mine_d, all_d, 2, ncclUint64, c->cw, st));
+    publish_words_on(s, st, all_d, host_word_first, 2 * W);
+    *out_dev = c->merged.p;
     IPCFP_CUDA(cudaEventRecord(c->tm[5], st));
 }
 void ShardExchange::timings(float* ms_exchange, float* ms_fetch, float* ms_union) const {
@@ -839,6 +941,12 @@ void ShardExchange::timings(float* ms_exchange, float* ms_fetch, float* ms_union
     }
     cudaEventElapsedTime(ms_fetch, c->tm[2], c->tm[3]);
     cudaEventElapsedTime(ms_union, c->tm[4], c->tm[5]);
+}
+// IPCFP_XCH_TRACE: where the protocol's stages sit on the call's own time axis (ms after `origin`, an event of the engine stream)
+void ShardExchange::trace_timeline(cudaEvent_t origin, const char* engine_part) const {
+    float t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], origin, c->tm[i]);
+    fprintf(stderr, "[ipcfp rank %u] timeline ms: %s | exchange %.3f-%.3f fetch %.3f-%.3f union %.3f-%.3f\n", c->rank, engine_part, t[0], t[1], t[2], t[3], t[4], t[5]);
 }
 
 }  // namespace ipcfp

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(128) k_storage_proofs(StorageArgs a) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= a.n || (threadIdx.x & 31)) return;
     Recorder rec{a.rec_list + t * REC_CAP, 0, a.wbits, false};
+    rec.rank_of = a.store.rank_of;
     ipcfp_storage_proof q;
     Fail f{0, 0};
     if (!storage_proof_one(a, t, rec, q, f)) { report_error(a.err, ST_STORAGE, t, f.code, f.detail); a.rec_n[t] = 0; return; }
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(128) k_read_slots(SlotArgs a) {
     if (a.per_warp) { if (threadIdx.x & 31) return; t >>= 5; }
     if (t >= a.n) return;
     Recorder rec{nullptr, 0, a.wbits, false};
+    rec.rank_of = a.store.rank_of;
     rec.strict_only = a.strict_only != 0;
     SlotValue sv;
     Fail f{0, 0};

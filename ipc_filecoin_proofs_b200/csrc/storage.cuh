@@ -20,8 +20,9 @@ struct Recorder {
     bool overflow;
     uint32_t hamt_nodes = 0, hamt_bytes = 0;   // HAMT nodes decoded through this recorder and their bytes (measurement: K5's algorithmic bytes)
     bool strict_only = false;                  // A/B switch (IPCFP_HAMT_STRICT=1): skip the fast node decoder
+    const uint32_t* rank_of = nullptr;         // StoreView::rank_of (witness bitmaps are indexed by Cid rank); nullptr = identity
     __device__ void note(uint32_t blk) {
-        if (wbits) witness_mark(wbits, blk);   // (the verifiers walk without recording)
+        if (wbits) witness_mark_rank(wbits, rank_of ? rank_of[blk] : blk);   // (the verifiers walk without recording)
         if (!list) return;
         for (uint32_t i = 0; i < n; i++) if (list[i] == blk) return;
         if (n < REC_CAP) list[n++] = blk; else overflow = true;

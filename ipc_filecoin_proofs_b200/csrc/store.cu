@@ -83,7 +83,7 @@ void PinnedPool::give(void* p, size_t cap) {
 struct DevPoolEntry { int device; void* p; size_t cap; };
 static std::mutex g_dp_mu;
 static std::vector<DevPoolEntry> g_dp;
-static const size_t DEV_POOL_MAX_ENTRIES = 24;
+static const size_t DEV_POOL_MAX_ENTRIES = 40;
 void* dev_pool_take(size_t bytes, size_t* cap_out) {
     int dev = 0;
     IPCFP_CUDA(cudaGetDevice(&dev));
@@ -206,6 +206,14 @@ __global__ void k_build_index(uint32_t n, const Digest* __restrict__ digests, co
     }
 }
 
+__global__ void k_iota(uint32_t* out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+__global__ void k_invert_perm(const uint32_t* __restrict__ perm, uint32_t n, uint32_t* inv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = i;
+}
 __global__ void k_build_recs(uint32_t n, const Digest* __restrict__ digests, const uint8_t* __restrict__ cls, const uint64_t* __restrict__ offsets,
                              const uint32_t* __restrict__ lengths, BlockRec* recs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,6 +251,11 @@ void publish_words_from(Store* s, const void* src_dev, uint32_t dst_first, uint3
     IPCFP_LAUNCH_CHECK();
 }
 
+void publish_words_on(Store* s, cudaStream_t stream, const void* src_dev, uint32_t dst_first, uint32_t n_words) {
+    k_publish<<<div_up(n_words, 64), 64, 0, stream>>>((const unsigned long long*)src_dev, (unsigned long long*)s->host_words.dev + dst_first, n_words);
+    IPCFP_LAUNCH_CHECK();
+}
+
 __global__ void k_lookup_one(StoreView v, const uint8_t* cid, int32_t* out) { out[0] = store_lookup(v, cid); }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -272,6 +285,7 @@ static void fill_view(Store* s) {
     v.blob = s->arena.p + 16;
     v.offsets = s->offsets.p; v.lengths = s->lengths.p; v.digests = s->digests.p; v.cls = s->cls.p; v.table = s->table.p;
     v.recs = s->recs.p;
+    v.rank_of = s->rank_of.p; v.block_at_rank = s->block_at_rank.p;
     v.mask = s->table.n - 1;
     v.n = (uint32_t)s->n;
     v.n_classes = (uint32_t)s->class_prefix.size();
@@ -312,7 +326,7 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     for (auto& e : s->ev) IPCFP_CUDA(cudaEventCreate(&e));
     cudaStream_t st = s->stream;
     s->dev_words.alloc_pooled(64);
-    host_words_take(device, s->host_words, 512);
+    host_words_take(device, s->host_words, 1024);
     {
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr); }
@@ -327,10 +341,12 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     s->digests.alloc_pooled(n + 1);
     s->cls.alloc_pooled(n + 1);
     s->recs.alloc_pooled(n + 1);
+    s->rank_of.alloc_pooled(n + 1);
+    s->block_at_rank.alloc_pooled(n + 1);
     uint64_t slots = 64;
     while (slots < 2 * n) slots <<= 1;
     s->table.alloc_pooled(slots);
-    DevBuf<uint8_t> cids_dev;
+    DevBuf<uint8_t> cids_dev, sort_ws;
     cids_dev.alloc_pooled(n * 38 + 16);
 
     // H2D. The CID array goes first so the index build overlaps the (much larger) blob copy.
@@ -399,6 +415,13 @@ Store* store_create(const uint8_t* cids, const uint64_t* offsets, const uint32_t
     }
     if (!n) { fill_view(s.get()); }
     if (n) {
+        // `Cid` Ord rank of every block (one sort per store, under the blob copy): witness bitmaps are indexed by rank, so that every
+        // later call reads its witness out of the bitmap already in BTreeSet<Cid> order
+        sort_ws.alloc_pooled(n * 4 + 256 + sort_by_cid_ws_bytes(n));   // released (to the device pool) when this function returns: after its final sync
+        uint32_t* iota = (uint32_t*)sort_ws.p;
+        k_iota<<<div_up(n, 256), 256, 0, st>>>(iota, (uint32_t)n); IPCFP_LAUNCH_CHECK();
+        sort_by_cid(s.get(), iota, s->block_at_rank.p, n, sort_ws.p + ((n * 4 + 255) & ~(uint64_t)255));
+        k_invert_perm<<<div_up(n, 256), 256, 0, st>>>(s->block_at_rank.p, (uint32_t)n, s->rank_of.p); IPCFP_LAUNCH_CHECK();
         k_build_recs<<<div_up(n, 256), 256, 0, st>>>((uint32_t)n, s->digests.p, s->cls.p, s->offsets.p, s->lengths.p, s->recs.p);
         IPCFP_LAUNCH_CHECK();
         k_build_index<<<div_up(n, 256), 256, 0, st>>>((uint32_t)n, s->digests.p, s->cls.p, (unsigned long long*)s->table.p, s->table.n - 1);

@@ -33,6 +33,11 @@ struct StoreView {
     uint32_t n;
     uint32_t n_classes;
     uint8_t class_prefix[IPCFP_MAX_CID_CLASSES][8];  // 6 significant bytes each
+    // Position of every block in `Cid` Ord among the blocks of this store, computed once at ingest, and its inverse. Witness bitmaps
+    // are indexed by RANK, so reading a bitmap in bit order yields the witness already in BTreeSet<Cid> order (no per-call sort).
+    // nullptr (host-side test stores) = identity.
+    const uint32_t* rank_of;
+    const uint32_t* block_at_rank;
 };
 
 #ifdef __CUDACC__
@@ -75,12 +80,17 @@ __device__ __forceinline__ const uint8_t* store_block(const StoreView& s, uint32
     len = __ldg(&q->len);
     return s.blob + __ldg(&q->off);
 }
-// RecordingBlockStore::get side effect: one bit per block
-__device__ __forceinline__ void witness_mark(uint32_t* wbits, uint32_t idx) {
-    uint32_t m = 1u << (idx & 31);
-    uint32_t* w = wbits + (idx >> 5);
+// RecordingBlockStore::get side effect: one bit per block, at the block's RANK in `Cid` Ord
+__device__ __forceinline__ void witness_mark_rank(uint32_t* wbits, uint32_t r) {
+    uint32_t m = 1u << (r & 31);
+    uint32_t* w = wbits + (r >> 5);
     if (!(*(volatile uint32_t*)w & m)) atomicOr(w, m);
 }
+__device__ __forceinline__ void witness_mark(const StoreView& s, uint32_t* wbits, uint32_t idx) {
+    witness_mark_rank(wbits, s.rank_of ? __ldg(s.rank_of + idx) : idx);
+}
+// identity ranks (host-side test stores only)
+__device__ __forceinline__ void witness_mark(uint32_t* wbits, uint32_t idx) { witness_mark_rank(wbits, idx); }
 #endif
 
 }  // namespace ipcfp

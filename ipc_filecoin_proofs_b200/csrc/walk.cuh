@@ -116,7 +116,7 @@ __device__ __forceinline__ void amt_item_expand(const ExpandArgs& a, uint64_t t,
                         if (d < a.cap) a.out.meta[d] = AMT_SENTINEL;
                     }
                     else {
-                        if (a.record) witness_mark(a.wbits, (uint32_t)child);
+                        if (a.record) witness_mark(a.store, a.wbits, (uint32_t)child);
                         if (d < a.cap) { a.out.blk[d] = (uint32_t)child; a.out.meta[d] = make_meta(amt, 0, level - 1); a.out.base[d] = base + (uint64_t)slot * pow_sat(3, level); }
                     }
                 } else {
@@ -214,7 +214,7 @@ __device__ __forceinline__ void amt_item_dense(const DenseArgs& a, const Frontie
         const uint32_t par = (round + 1) & 1;
         out.meta[d] = make_meta(amt, 0, level - 1); out.base[d] = cb;
         a.f_off[par][d] = __ldg(&rec->off); a.f_len[par][d] = __ldg(&rec->len);
-        if (a.record) witness_mark(a.wbits, (uint32_t)child);
+        if (a.record) witness_mark(a.store, a.wbits, (uint32_t)child);
     } else {
         const uint8_t* src = item + 5;
         RawCid c;

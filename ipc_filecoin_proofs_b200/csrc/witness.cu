@@ -6,8 +6,10 @@
 //   snapshot (after the message-AMT walk): bitmap → ordered index list A → block bytes gathered
 //            into a 16-byte-padded staging blob → D2H on a second stream while pass 1/2 run;
 //   finish   (after pass 2): B = bits set since the snapshot → gathered + copied behind A;
-//            radix sort of A∪B by (class rank, digest) → cids / offsets / lengths arrays.
-// The output keeps block bytes in arrival order and the (cid, offset, length) index in `Cid` order.
+//            A and B are both in `Cid` order already (the bitmap is indexed by the blocks' Cid RANK, computed once per store at
+//            ingest), so the merged position of an entry is its own position plus the number of the other list's bits below it:
+//            one emit kernel, no per-call sort → cids / offsets / lengths arrays.
+// The output keeps block bytes in arrival order (A then B) and the (cid, offset, length) index in `Cid` order.
 #include "engine.cuh"
 #include "prims.cuh"
 
@@ -66,28 +68,49 @@ __global__ void k_tie_fix(const uint32_t* __restrict__ idx, uint32_t* ord, uint6
     }
 }
 
-// ord (device, m entries) receives the permutation that sorts idx[] by CID
-static void sort_by_cid(Store* s, const uint32_t* idx_dev, uint32_t* ord, uint64_t m) {
+// ord (device, m entries) receives the permutation that sorts idx[] by CID (stable). Runs once per store, at ingest; the caller owns
+// the workspace (sort_by_cid_ws_bytes(m) bytes — from the device pool, not stream-ordered: a new store has a new stream).
+static inline size_t ws_round(size_t b) { return (b + 255) & ~(size_t)255; }
+size_t sort_by_cid_ws_bytes(uint64_t m) {
+    const unsigned nb = radix_blocks(m);
+    return 3 * ws_round(m * 4 + 64) + ws_round(((size_t)256 * nb + 256) * 4) + ws_round(((size_t)256 * nb + 256) * 8) +
+           ws_round((scan_scratch_elems((uint64_t)256 * nb) + 8) * 8);
+}
+void sort_by_cid(Store* s, const uint32_t* idx_dev, uint32_t* ord, uint64_t m, void* ws) {
     if (m == 0) return;
     cudaStream_t st = s->stream;
-    AsyncBuf<uint32_t> keys(m, st), keys_alt(m, st), vals_alt(m, st);
-    unsigned nb = radix_blocks(m);
-    AsyncBuf<uint32_t> hist((size_t)256 * nb + 256, st);
-    AsyncBuf<uint64_t> scan_tmp((size_t)256 * nb + 256, st), scratch(scan_scratch_elems((uint64_t)256 * nb) + 8, st);
+    const unsigned nb = radix_blocks(m);
+    uint8_t* w = (uint8_t*)ws;
+    uint32_t* keys = (uint32_t*)w; w += ws_round(m * 4 + 64);
+    uint32_t* keys_alt = (uint32_t*)w; w += ws_round(m * 4 + 64);
+    uint32_t* vals_alt = (uint32_t*)w; w += ws_round(m * 4 + 64);
+    uint32_t* hist = (uint32_t*)w; w += ws_round(((size_t)256 * nb + 256) * 4);
+    uint64_t* scan_tmp = (uint64_t*)w; w += ws_round(((size_t)256 * nb + 256) * 8);
+    uint64_t* scratch = (uint64_t*)w;
     ClassRanks cr{};
     for (size_t c = 0; c < s->class_rank.size(); c++) cr.r[c] = (uint8_t)s->class_rank[c];
-    k_digest_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->digests.p, keys.p, ord); IPCFP_LAUNCH_CHECK();
-    radix_sort_pairs(keys.p, ord, keys_alt.p, vals_alt.p, m, 32, hist.p, scan_tmp.p, scratch.p, st);
+    k_digest_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, m, s->digests.p, keys, ord); IPCFP_LAUNCH_CHECK();
+    radix_sort_pairs(keys, ord, keys_alt, vals_alt, m, 32, hist, scan_tmp, scratch, st);
     if (s->class_prefix.size() > 1) {
-        k_class_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, ord, m, s->cls.p, cr, keys.p); IPCFP_LAUNCH_CHECK();
-        radix_sort_pairs(keys.p, ord, keys_alt.p, vals_alt.p, m, 8, hist.p, scan_tmp.p, scratch.p, st);
+        k_class_keys<<<div_up(m, 256), 256, 0, st>>>(idx_dev, ord, m, s->cls.p, cr, keys); IPCFP_LAUNCH_CHECK();
+        radix_sort_pairs(keys, ord, keys_alt, vals_alt, m, 8, hist, scan_tmp, scratch, st);
     }
     k_tie_fix<<<div_up(m, 256), 256, 0, st>>>(idx_dev, ord, m, s->digests.p, s->cls.p, cr); IPCFP_LAUNCH_CHECK();
 }
 
-__global__ void k_padded_lengths(const uint32_t* __restrict__ idx, uint64_t m, const uint32_t* __restrict__ lengths, uint32_t* out) {
+// idx[] holds RANKS (bit positions of the witness bitmap); bar = StoreView::block_at_rank
+__global__ void k_padded_lengths(const uint32_t* __restrict__ idx, uint64_t m, const uint32_t* __restrict__ lengths, const uint32_t* __restrict__ bar, uint32_t* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) out[i] = (lengths[idx[i]] + 15u) & ~15u;
+    if (i < m) out[i] = (lengths[bar[idx[i]]] + 15u) & ~15u;
+}
+// Σ padded lengths of the late list (its length is only known on the device): out += …
+__global__ void k_sum_padded_dev(const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ count, uint64_t n_max, const uint32_t* __restrict__ lengths,
+                                 const uint32_t* __restrict__ bar, unsigned long long* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = (i < n_max && i < *count) ? (unsigned long long)((lengths[bar[idx[i]]] + 15u) & ~15u) : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 __global__ void k_andnot(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* out, uint64_t nwords) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,7 +124,7 @@ __global__ void __launch_bounds__(256) k_witness_copy(const uint32_t* __restrict
     uint32_t lane = threadIdx.x & 31;
     if (w >= m) return;
     uint32_t len;
-    const uint8_t* src = store_block(v, idx[w], len);
+    const uint8_t* src = store_block(v, v.block_at_rank[idx[w]], len);
     uint8_t* dst = out + offsets[w];
     if (((uintptr_t)src & 15) == 0) {
         uint32_t nv = (len + 15) >> 4;  // the arena is padded, reading the tail of the last 16 bytes is safe
@@ -112,16 +135,25 @@ __global__ void __launch_bounds__(256) k_witness_copy(const uint32_t* __restrict
         for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
     }
 }
-__global__ void k_witness_emit(const uint32_t* __restrict__ ord, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ offs, uint64_t m,
-                               uint64_t mA, uint64_t baseB, StoreView v, uint8_t* cids, uint64_t* out_offs, uint32_t* out_lens, uint32_t* out_idx) {
+// number of set bits of a bitmap below bit r (prefix = exclusive popcount prefix per word, as bitmap_to_indices leaves it)
+__device__ __forceinline__ uint32_t bits_below(const uint32_t* __restrict__ bits, const uint64_t* __restrict__ prefix, uint32_t r) {
+    return (uint32_t)prefix[r >> 5] + (uint32_t)__popc(bits[r >> 5] & ((1u << (r & 31)) - 1u));
+}
+// idx = [A: mA ranks ascending][B: m - mA ranks ascending], A and B disjoint. Entry i goes to its merged position f.
+__global__ void k_witness_emit(const uint32_t* __restrict__ idx, const uint64_t* __restrict__ offs, uint64_t m, uint64_t mA, uint64_t baseB,
+                               const uint32_t* __restrict__ bitsA, const uint64_t* __restrict__ prefixA, const uint32_t* __restrict__ bitsB,
+                               const uint64_t* __restrict__ prefixB, StoreView v, uint8_t* cids, uint64_t* out_offs, uint32_t* out_lens, uint32_t* out_idx) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    uint32_t p = ord[i];
-    uint32_t b = idx[p];
-    out_offs[i] = offs[p] + (p >= mA ? baseB : 0);
-    out_lens[i] = v.lengths[b];
-    out_idx[i] = b;
-    uint8_t* o = cids + 38 * i;
+    const uint32_t r = idx[i];
+    uint64_t f;
+    if (i < mA) f = i + (m > mA ? bits_below(bitsB, prefixB, r) : 0u);
+    else f = (i - mA) + bits_below(bitsA, prefixA, r);
+    const uint32_t b = v.block_at_rank[r];
+    out_offs[f] = offs[i] + (i >= mA ? baseB : 0);
+    out_lens[f] = v.lengths[b];
+    out_idx[f] = b;
+    uint8_t* o = cids + 38 * f;
     uint32_t c = v.cls[b];
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = v.class_prefix[c][k];
@@ -143,6 +175,7 @@ WitnessBuilder::WitnessBuilder(Store* store) : s(store) {
     plen.alloc(n + 64, st);
     bitsA.alloc(nwords + 8, st);
     word_prefix.alloc(nwords + 8, st);
+    word_prefixB.alloc(nwords + 8, st);
     scratch.alloc(scan_scratch_elems(std::max<uint64_t>(nwords, n)) + 8, st);
 }
 
@@ -156,9 +189,9 @@ __global__ void k_chunk_bounds(const uint64_t* __restrict__ offs, const unsigned
 }
 // padded length of every candidate slot of idx[] (the count is only known on the device: zero past it)
 __global__ void k_padded_lengths_dev(const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ count, uint64_t n_max,
-                                     const uint32_t* __restrict__ lengths, uint32_t* out) {
+                                     const uint32_t* __restrict__ lengths, const uint32_t* __restrict__ bar, uint32_t* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_max) out[i] = i < *count ? (lengths[idx[i]] + 15u) & ~15u : 0u;
+    if (i < n_max) out[i] = i < *count ? (lengths[bar[idx[i]]] + 15u) & ~15u : 0u;
 }
 // enqueue: bitmap → idx[0..mA), padded offsets; totals land in dev_words[8] (mA) and [9] (bytesA) — the caller
 // publishes both and syncs ONCE before start_copy
@@ -166,7 +199,7 @@ void WitnessBuilder::snapshot(const uint32_t* wbits) {
     unsigned long long* dw = s->dev_words.p;
     IPCFP_CUDA(cudaMemcpyAsync(bitsA.p, wbits, nwords * 4, cudaMemcpyDeviceToDevice, st));
     bitmap_to_indices(bitsA.p, s->n, idx.p, (uint64_t*)(dw + 8), word_prefix.p, scratch.p, st);
-    if (s->n) { k_padded_lengths_dev<<<div_up(s->n, 256), 256, 0, st>>>(idx.p, dw + 8, s->n, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK(); }
+    if (s->n) { k_padded_lengths_dev<<<div_up(s->n, 256), 256, 0, st>>>(idx.p, dw + 8, s->n, s->lengths.p, s->block_at_rank.p, plen.p); IPCFP_LAUNCH_CHECK(); }
     exclusive_scan_u32(plen.p, offs.p, s->n, (uint64_t*)(dw + 9), scratch.p, st);
     k_chunk_bounds<<<1, 1, 0, st>>>(offs.p, dw + 8, dw + 9, dw + 16); IPCFP_LAUNCH_CHECK();
     have_snapshot = true;
@@ -197,23 +230,24 @@ void WitnessBuilder::finish_enqueue(const uint32_t* wbits) {
     unsigned long long* dw = s->dev_words.p;
     bitsB.alloc(nwords + 8, st);
     k_andnot<<<div_up(nwords ? nwords : 1, 256), 256, 0, st>>>(wbits, bitsA.p, bitsB.p, nwords); IPCFP_LAUNCH_CHECK();
-    bitmap_to_indices(bitsB.p, s->n, idx.p + mA, (uint64_t*)(dw + 10), word_prefix.p, scratch.p, st);
+    bitmap_to_indices(bitsB.p, s->n, idx.p + mA, (uint64_t*)(dw + 10), word_prefixB.p, scratch.p, st);
+    // their padded bytes, so that the host learns both numbers with the caller's next synchronisation
+    IPCFP_CUDA(cudaMemsetAsync(dw + 11, 0, 8, st));
+    const uint64_t bound = s->n > mA ? s->n - mA : 0;
+    if (bound) { k_sum_padded_dev<<<div_up(bound, 256), 256, 0, st>>>(idx.p + mA, dw + 10, bound, s->lengths.p, s->block_at_rank.p, dw + 11); IPCFP_LAUNCH_CHECK(); }
 }
-void WitnessBuilder::finish(uint64_t mB_, WitnessOut& out, bool want_sorted_idx) {
-    finish_start(mB_, out, want_sorted_idx);
+void WitnessBuilder::finish(uint64_t mB_, uint64_t bytesB_, WitnessOut& out, bool want_sorted_idx) {
+    finish_start(mB_, bytesB_, out, want_sorted_idx);
     finish_join(out);
 }
-void WitnessBuilder::finish_start(uint64_t mB_, WitnessOut& out, bool want_sorted_idx) {
+void WitnessBuilder::finish_start(uint64_t mB_, uint64_t bytesB_, WitnessOut& out, bool want_sorted_idx) {
     mB = mB_;
+    bytesB = bytesB_;
     unsigned long long* dw = s->dev_words.p;
     uint64_t m = mA + mB;
-    bytesB = 0;
     if (mB) {
-        k_padded_lengths<<<div_up(mB, 256), 256, 0, st>>>(idx.p + mA, mB, s->lengths.p, plen.p); IPCFP_LAUNCH_CHECK();
+        k_padded_lengths<<<div_up(mB, 256), 256, 0, st>>>(idx.p + mA, mB, s->lengths.p, s->block_at_rank.p, plen.p); IPCFP_LAUNCH_CHECK();
         exclusive_scan_u32(plen.p, offs.p + mA, mB, (uint64_t*)(dw + 11), scratch.p, st);
-        publish_words(s, 11, 1);
-        IPCFP_CUDA(cudaStreamSynchronize(st));
-        bytesB = s->host_words.p[11];
     }
     if (bytesA + bytesB > host_cap) {  // rare: more late blocks than the slack — move to a bigger buffer
         IPCFP_CUDA(cudaStreamSynchronize(st2));
@@ -228,14 +262,15 @@ void WitnessBuilder::finish_start(uint64_t mB_, WitnessOut& out, bool want_sorte
         IPCFP_CUDA(cudaMemcpyAsync((uint8_t*)host_blob.p + bytesA, dblobB.p, bytesB, cudaMemcpyDeviceToHost, st));
     }
     // index arrays in Cid order
-    AsyncBuf<uint32_t> ord(m + 8, st), d_lens(m + 8, st), d_idx(m + 8, st);
+    AsyncBuf<uint32_t> d_lens(m + 8, st), d_idx(m + 8, st);
     AsyncBuf<uint64_t> d_offs(m + 8, st);
     AsyncBuf<uint8_t> d_cids(m * 38 + 64, st);
-    sort_by_cid(s, idx.p, ord.p, m);
     if (m) {
-        k_witness_emit<<<div_up(m, 256), 256, 0, st>>>(ord.p, idx.p, offs.p, m, mA, bytesA, s->view, d_cids.p, d_offs.p, d_lens.p, d_idx.p);
+        k_witness_emit<<<div_up(m, 256), 256, 0, st>>>(idx.p, offs.p, m, mA, bytesA, bitsA.p, word_prefix.p, bitsB.p, word_prefixB.p, s->view, d_cids.p, d_offs.p,
+                                                       d_lens.p, d_idx.p);
         IPCFP_LAUNCH_CHECK();
     }
+    IPCFP_CUDA(cudaEventRecord(s->ev[6], st));   // the sorted CID list exists on the device (the multi-GPU union waits for this, not for the copies below)
     out.n = m;
     out.blob_size = bytesA + bytesB;
     out.cids = PinnedArray(s->pool, m * 38 + 64);
@@ -265,7 +300,7 @@ void materialize_witness(Store* s, const uint32_t* wbits_dev, WitnessOut& out) {
     publish_words(s, 8, 2);
     IPCFP_CUDA(cudaStreamSynchronize(s->stream));
     wb.start_copy(s->host_words.p[8], s->host_words.p[9], s->host_words.p[8], s->host_words.p[9]);   // one part
-    wb.finish(0, out, true);
+    wb.finish(0, 0, out, true);
 }
 
 }  // namespace ipcfp

@@ -184,9 +184,16 @@ def nccl_worker(rank, world, port, q):
         L = api.lib()
         comm = PL.ShardedComm.from_torch_group(L, dist, dev)
         for params in (PARAMS, dict(seed=5, n_receipts=20011, events_per_receipt=8, match_ppm=2000, dup_msgs=0, n_parents=2),
-                       dict(seed=9, n_receipts=257, events_per_receipt=3, match_ppm=500000, dup_msgs=40, n_parents=5)):
+                       dict(seed=9, n_receipts=257, events_per_receipt=3, match_ppm=500000, dup_msgs=40, n_parents=5),
+                       # uneven shards: rank 0 owns 70 % of the receipts, so the per-rank match counts differ by hundreds (request padding)
+                       dict(seed=11, n_receipts=4001, events_per_receipt=4, match_ppm=300000, dup_msgs=25, n_parents=3, skew=True)):
+            params = dict(params)
+            skew = params.pop("skew", False)
             N = params["n_receipts"]
             bounds = [N * r // world for r in range(world + 1)]
+            if skew and world > 1:
+                head = N * 7 // 10
+                bounds = [0] + [head + (N - head) * r // (world - 1) for r in range(world)]
             lo, hi = bounds[rank], bounds[rank + 1]
             full = synth.Tipset(synth.default_params(**params))
             shard = synth.Tipset(synth.default_params(shard_lo=lo, shard_hi=hi, **params)) if world > 1 else full
@@ -198,14 +205,31 @@ def nccl_worker(rank, world, port, q):
             d, keep = A.make_tipset_desc(shard)
             tip = C.c_void_p()
             assert L.ipcfp_tipset_upload(store._h, C.byref(d), C.byref(tip)) == 0
-            for rep in range(2):                           # the second call reuses every buffer of the communicator
-                out = comm.generate_event_proof(store._h, tip, spec, bounds, A.SHARDED_UNION_TO_HOST)
+            for rep in range(3):                           # later calls reuse every buffer of the communicator
+                # rep 0, 2: the witness union stays distributed (this rank's partition); rep 1: the whole list on every rank
+                full_union = rep == 1
+                if rep == 2:
+                    os.environ["IPCFP_UNION_CAP"] = "3"      # pieces of 3 CIDs: the first attempt overflows on every rank, the repeat must deliver
+                else:
+                    os.environ.pop("IPCFP_UNION_CAP", None)
+                out = comm.generate_event_proof(store._h, tip, spec, bounds, A.SHARDED_UNION_TO_HOST | (A.SHARDED_UNION_FULL if full_union else 0))
                 r = out.contents
                 got = A.event_result_from_c(r)
-                n_union = int(r.n_union_cids)
-                union = np.frombuffer((C.c_uint8 * (n_union * 38)).from_address(r.union_cids), dtype=np.uint8).reshape(-1, 38).copy() if n_union else np.zeros((0, 38), np.uint8)
+                n_union, n_part, part_first = int(r.n_union_cids), int(r.n_union_part), int(r.union_part_first)
+                union = np.frombuffer((C.c_uint8 * (n_part * 38)).from_address(r.union_cids), dtype=np.uint8).reshape(-1, 38).copy() if n_part else np.zeros((0, 38), np.uint8)
                 totals = (int(r.total_matching), int(r.total_proofs), int(r.n_exec))
                 L.ipcfp_event_result_free(out)
+                assert n_union == len(exp.witness.cids), (n_union, len(exp.witness.cids))
+                if full_union:
+                    assert (part_first, n_part) == (0, n_union)
+                else:
+                    parts = [None] * world
+                    dist.all_gather_object(parts, (part_first, union.tobytes()))
+                    assert [p[0] for p in parts] == [sum(len(q[1]) // 38 for q in parts[:k]) for k in range(world)], [p[0] for p in parts]
+                    if world > 1 and n_union > 64 * world:
+                        assert all(len(p[1]) for p in parts), "a partition is empty: CIDs are not spread over the ranks"
+                    union = np.frombuffer(b"".join(p[1] for p in parts), dtype=np.uint8).reshape(-1, 38)
+                os.environ.pop("IPCFP_UNION_CAP", None)
                 assert totals == (len(exp.matching), len(exp.proofs), exp.n_exec), (totals, len(exp.matching), len(exp.proofs), exp.n_exec)
                 assert got.matching.tolist() == exp_shard.matching.tolist()
                 mine = [p for p in exp.proofs if lo <= p.exec_index < hi]
@@ -255,7 +279,7 @@ def nccl_worker(rank, world, port, q):
             tp = C.c_void_p()
             assert L.ipcfp_tipset_upload(st_._h, C.byref(d_), C.byref(tp)) == 0
             try:
-                o = comm.generate_event_proof(st_._h, tp, spec, bounds, A.SHARDED_UNION_TO_HOST)
+                o = comm.generate_event_proof(st_._h, tp, spec, bounds, A.SHARDED_UNION_TO_HOST | A.SHARDED_UNION_FULL)
                 r_ = o.contents
                 g = A.event_result_from_c(r_)
                 nu = int(r_.n_union_cids)
