@@ -348,14 +348,16 @@ def run_engine(args, world, rank, local):
 
     # ---- resident timing
     log("store + tipset resident; warm-up")
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
+    # the clock sampler starts BEFORE the warm-up steps, so that nothing idles between the last warm-up step and the timed region
+    # (a 0.3 s pause there let the GPUs and NCCL's proxy threads fall asleep: the first timed step then took up to 1.6x a normal one)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()   # every rank enters the timed region together (rank 0 just waited for the sampler)
+    barrier()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()   # every rank enters the timed region together
     launches0 = api.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase = {k: [] for k in ("total", "txamt", "pass1", "pass2", "witness", "exchange", "fetch", "union")}
