@@ -209,13 +209,14 @@ def raw_positions_of(exec_indices, dups_sorted):
         p = q
 
 
-def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices, seg_counts=None, need_counts=None):
+def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indices, seg_counts=None, need_counts=None, bucket_cap=None):
     """Runs the distributed first-seen dedup and returns (n_exec, (sorted exec indices, their 40-byte records)).
 
     seg_ptr/nseg: this rank's slice of the raw message list (device pointer for CudaShardOps);
     matching: the rank's matching receipt indices (for the MISSING_EXEC check, events/generator.rs:244-246);
     proof_exec_indices: exec indices whose message CID the rank's proofs need;
-    seg_counts: per-rank slice lengths if the caller already gathered them."""
+    seg_counts: per-rank slice lengths if the caller already gathered them; bucket_cap: first bucket capacity to try (the same on every
+    rank; default 1.25·max/world + 1024, doubled on every rank together while some rank's split does not fit)."""
     world, rank = coll.world, coll.rank
     if seg_counts is None:
         with _Phase("x.counts"):
@@ -223,16 +224,35 @@ def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indic
     counts = np.asarray(seg_counts, dtype=np.int64)
     pos0 = int(counts[:rank].sum())
     nraw = int(counts.sum())
-    cap = int(counts.max()) // world + int(counts.max()) // (4 * world) + 1024
-    with _Phase("x.bucketize"):
-        send, cnt = ops.bucketize(seg_ptr, nseg, pos0, world, cap)
-    with _Phase("x.count_matrix"):
-        cnt_matrix = coll.all_gather_i64(cnt.view(np.int64))          # [sender, owner]
+    # A rank-local failure of a device helper must not leave the other ranks waiting in the next collective: every helper's status
+    # rides on the collective that follows it, and all ranks continue, retry or raise TOGETHER (first failing rank's error).
+    FAIL = -1
+    cap = int(bucket_cap) if bucket_cap else int(counts.max()) // world + int(counts.max()) // (4 * world) + 1024
+    while True:
+        err = None
+        with _Phase("x.bucketize"):
+            try:
+                send, cnt = ops.bucketize(seg_ptr, nseg, pos0, world, cap)
+                row = np.asarray(cnt).view(np.int64)
+            except A.IpcfpError as e:
+                err, send, row = e, None, np.full(world, FAIL, dtype=np.int64)
+        with _Phase("x.count_matrix"):
+            cnt_matrix = coll.all_gather_i64(row)                       # [sender, owner]; a row of -1 = that sender's bucketize failed
+        failed = [r for r in range(world) if int(cnt_matrix[r, 0]) == FAIL]
+        if not failed:
+            break
+        if cap >= int(counts.max()) + 1:                                 # even one bucket holding a whole slice did not fit: not a capacity problem
+            raise err if err is not None else A.IpcfpError(A.ERR_INVALID_ARG, f"exec bucketize failed on rank {failed[0]}", failed[0])
+        cap = min(2 * cap, int(counts.max()) + 1)                        # skewed CID→owner split: every rank retries with larger buckets
     recv_counts = cnt_matrix[:, rank].astype(np.uint64)
     with _Phase("x.all_to_all"):
         recv = coll.all_to_all_bytes(send, cap * ENTRY)
     with _Phase("x.dedup"):
-        dups_local = ops.dedup(recv, recv_counts, world, cap)
+        dedup_err = None
+        try:
+            dups_local = ops.dedup(recv, recv_counts, world, cap)
+        except A.IpcfpError as e:
+            dedup_err, dups_local = e, np.zeros(0, dtype=np.uint64)
     # ONE fixed-size all-gather carries, per rank, the duplicate positions it found as an owner and the exec indices its
     # proofs need: [n_dups, n_need, dups…(DUP_CAP), need…(capq)]. Every rank then knows D and every rank's requests, so the
     # raw positions of ALL requests are derived locally (no second round trip). The rare overflow of the duplicate list
@@ -246,12 +266,15 @@ def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indic
     capq = int(req_counts.max()) if len(req_counts) else 0
     with _Phase("x.dups_gather"):
         pad = np.zeros(2 + DUP_CAP + capq, dtype=np.int64)
-        pad[0] = len(dups_local)
+        pad[0] = FAIL if dedup_err is not None else len(dups_local)
         pad[1] = len(need)
         k = min(len(dups_local), DUP_CAP)
         pad[2:2 + k] = dups_local[:k].view(np.int64)
         pad[2 + DUP_CAP:2 + DUP_CAP + len(need)] = need.view(np.int64)
         allp = coll.all_gather_i64(pad)
+        bad_ranks = [r for r in range(world) if int(allp[r, 0]) == FAIL]
+        if bad_ranks:
+            raise dedup_err if dedup_err is not None else A.IpcfpError(A.ERR_INVALID_ARG, f"exec dedup failed on rank {bad_ranks[0]}", bad_ranks[0])
         if int(allp[:, 0].max()) > DUP_CAP:
             dups, _ = coll.all_gather_var_u64(dups_local)
         else:
@@ -268,16 +291,25 @@ def resolve_execution_order(ops, coll, seg_ptr, nseg, matching, proof_exec_indic
     req_all = np.concatenate([raw_positions_of(np.minimum(allp[r, 2 + DUP_CAP:2 + DUP_CAP + int(allp[r, 1])].view(np.uint64), last), D)
                               for r in range(world)]) if capq else np.zeros(0, np.uint64)
     with _Phase("x.fetch"):
-        ans = ops.fetch(seg_ptr, nseg, pos0, req_all)                # zeros where another rank owns the position
+        fetch_err = None
+        try:
+            ans = ops.fetch(seg_ptr, nseg, pos0, req_all)            # zeros where another rank owns the position
+        except A.IpcfpError as e:
+            fetch_err, ans = e, np.zeros((len(req_all), REC), dtype=np.uint8)
     with _Phase("x.ans_reduce"):
-        verdict = np.zeros(world, dtype=np.int64)
+        verdict = np.zeros(2 * world, dtype=np.int64)                # [first missing exec index per rank | fetch failed per rank]
         verdict[rank] = my_bad
+        verdict[world + rank] = 1 if fetch_err is not None else 0
         flat = np.concatenate([np.ascontiguousarray(ans).reshape(-1).view(np.int64), verdict])
         red = coll.all_reduce_sum_i64(flat)
-        first_bad = int(red[len(red) - world:].min())
+        tail = red[len(red) - 2 * world:]
+        if tail[world:].any():
+            r_bad = int(np.flatnonzero(tail[world:])[0])
+            raise fetch_err if fetch_err is not None else A.IpcfpError(A.ERR_INVALID_ARG, f"exec fetch failed on rank {r_bad}", r_bad)
+        first_bad = int(tail[:world].min())
         if first_bad != NO_BAD:
             raise A.IpcfpError(A.ERR_MISSING_EXEC, "Missing message at index", first_bad)
-        ans = red[:len(red) - world].view(np.uint8).reshape(-1, REC)
+        ans = red[:len(red) - 2 * world].view(np.uint8).reshape(-1, REC)
     start = int(req_counts[:rank].sum())
     mine = ans[start:start + len(need)]
     return n_exec, (need, mine)

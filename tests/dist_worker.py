@@ -119,6 +119,37 @@ def cpu_worker(rank, world, port, q):
             raise AssertionError("expected MISSING_EXEC")
         except A.IpcfpError as e:
             assert e.status == A.ERR_MISSING_EXEC and e.index == 10 ** 9
+        # rank-local helper failures are agreed, not left to hang the peers: a bucketize that reports 'bucket capacity too
+        # small' on ONE rank makes every rank retry with larger buckets; a dedup / fetch failure on one rank raises on all of them
+        class Flaky(NumpyShardOps):
+            def __init__(self, fail_rank, what):
+                self.fail_rank, self.what, self.calls = fail_rank, what, 0
+
+            def bucketize(self, seg, nseg, pos0, world, cap):
+                self.calls += 1
+                if self.what == "bucketize" and rank == self.fail_rank and self.calls == 1:
+                    raise A.IpcfpError(A.ERR_INVALID_ARG, "bucket capacity too small", 0)
+                return super().bucketize(seg, nseg, pos0, world, cap)
+
+            def dedup(self, recv, counts, world, cap):
+                if self.what == "dedup" and rank == self.fail_rank:
+                    raise A.IpcfpError(A.ERR_INVALID_ARG, "duplicate list capacity too small", 0)
+                return super().dedup(recv, counts, world, cap)
+
+            def fetch(self, seg, nseg, pos0, req):
+                if self.what == "fetch" and rank == self.fail_rank:
+                    raise A.IpcfpError(A.ERR_INVALID_ARG, "fetch failed", 0)
+                return super().fetch(seg, nseg, pos0, req)
+
+        fl = Flaky(1, "bucketize")
+        n2, _ = PL.resolve_execution_order(fl, coll, seg, len(seg), res.matching, [p.exec_index for p in res.proofs], bucket_cap=len(raw) // world)
+        assert n2 == exp.n_exec and fl.calls == 2, (n2, fl.calls)          # both ranks went round twice
+        for what, fr in (("dedup", 0), ("fetch", 1)):
+            try:
+                PL.resolve_execution_order(Flaky(fr, what), coll, seg, len(seg), res.matching, [p.exec_index for p in res.proofs])
+                raise AssertionError("expected the injected " + what + " failure on every rank")
+            except A.IpcfpError as e:
+                assert e.status == A.ERR_INVALID_ARG
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
