@@ -288,6 +288,98 @@ pub fn generate_event_proof_gpu(
     res
 }
 
+/// One rank's handle on the library's cross-shard protocol (`ipcfp_comm_init`): two NCCL communicators and the
+/// exchange streams of this process's GPU. Rank 0 makes the id with [`ShardedComm::unique_id`] and hands the 128 bytes to the other
+/// ranks by any means the host already has (the reference's own RPC, MPI, a file).
+pub struct ShardedComm {
+    h: *mut sys::ipcfp_comm,
+    world: u32,
+    rank: u32,
+}
+unsafe impl Send for ShardedComm {}
+
+impl ShardedComm {
+    pub fn unique_id() -> Result<[u8; sys::IPCFP_COMM_ID_BYTES]> {
+        let mut id = [0u8; sys::IPCFP_COMM_ID_BYTES];
+        check(unsafe { sys::ipcfp_comm_unique_id(id.as_mut_ptr()) })?;
+        Ok(id)
+    }
+    pub fn new(id: &[u8; sys::IPCFP_COMM_ID_BYTES], world: u32, rank: u32, device: i32) -> Result<Self> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::ipcfp_comm_init(id.as_ptr(), world, rank, device, &mut h) })?;
+        Ok(Self { h, world, rank })
+    }
+}
+impl Drop for ShardedComm {
+    fn drop(&mut self) {
+        unsafe { sys::ipcfp_comm_destroy(self.h) }
+    }
+}
+
+/// What one rank holds after a sharded call: its own proofs and witness blocks, and its part of the merged witness CID set.
+pub struct ShardedEventProof {
+    /// proofs of the receipts this rank owns (`message_cid` and `exec_index` final: the execution order was resolved across shards)
+    pub proofs: Vec<EventProof>,
+    /// this shard's witness blocks in `Cid` order
+    pub blocks: Vec<ProofBlock>,
+    /// entries `[union_first, union_first + union_part.len())` of the `BTreeSet<Cid>` union over ALL shards (`common/witness.rs:24-40`);
+    /// the parts of ranks 0..world, concatenated, are the whole sorted set of `union_total` CIDs
+    pub union_part: Vec<Cid>,
+    pub union_first: u64,
+    pub union_total: u64,
+    pub total_matching: u64,
+    pub total_proofs: u64,
+}
+
+/// `generate_event_proof` (`src/proofs/events/generator.rs:60-107`) for ONE tipset split over `comm.world` GPUs by receipt index:
+/// rank r scans receipts `bounds[r]..bounds[r+1]` out of a store that holds the blocks that range needs. Every rank must make the
+/// call; they succeed or fail together, naming the error the single-store call on the whole tipset would have named.
+pub fn generate_event_proof_sharded_gpu(
+    comm: &ShardedComm,
+    store: &GpuBlockstore,
+    parent: &ApiTipset,
+    child: &ApiTipset,
+    receipts: &[ApiReceipt],
+    bounds: &[u64],
+    event_signature: &str,
+    topic_1: &str,
+    actor_id_filter: Option<u64>,
+) -> Result<ShardedEventProof> {
+    if bounds.len() != comm.world as usize + 1 {
+        return Err(anyhow!("bounds must hold world + 1 receipt indices"));
+    }
+    let desc = TipsetDesc::new(parent, child, receipts)?;
+    let spec = spec_c(event_signature, topic_1, actor_id_filter)?;
+    let mut tip = std::ptr::null_mut();
+    check(unsafe { sys::ipcfp_tipset_upload(store.h, &desc.raw(), &mut tip) })?;
+    let mut out = std::ptr::null_mut();
+    let st = unsafe {
+        sys::ipcfp_generate_event_proof_sharded(comm.h, store.h, tip, &spec.raw, bounds.as_ptr(), sys::IPCFP_SHARDED_UNION_TO_HOST, &mut out)
+    };
+    unsafe { sys::ipcfp_tipset_free(tip) };
+    check(st)?;
+    let r = unsafe { &*out };
+    let res = (|| -> Result<ShardedEventProof> {
+        let part = unsafe { std::slice::from_raw_parts(r.union_cids, r.n_union_part as usize * CID_LEN) };
+        let mut union_part = Vec::with_capacity(r.n_union_part as usize);
+        for c in part.chunks_exact(CID_LEN) {
+            union_part.push(Cid::try_from(c)?);
+        }
+        Ok(ShardedEventProof {
+            proofs: event_proofs_of(r, parent, child)?,
+            blocks: witness_blocks(&r.witness)?,
+            union_part,
+            union_first: r.union_part_first,
+            union_total: r.n_union_cids,
+            total_matching: r.total_matching,
+            total_proofs: r.total_proofs,
+        })
+    })();
+    unsafe { sys::ipcfp_event_result_free(out) };
+    let _keep = (&spec.sig, &spec.topic, comm.rank);
+    res
+}
+
 fn storage_proof_of(p: &sys::ipcfp_storage_proof, child: &ApiTipset, desc: &TipsetDesc) -> Result<StorageProof> {
     Ok(StorageProof {
         child_epoch: child.height,
