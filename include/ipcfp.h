@@ -141,7 +141,7 @@ typedef struct ipcfp_witness {
     const uint8_t* cids;      /* n_blocks*38, sorted by (version, codec, multihash) */
     const uint64_t* offsets;  /* n_blocks: block i = blob[offsets[i] .. offsets[i]+lengths[i])   */
     const uint32_t* lengths;  /* n_blocks                                                        */
-    const uint8_t* blob;      /* block bytes; blocks may sit in any order / with padding in here */
+    const uint8_t* blob;      /* block bytes; blocks may sit in any order / with padding in here. NULL with IPCFP_WITNESS_BY_REFERENCE: offsets then index the blob given to ipcfp_store_create */
     uint64_t blob_size;
 } ipcfp_witness;
 
@@ -243,6 +243,11 @@ typedef struct ipcfp_bundle {
 #define IPCFP_SCAN_SKIP_TX_AMTS 0x1u  /* find_matching_events only: no record_transaction_amts / base witness;
                                          execution order still built                                          */
 #define IPCFP_SHARDED_UNION_TO_HOST 0x2u /* ipcfp_generate_event_proof_sharded: also copy this rank's part of the merged witness CID list to the host */
+/* Witness BY REFERENCE (all ipcfp_generate_event_proof* calls): the result's witness carries no block bytes. witness.blob is NULL,
+ * blob_size 0, and offsets[i] / lengths[i] locate block i inside the blob the STORE WAS CREATED FROM (the caller's own host array,
+ * which it still holds): cids / offsets / lengths arrive as usual, in `Cid` order. Saves copying ≈ 51 MB per 1 M receipts that the
+ * host already has; WitnessCollector::materialize (src/proofs/common/witness.rs:43-56) becomes a gather over the caller's blocks. */
+#define IPCFP_WITNESS_BY_REFERENCE 0x8u
 #define IPCFP_SHARDED_UNION_FULL 0x4u    /* … every rank receives the WHOLE merged list (all-gather + merge of `world` lists on every rank) instead of its partition */
 
 /* generate_event_proof (src/proofs/events/generator.rs:60-107): base witness, message-AMT

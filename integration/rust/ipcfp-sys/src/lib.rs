@@ -22,6 +22,7 @@ pub const IPCFP_STORE_VERIFY_CIDS: u32 = 0x1;
 pub const IPCFP_SCAN_SKIP_TX_AMTS: u32 = 0x1;
 pub const IPCFP_SHARDED_UNION_TO_HOST: u32 = 0x2;
 pub const IPCFP_SHARDED_UNION_FULL: u32 = 0x4;
+pub const IPCFP_WITNESS_BY_REFERENCE: u32 = 0x8;
 pub const IPCFP_COMM_ID_BYTES: usize = 128;
 
 #[repr(C)] pub struct ipcfp_store { _p: [u8; 0] }

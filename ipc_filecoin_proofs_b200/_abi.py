@@ -27,6 +27,7 @@ STORE_VERIFY_CIDS = 0x1
 SCAN_SKIP_TX_AMTS = 0x1
 SHARDED_UNION_TO_HOST = 0x2
 SHARDED_UNION_FULL = 0x4
+WITNESS_BY_REFERENCE = 0x8
 COMM_ID_BYTES = 128
 
 

@@ -132,6 +132,7 @@ ipcfp_status ipcfp_bundle_to_json(const ipcfp_bundle* b, const ipcfp_tipset_desc
 }
 ipcfp_status ipcfp_event_result_to_json(const ipcfp_event_result* r, const ipcfp_tipset_desc* t, char** out, uint64_t* out_len) {
     if (!r || !t || !out || !t->child_cid || (t->n_parents && !t->parent_cids)) return IPCFP_ERR_INVALID_ARG;
+    if (r->witness.n_blocks && !r->witness.blob) return IPCFP_ERR_INVALID_ARG;   // a by-reference witness (IPCFP_WITNESS_BY_REFERENCE) carries no bytes to render
     std::string o;
     o.reserve(64 + r->witness.blob_size * 4 / 3 + r->witness.n_blocks * 200);
     o += "{\"proofs\":[";

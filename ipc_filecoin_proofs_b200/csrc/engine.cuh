@@ -204,6 +204,7 @@ struct WitnessBuilder {
     cudaStream_t st, st2;
     uint64_t nwords = 0, mA = 0, mB = 0, bytesA = 0, bytesB = 0, host_cap = 0;
     bool have_snapshot = false;
+    bool by_ref = false;          // IPCFP_WITNESS_BY_REFERENCE: no block bytes are gathered or copied; offsets are the store's own
     AsyncBuf<uint32_t> idx, plen, bitsA, bitsB;
     AsyncBuf<uint64_t> offs, word_prefix, word_prefixB, scratch;
     AsyncBuf<uint8_t> dblobA, dblobB_keep;

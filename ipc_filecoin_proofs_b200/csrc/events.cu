@@ -704,6 +704,7 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
     // Witness snapshot: base witness + every message-AMT block are final at this point — start moving
     // them to the host while pass 1 / pass 2 run (witness.cu).
     WitnessBuilder wbuild(s);
+    wbuild.by_ref = (flags & IPCFP_WITNESS_BY_REFERENCE) != 0;
     if (!exo) wbuild.snapshot(wbits.p);
     publish_words(s, 0, 18);   // error word, frontier counters (dw[1]/dw[2]), witness counts (dw[8], dw[9]), dense-walk flag (dw[14]), gather split (dw[16], dw[17])
     IPCFP_CUDA(cudaStreamSynchronize(st));

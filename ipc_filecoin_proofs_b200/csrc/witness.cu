@@ -142,7 +142,8 @@ __device__ __forceinline__ uint32_t bits_below(const uint32_t* __restrict__ bits
 // idx = [A: mA ranks ascending][B: m - mA ranks ascending], A and B disjoint. Entry i goes to its merged position f.
 __global__ void k_witness_emit(const uint32_t* __restrict__ idx, const uint64_t* __restrict__ offs, uint64_t m, uint64_t mA, uint64_t baseB,
                                const uint32_t* __restrict__ bitsA, const uint64_t* __restrict__ prefixA, const uint32_t* __restrict__ bitsB,
-                               const uint64_t* __restrict__ prefixB, StoreView v, uint8_t* cids, uint64_t* out_offs, uint32_t* out_lens, uint32_t* out_idx) {
+                               const uint64_t* __restrict__ prefixB, StoreView v, uint8_t* cids, uint64_t* out_offs, uint32_t* out_lens, uint32_t* out_idx,
+                               int by_ref) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint32_t r = idx[i];
@@ -150,7 +151,7 @@ __global__ void k_witness_emit(const uint32_t* __restrict__ idx, const uint64_t*
     if (i < mA) f = i + (m > mA ? bits_below(bitsB, prefixB, r) : 0u);
     else f = (i - mA) + bits_below(bitsA, prefixA, r);
     const uint32_t b = v.block_at_rank[r];
-    out_offs[f] = offs[i] + (i >= mA ? baseB : 0);
+    out_offs[f] = by_ref ? v.offsets[b] : offs[i] + (i >= mA ? baseB : 0);   // by reference: where the block sits in the blob the store was created from
     out_lens[f] = v.lengths[b];
     out_idx[f] = b;
     uint8_t* o = cids + 38 * f;
@@ -208,6 +209,11 @@ void WitnessBuilder::snapshot(const uint32_t* wbits) {
 void WitnessBuilder::start_copy(uint64_t mA_, uint64_t bytesA_, uint64_t split_idx, uint64_t split_bytes) {
     mA = mA_;
     bytesA = bytesA_;
+    if (by_ref) {   // nothing to gather or copy: the index arrays are all the host gets (finish_start)
+        bytesA = 0;
+        IPCFP_CUDA(cudaEventRecord(s->ev[7], st2));
+        return;
+    }
     host_cap = bytesA + bytesA / 8 + (8u << 20);
     host_blob = PinnedArray(s->pool, host_cap);
     host_cap = host_blob.cap;
@@ -245,7 +251,8 @@ void WitnessBuilder::finish_start(uint64_t mB_, uint64_t bytesB_, WitnessOut& ou
     bytesB = bytesB_;
     unsigned long long* dw = s->dev_words.p;
     uint64_t m = mA + mB;
-    if (mB) {
+    if (by_ref) { bytesB = 0; mB_ = 0; }   // (mB stays: the late entries are still listed; only their bytes are not gathered)
+    if (mB_) {
         k_padded_lengths<<<div_up(mB, 256), 256, 0, st>>>(idx.p + mA, mB, s->lengths.p, s->block_at_rank.p, plen.p); IPCFP_LAUNCH_CHECK();
         exclusive_scan_u32(plen.p, offs.p + mA, mB, (uint64_t*)(dw + 11), scratch.p, st);
     }
@@ -257,7 +264,7 @@ void WitnessBuilder::finish_start(uint64_t mB_, uint64_t bytesB_, WitnessOut& ou
         host_cap = host_blob.cap;
     }
     AsyncBuf<uint8_t> dblobB(bytesB + 64, st);
-    if (mB) {
+    if (mB_) {
         k_witness_copy<<<div_up(mB * 32, 256), 256, 0, st>>>(idx.p + mA, mB, s->view, offs.p + mA, dblobB.p); IPCFP_LAUNCH_CHECK();
         IPCFP_CUDA(cudaMemcpyAsync((uint8_t*)host_blob.p + bytesA, dblobB.p, bytesB, cudaMemcpyDeviceToHost, st));
     }
@@ -267,7 +274,7 @@ void WitnessBuilder::finish_start(uint64_t mB_, uint64_t bytesB_, WitnessOut& ou
     AsyncBuf<uint8_t> d_cids(m * 38 + 64, st);
     if (m) {
         k_witness_emit<<<div_up(m, 256), 256, 0, st>>>(idx.p, offs.p, m, mA, bytesA, bitsA.p, word_prefix.p, bitsB.p, word_prefixB.p, s->view, d_cids.p, d_offs.p,
-                                                       d_lens.p, d_idx.p);
+                                                       d_lens.p, d_idx.p, by_ref ? 1 : 0);
         IPCFP_LAUNCH_CHECK();
     }
     IPCFP_CUDA(cudaEventRecord(s->ev[6], st));   // the sorted CID list exists on the device (the multi-GPU union waits for this, not for the copies below)
