@@ -5,6 +5,7 @@ import json
 from types import SimpleNamespace
 
 import numpy as np
+import pytest
 
 from ipc_filecoin_proofs_b200 import _abi as A
 from ipc_filecoin_proofs_b200 import bundle_json as J
@@ -116,5 +117,12 @@ def test_c_abi_json_equals_python_rendering(oracle_mod, ts3_small, ts1):
     try:
         text = api.event_result_to_json(eo, ts1)
         assert text == J.dumps(J.event_bundle(ts1, A.event_result_from_c(eo.contents)))
+        # a by-reference witness (IPCFP_WITNESS_BY_REFERENCE: blob == NULL) has no bytes to render: refused, not dereferenced
+        byref = A.EventResultC.from_buffer_copy(eo.contents)
+        byref.witness.blob = None
+        byref.witness.blob_size = 0
+        with pytest.raises(A.IpcfpError) as ei:
+            api.event_result_to_json(C.pointer(byref), ts1)
+        assert ei.value.status == A.ERR_INVALID_ARG
     finally:
         OL.oracle_event_result_free(eo)
