@@ -17,8 +17,11 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CU_HDRS)
 $(CSRC)/bundle_json.o: $(CSRC)/bundle_json.cpp include/ipcfp.h
 	$(CXX) -O2 -std=c++17 -fPIC -c $< -o $@
 
-$(LIB): $(CU_OBJS) $(CSRC)/bundle_json.o
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) $(CSRC)/bundle_json.o -lcudart -ldl
+$(CSRC)/bundle_parse.o: $(CSRC)/bundle_parse.cpp include/ipcfp.h
+	$(CXX) -O2 -std=c++17 -fPIC -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o -lcudart -ldl
 
 synth/libipcfp_synth.so: synth/synth.cpp synth/synth.h synth/cpu_crypto.h
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ synth/synth.cpp
@@ -27,6 +30,6 @@ oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h synth/cpu_crypto.h includ
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ oracle/oracle.cpp
 
 clean:
-	rm -f $(CU_OBJS) $(CSRC)/bundle_json.o $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
+	rm -f $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
 
 .PHONY: all clean

@@ -298,6 +298,26 @@ ipcfp_status ipcfp_bundle_to_json(const ipcfp_bundle* b, const ipcfp_tipset_desc
 ipcfp_status ipcfp_event_result_to_json(const ipcfp_event_result* r, const ipcfp_tipset_desc* t, char** out, uint64_t* out_len);
 void ipcfp_json_free(char* p);
 
+/* The way back (csrc/bundle_parse.cpp, host C++): what serde_json::from_str::<UnifiedProofBundle> / ::<EventProofBundle> reads, as
+ * the PODs the batched verifiers below take and the flat block arrays ipcfp_store_create takes for the witness store. `tipset` holds
+ * the fields every proof of the bundle shares (parent_epoch, child_epoch, n_parents, parent_cids, child_cid,
+ * child_parent_state_root; the other members are NULL / 0); a bundle whose proofs disagree on them, CIDs that are not 38 bytes or
+ * topics that are not 32 bytes are refused with IPCFP_ERR_UNSUPPORTED, malformed JSON / hex / base32 / base64 with
+ * IPCFP_ERR_INVALID_ARG. Blocks are kept in the order given (16-byte aligned inside `witness.blob`); storage proofs come back with
+ * found = 1, raw_len = 32 (the wire format carries the padded value only). No device is needed. */
+typedef struct ipcfp_parsed_bundle {
+    ipcfp_tipset_desc tipset;
+    uint64_t n_storage_proofs;
+    const ipcfp_storage_proof* storage_proofs;
+    uint64_t n_event_proofs;
+    const ipcfp_event_proof* event_proofs;
+    const uint8_t* data_blob;          /* topics / data of the event proofs (topics_off / data_off index it) */
+    uint64_t data_blob_size;
+    ipcfp_witness witness;             /* Vec<ProofBlock> */
+} ipcfp_parsed_bundle;
+ipcfp_status ipcfp_bundle_from_json(const char* json, uint64_t len, ipcfp_parsed_bundle** out);
+void ipcfp_parsed_bundle_free(ipcfp_parsed_bundle* b);
+
 /* ------------------------------------------------------------------------------------------
  * Batched verifiers (src/proofs/events/verifier.rs:51-290, src/proofs/storage/verifier.rs:24-170): replay every proof against a
  * store that holds ONLY the witness blocks. Create that store with IPCFP_STORE_VERIFY_CIDS: this is the Blake2b-256 check of every

@@ -79,6 +79,10 @@ pub struct ipcfp_storage_result {
 pub struct ipcfp_slot_result { pub n: u64, pub found: *const u8, pub raw_len: *const u32, pub values: *const u8, pub witness: ipcfp_witness, pub ms_total: f32, pub ms_lookup: f32,
                                 pub lookup_nodes: u64, pub lookup_bytes: u64 }
 #[repr(C)]
+pub struct ipcfp_parsed_bundle { pub tipset: ipcfp_tipset_desc, pub n_storage_proofs: u64, pub storage_proofs: *const ipcfp_storage_proof,
+                                 pub n_event_proofs: u64, pub event_proofs: *const ipcfp_event_proof, pub data_blob: *const u8, pub data_blob_size: u64,
+                                 pub witness: ipcfp_witness }
+#[repr(C)]
 pub struct ipcfp_bundle { pub storage: *mut ipcfp_storage_result, pub n_event_results: u64, pub events: *mut *mut ipcfp_event_result, pub witness: ipcfp_witness }
 
 extern "C" {
@@ -127,6 +131,8 @@ extern "C" {
     pub fn ipcfp_bundle_to_json(b: *const ipcfp_bundle, t: *const ipcfp_tipset_desc, out: *mut *mut c_char, out_len: *mut u64) -> ipcfp_status;
     pub fn ipcfp_event_result_to_json(r: *const ipcfp_event_result, t: *const ipcfp_tipset_desc, out: *mut *mut c_char, out_len: *mut u64) -> ipcfp_status;
     pub fn ipcfp_json_free(p: *mut c_char);
+    pub fn ipcfp_bundle_from_json(json: *const c_char, len: u64, out: *mut *mut ipcfp_parsed_bundle) -> ipcfp_status;
+    pub fn ipcfp_parsed_bundle_free(b: *mut ipcfp_parsed_bundle);
     pub fn ipcfp_verify_event_proofs(witness_store: *mut ipcfp_store, t: *const ipcfp_tipset_desc, proofs: *const ipcfp_event_proof, n_proofs: u64,
                                      data_blob: *const u8, data_blob_size: u64, filter: *const ipcfp_event_spec, results: *mut u8) -> ipcfp_status;
     pub fn ipcfp_verify_storage_proofs(witness_store: *mut ipcfp_store, t: *const ipcfp_tipset_desc, proofs: *const ipcfp_storage_proof, n_proofs: u64,

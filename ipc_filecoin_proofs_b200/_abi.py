@@ -132,6 +132,20 @@ class StorageProofC(C.Structure):
     ]
 
 
+class ParsedBundleC(C.Structure):
+    """ipcfp_parsed_bundle (ipcfp_bundle_from_json)."""
+    _fields_ = [
+        ("tipset", TipsetDesc),
+        ("n_storage_proofs", C.c_uint64),
+        ("storage_proofs", C.c_void_p),
+        ("n_event_proofs", C.c_uint64),
+        ("event_proofs", C.c_void_p),
+        ("data_blob", C.c_void_p),
+        ("data_blob_size", C.c_uint64),
+        ("witness", Witness),
+    ]
+
+
 class StorageResultC(C.Structure):
     _fields_ = [
         ("n_proofs", C.c_uint64),

@@ -43,6 +43,7 @@ EXPORTS = [
     "ipcfp_store_stream", "ipcfp_exec_bucketize", "ipcfp_exec_dedup", "ipcfp_exec_fetch",
     "ipcfp_comm_unique_id", "ipcfp_comm_init", "ipcfp_comm_destroy", "ipcfp_generate_event_proof_sharded",
     "ipcfp_verify_event_proofs", "ipcfp_verify_storage_proofs", "ipcfp_bundle_to_json", "ipcfp_event_result_to_json", "ipcfp_json_free",
+    "ipcfp_bundle_from_json", "ipcfp_parsed_bundle_free",
 ]
 
 
@@ -135,6 +136,9 @@ def lib():
             f.restype = C.c_int32
             f.argtypes = [C.c_void_p, C.POINTER(A.TipsetDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.ipcfp_json_free.argtypes = [C.c_void_p]
+        L.ipcfp_bundle_from_json.restype = C.c_int32
+        L.ipcfp_bundle_from_json.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(A.ParsedBundleC))]
+        L.ipcfp_parsed_bundle_free.argtypes = [C.POINTER(A.ParsedBundleC)]
         _lib = L
     return _lib
 
@@ -327,6 +331,51 @@ def bundle_to_json(bundle_c_ptr, ts):
 def event_result_to_json(result_c_ptr, ts):
     """`serde_json::to_string(&EventProofBundle)` of an ipcfp_event_result."""
     return _to_json("ipcfp_event_result_to_json", C.cast(result_c_ptr, C.c_void_p), ts)
+
+
+class ParsedBundle:
+    """`serde_json::from_str::<UnifiedProofBundle | EventProofBundle>` through the C ABI (ipcfp_bundle_from_json): PODs ready for the
+    batched verifiers + the witness block arrays. Owns the C object; `.c` is the ipcfp_parsed_bundle."""
+
+    def __init__(self, text):
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        self._p = C.POINTER(A.ParsedBundleC)()
+        st = lib().ipcfp_bundle_from_json(raw, len(raw), C.byref(self._p))
+        if st != A.OK:
+            raise A.IpcfpError(st, "ipcfp_bundle_from_json", 0)
+        self.c = self._p.contents
+
+    @property
+    def witness(self):
+        return A.witness_from_c(self.c.witness)
+
+    @property
+    def event_proofs_raw(self):
+        n = int(self.c.n_event_proofs)
+        return A._arr(self.c.event_proofs, n * C.sizeof(A.EventProofC), np.uint8), A._arr(self.c.data_blob, int(self.c.data_blob_size), np.uint8)
+
+    @property
+    def storage_proofs_raw(self):
+        return A._arr(self.c.storage_proofs, int(self.c.n_storage_proofs) * C.sizeof(A.StorageProofC), np.uint8)
+
+    def tipset_fields(self):
+        t = self.c.tipset
+        P = int(t.n_parents)
+        return dict(parent_epoch=int(t.parent_epoch), child_epoch=int(t.child_epoch),
+                    parent_cids=A._arr(t.parent_cids, P * A.CID_LEN, np.uint8).tobytes(),
+                    child_cid=A._arr(t.child_cid, A.CID_LEN if t.child_cid else 0, np.uint8).tobytes(),
+                    parent_state_root=A._arr(t.child_parent_state_root, A.CID_LEN if t.child_parent_state_root else 0, np.uint8).tobytes())
+
+    def close(self):
+        if self._p:
+            lib().ipcfp_parsed_bundle_free(self._p)
+            self._p = C.POINTER(A.ParsedBundleC)()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def verify_event_proofs(witness, ts, result, filter_spec=None, device=0):

@@ -14,6 +14,7 @@ STRUCTS = {
     "ipcfp_tipset_desc": A.TipsetDesc, "ipcfp_event_spec": A.EventSpec, "ipcfp_storage_spec": A.StorageSpec, "ipcfp_witness": A.Witness,
     "ipcfp_event_proof": A.EventProofC, "ipcfp_event_result": A.EventResultC, "ipcfp_storage_proof": A.StorageProofC,
     "ipcfp_storage_result": A.StorageResultC, "ipcfp_slot_result": A.SlotResultC, "ipcfp_bundle": A.BundleC,
+    "ipcfp_parsed_bundle": A.ParsedBundleC,
 }
 
 

@@ -126,3 +126,95 @@ def test_c_abi_json_equals_python_rendering(oracle_mod, ts3_small, ts1):
         assert ei.value.status == A.ERR_INVALID_ARG
     finally:
         OL.oracle_event_result_free(eo)
+
+
+def test_c_abi_json_parser_round_trip(oracle_mod, ts3_small, ts1):
+    """ipcfp_bundle_from_json (csrc/bundle_parse.cpp): JSON → the PODs the batched verifiers take + the witness block arrays. The parsed
+    PODs equal what the Python parser + packers produce from the same text, byte for byte, and the restated verifiers accept them."""
+    from ipc_filecoin_proofs_b200 import api
+    # --- UnifiedProofBundle
+    ts = ts3_small
+    slot = oracle_mod.compute_mapping_slot((b"calib-subnet-1" + bytes(32))[:32], 0)
+    ost = oracle_mod.Store.from_tipset(ts)
+    b = ost.generate_proof_bundle(ts, [(1001, slot), (1003, slot)], [spec_of(ts)])
+    text = J.dumps(J.unified_bundle(ts, b))
+    pb = api.ParsedBundle(text)
+    doc = J.loads(text)
+    w_py = J.witness_from_blocks(doc["blocks"])
+    w_c = pb.witness
+    assert np.array_equal(w_c.cids, w_py.cids) and np.array_equal(w_c.lengths, w_py.lengths)
+    assert [w_c.block(i) for i in range(w_c.n_blocks)] == [w_py.block(i) for i in range(w_py.n_blocks)]
+    assert all(int(o) % 16 == 0 for o in w_c.offsets)
+    ep = J.event_proofs_from_json(doc["event_proofs"])
+    raw_c, blob_c = pb.event_proofs_raw
+    raw_py, blob_py = A.pack_event_proofs(ep)
+    assert raw_c.tobytes() == raw_py.tobytes() and blob_c.tobytes() == blob_py.tobytes()[:len(blob_c)]
+    sp = J.storage_proofs_from_json(doc["storage_proofs"])
+    assert pb.storage_proofs_raw.tobytes() == A.pack_storage_proofs(sp).tobytes()
+    f = pb.tipset_fields()
+    assert f["child_epoch"] == int(ts.child_epoch) and f["child_cid"] == bytes(ts.child_cid)
+    if doc["event_proofs"]:   # parent epoch / parent tipset CIDs travel with the event proofs only (events/bundle.rs:14-23)
+        assert f["parent_epoch"] == int(ts.parent_epoch) and f["parent_cids"] == bytes(np.asarray(ts.parent_cids, dtype=np.uint8).reshape(-1))
+    assert f["parent_state_root"] == bytes(ts.parent_state_root)
+    # closed loop: the restated verifiers on what the C parser produced
+    assert all(oracle_mod.verify_event_proofs(w_c, ts, SimpleNamespace(proofs=ep, raw_proofs=raw_c, data_blob=blob_c), spec_of(ts)))
+    assert all(oracle_mod.verify_storage_proofs(w_c, ts, SimpleNamespace(proofs=sp, raw_proofs=pb.storage_proofs_raw)))
+    pb.close()
+    # --- EventProofBundle, with the other CID spellings of ProofBlock.cid and an unknown field (serde ignores it)
+    r1 = oracle_mod.Store.from_tipset(ts1).generate_event_proof(ts1, spec_of(ts1))
+    d1 = J.event_bundle(ts1, r1)
+    for k, blk in enumerate(d1["blocks"]):
+        if k % 3 == 1:
+            blk["cid"] = {"/": J.cid_to_string(bytes(blk["cid"]))}
+        elif k % 3 == 2:
+            blk["cid"] = J.cid_to_string(bytes(blk["cid"]))
+    d1["note"] = {"ignored": [1, 2.5e3, None, True, "é\\"]}
+    pb1 = api.ParsedBundle(json.dumps(d1))
+    assert np.array_equal(pb1.witness.cids, r1.witness.cids) and pb1.witness.blocks() == r1.witness.blocks()
+    raw1, blob1 = pb1.event_proofs_raw
+    assert raw1.tobytes() == A.pack_event_proofs(r1.proofs)[0].tobytes()
+    assert pb1.c.n_storage_proofs == 0 and not pb1.c.tipset.child_parent_state_root
+    f1 = pb1.tipset_fields()
+    assert (f1["parent_epoch"], f1["child_epoch"]) == (int(ts1.parent_epoch), int(ts1.child_epoch))
+    assert f1["parent_cids"] == bytes(np.asarray(ts1.parent_cids, dtype=np.uint8).reshape(-1)) and f1["child_cid"] == bytes(ts1.child_cid)
+
+
+def test_c_abi_json_parser_refuses_malformed_input(oracle_mod, ts1):
+    from ipc_filecoin_proofs_b200 import api
+    r1 = oracle_mod.Store.from_tipset(ts1).generate_event_proof(ts1, spec_of(ts1))
+    good = J.dumps(J.event_bundle(ts1, r1))
+    api.ParsedBundle(good).close()
+
+    def status(text):
+        try:
+            api.ParsedBundle(text).close()
+            return A.OK
+        except A.IpcfpError as e:
+            return e.status
+
+    rng = np.random.default_rng(5)
+    for cut in rng.integers(1, len(good) - 1, 200):                       # every truncation is malformed JSON
+        assert status(good[:int(cut)]) == A.ERR_INVALID_ARG
+    assert status(good + " x") == A.ERR_INVALID_ARG                        # trailing characters
+    assert status("[]") == A.ERR_INVALID_ARG and status('{"blocks":[]}') == A.ERR_INVALID_ARG
+    doc = json.loads(good)
+    assert doc["proofs"], "the fixture has proofs"
+
+    def mutated(fn):
+        d = json.loads(good)
+        fn(d)
+        return json.dumps(d)
+
+    assert status(mutated(lambda d: d["proofs"][0].__setitem__("exec_index", -1))) == A.ERR_INVALID_ARG
+    assert status(mutated(lambda d: d["proofs"][0].__setitem__("exec_index", 1.5))) == A.ERR_INVALID_ARG
+    assert status(mutated(lambda d: d["proofs"][0].__setitem__("exec_index", 2 ** 64))) == A.ERR_INVALID_ARG
+    assert status(mutated(lambda d: d["proofs"][0]["event_data"].__setitem__("data", "0xabc"))) == A.ERR_INVALID_ARG        # odd hex
+    assert status(mutated(lambda d: d["proofs"][0]["event_data"].__setitem__("data", "abcd"))) == A.ERR_INVALID_ARG         # no 0x
+    assert status(mutated(lambda d: d["proofs"][0].__setitem__("message_cid", "bafy!"))) == A.ERR_INVALID_ARG
+    assert status(mutated(lambda d: d["proofs"][0].__setitem__("message_cid", "baeaaa"))) == A.ERR_UNSUPPORTED                 # not a 38-byte CID
+    assert status(mutated(lambda d: d["blocks"][0].__setitem__("data", d["blocks"][0]["data"][:-1]))) == A.ERR_INVALID_ARG    # base64 length
+    assert status(mutated(lambda d: d["blocks"][0].__setitem__("cid", d["blocks"][0]["cid"][:-1]))) == A.ERR_UNSUPPORTED
+    assert status(mutated(lambda d: d["proofs"][0]["event_data"].__setitem__("topics", ["0x00"]))) == A.ERR_UNSUPPORTED       # topic not 32 bytes
+    if len(doc["proofs"]) > 1:                                                                                                # proofs of two tipsets in one bundle
+        assert status(mutated(lambda d: d["proofs"][1].__setitem__("child_epoch", d["proofs"][1]["child_epoch"] + 1))) == A.ERR_UNSUPPORTED
+    assert status(mutated(lambda d: d["proofs"][0].pop("event_index"))) == A.ERR_INVALID_ARG                                  # missing field

@@ -38,3 +38,31 @@ def test_by_reference_shuffled_misaligned_store(api, oracle_mod, ts2):
 def test_by_reference_general_walk(api, oracle_mod, synth_mod, monkeypatch):
     monkeypatch.setenv("IPCFP_BFS_GENERAL", "1")
     _check(api, oracle_mod, synth_mod.Tipset(synth_mod.default_params(seed=7, n_receipts=700, events_per_receipt=5, match_ppm=50000, n_parents=3, dup_msgs=4)))
+
+
+def test_json_bundle_verified_through_the_c_abi_alone(api, oracle_mod, synth_mod):
+    """The flow a non-Rust host has: EventProofBundle as JSON text → ipcfp_bundle_from_json → witness store with every block
+    Blake2b-checked → ipcfp_verify_event_proofs, with the tipset fields exactly as the parser recovered them from the proofs."""
+    import ctypes as C
+    from ipc_filecoin_proofs_b200 import bundle_json as J
+    ts = synth_mod.Tipset(synth_mod.config_params(2))
+    spec = spec_of(ts)
+    r = api.BlockStore.from_tipset(ts, verify_cids=True).generate_event_proof(ts, spec)
+    assert len(r.proofs) > 0
+    pb = api.ParsedBundle(J.dumps(J.event_bundle(ts, r)))
+    L = api.lib()
+    w = pb.c.witness
+    store = C.c_void_p()
+    assert L.ipcfp_store_create(w.cids, w.offsets, w.lengths, w.blob, w.blob_size, w.n_blocks, 0, A.STORE_VERIFY_CIDS, C.byref(store)) == 0, L.ipcfp_last_error()
+    try:
+        n = int(pb.c.n_event_proofs)
+        assert n == len(r.proofs)
+        res = np.zeros(n, dtype=np.uint8)
+        st = L.ipcfp_verify_event_proofs(store, C.byref(pb.c.tipset), pb.c.event_proofs, n, pb.c.data_blob, pb.c.data_blob_size, C.addressof(spec),
+                                         res.ctypes.data)
+        assert st == 0, L.ipcfp_last_error()
+        assert res.all()
+        assert [bool(x) for x in res] == oracle_mod.verify_event_proofs(r.witness, ts, r, spec)
+    finally:
+        L.ipcfp_store_destroy(store)
+        pb.close()
