@@ -8,7 +8,11 @@
  * orchestration line by line and the crates' published formats; it is pinned instead by
  *   (1) known-answer hash vectors + hashlib,
  *   (2) an independent Python (cbor2 + hashlib) builder/scanner (oracle/pyoracle.py),
- *   (3) the restated verifiers (every witness must verify; dropping a block must fail).
+ *   (3) the restated verifiers (every witness must verify; dropping a block must fail),
+ *   (4) three constants of the public Filecoin chain (empty TxMeta over v0 AMTs, builtin-actors' EMPTY_ARR_CID, the empty HAMT
+ *       node): tests/test_oracle_cpu.py::test_public_filecoin_constants_pin_the_encodings — the basic encodings (DAG-CBOR tuples
+ *       and links, AMT v0/v3 and HAMT node layouts, Blake2b-256 CIDs) are checked against the real network, not only against
+ *       ourselves.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library. The product library never links or calls it.

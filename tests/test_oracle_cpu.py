@@ -354,3 +354,57 @@ def test_oracle_vs_python_oracle_full_size_hamt(oracle_mod, synth_mod):
     for (a, s), p in zip(specs, r.proofs):
         pp = P.generate_storage_proof(store, ts, a, s)
         assert (p.actor_state_cid, p.storage_root, p.value) == (pp["actor_state_cid"], pp["storage_root"], pp["value"])
+
+
+# Constants of the public Filecoin chain — NOT taken from /root/reference (which holds no vectors); any Filecoin node or block explorer
+# shows them: the `Messages` CID of every block header without messages (MsgMeta/TxMeta over two empty v0 AMTs), builtin-actors'
+# `EMPTY_ARR_CID` (empty AMT v3, bit width 3) and the empty HAMT node (the "empty map" of actor state).
+FILECOIN_EMPTY_TXMETA = "bafy2bzacecmda75ovposbdateg7eyhwij65zklgyijgcjwynlklmqazpwlhba"
+FILECOIN_EMPTY_ARR = "bafy2bzacedijw74yui7otvo63nfl3hdq2vdzuy7wx2tnptwed6zml4vvz7wee"
+FILECOIN_EMPTY_HAMT = "bafy2bzaceamp42wmmgr2g2ymg46euououzfyck7szknvfacqscohrvaikwfay"
+EMPTY_AMT_V0 = bytes([0x83, 0x00, 0x00, 0x83, 0x41, 0x00, 0x80, 0x80])            # [height 0, count 0, [bmap h'00', [], []]]
+EMPTY_AMT_V3 = bytes([0x84, 0x03, 0x00, 0x00, 0x83, 0x41, 0x00, 0x80, 0x80])      # [bit_width 3, height 0, count 0, node]
+EMPTY_HAMT_NODE = bytes([0x82, 0x40, 0x80])                                       # [bitfield h'', []]
+
+
+def test_public_filecoin_constants_pin_the_encodings(oracle_mod, synth_mod):
+    """External known answers for the [UPSTREAM] encodings the whole path rests on: DAG-CBOR tuples and links,
+    AMT v0 / v3 root and node layout, the HAMT node layout, Blake2b-256 CIDv1 (dag-cbor) and its base32 spelling. Three independent
+    implementations must land on the chain's own constants: hashlib + the Python helpers, the C++ oracle's hash, and the synthetic
+    tipset builder (whose blocks are what every parity test feeds to the engine)."""
+    from ipc_filecoin_proofs_b200 import bundle_json as J
+    from oracle import pyoracle as P
+    import cbor2
+
+    def link(c):
+        return bytes([0xd8, 0x2a, 0x58, 0x27, 0x00]) + c
+
+    cid_v0, cid_v3, cid_h = P.cid_of(EMPTY_AMT_V0), P.cid_of(EMPTY_AMT_V3), P.cid_of(EMPTY_HAMT_NODE)
+    txmeta = bytes([0x82]) + link(cid_v0) + link(cid_v0)
+    assert J.cid_to_string(P.cid_of(txmeta)) == FILECOIN_EMPTY_TXMETA
+    assert J.cid_to_string(cid_v3) == FILECOIN_EMPTY_ARR
+    assert J.cid_to_string(cid_h) == FILECOIN_EMPTY_HAMT
+    assert J.cid_from_string(FILECOIN_EMPTY_TXMETA) == P.cid_of(txmeta)
+    # the C++ oracle's Blake2b agrees on the same bytes
+    for blk in (EMPTY_AMT_V0, EMPTY_AMT_V3, EMPTY_HAMT_NODE, txmeta):
+        assert bytes(oracle_mod.blake2b256(blk)) == P.cid_of(blk)[6:]
+    # the decoders read these blocks as what they are: empty AMTs (both versions), an empty HAMT node
+    store = {cid_v0: EMPTY_AMT_V0, cid_v3: EMPTY_AMT_V3, cid_h: EMPTY_HAMT_NODE, P.cid_of(txmeta): txmeta}
+    for cid, ver in ((cid_v0, 0), (cid_v3, 3)):
+        amt = P.Amt(cid, P.Recorder(store), ver)
+        seen = []
+        amt.for_each(lambda i, v: seen.append(i))
+        assert (amt.bw, amt.height, amt.count, seen) == (3, 0, 0, []) and amt.get(0) is None
+    assert P.hamt_get(P.Recorder(store), cid_h, 5, bytes(32)) is None
+    assert [bytes(t.value) for t in cbor2.loads(txmeta)] == [bytes([0]) + cid_v0] * 2
+    # the synthetic tipset builder emits exactly the chain's constant for a parent block without messages …
+    ts = synth_mod.Tipset(synth_mod.default_params(seed=1, n_receipts=1, n_parents=3))
+    tx = [J.cid_to_string(bytes(t)) for t in np.asarray(ts.parent_txmeta_cids, dtype=np.uint8).reshape(-1, 38)]
+    assert tx.count(FILECOIN_EMPTY_TXMETA) == 2
+    blocks = ts.as_dict()
+    assert blocks[J.cid_from_string(FILECOIN_EMPTY_TXMETA)] == txmeta and blocks[cid_v0] == EMPTY_AMT_V0
+    # … and both oracles walk such a tipset to the same answer (the empty AMTs are recorded into the witness like any other block)
+    spec = spec_of(ts)
+    r = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec)
+    wit = {bytes(c) for c in r.witness.cids}
+    assert J.cid_from_string(FILECOIN_EMPTY_TXMETA) in wit and cid_v0 in wit
