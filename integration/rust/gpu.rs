@@ -63,6 +63,9 @@ fn hex0x(b: &[u8]) -> String {
 /// (`src/client/blockstore.rs:20-37`, `src/client/cached_blockstore.rs:53-85`).
 pub struct GpuBlockstore {
     h: *mut sys::ipcfp_store,
+    /// the packed block bytes as handed to `ipcfp_store_create`, kept when the caller asked for it (`ingest_keeping_blocks`): the
+    /// array a by-reference witness (`IPCFP_WITNESS_BY_REFERENCE`) points into
+    kept_blob: Option<Vec<u8>>,
 }
 unsafe impl Send for GpuBlockstore {}
 
@@ -70,6 +73,20 @@ impl GpuBlockstore {
     /// `blocks`: what the RPC layer fetched (`ChainReadObj` results, or a `CachedBlockstore`'s shared cache), in any order.
     /// `verify`: Blake2b-256 every block against its CID on the GPU (the check the reference never makes — SURVEY F6).
     pub fn ingest<'a, I>(blocks: I, device: i32, verify: bool) -> Result<Self>
+    where
+        I: IntoIterator<Item = (&'a Cid, &'a [u8])>,
+    {
+        Self::ingest_impl(blocks, device, verify, false)
+    }
+    /// As `ingest`, and the store keeps its host copy of the packed blocks: witnesses can then come back by reference
+    /// (`generate_event_proof_gpu_by_reference`) — what a `CachedBlockstore` that outlives the proof holds anyway.
+    pub fn ingest_keeping_blocks<'a, I>(blocks: I, device: i32, verify: bool) -> Result<Self>
+    where
+        I: IntoIterator<Item = (&'a Cid, &'a [u8])>,
+    {
+        Self::ingest_impl(blocks, device, verify, true)
+    }
+    fn ingest_impl<'a, I>(blocks: I, device: i32, verify: bool, keep: bool) -> Result<Self>
     where
         I: IntoIterator<Item = (&'a Cid, &'a [u8])>,
     {
@@ -106,7 +123,7 @@ impl GpuBlockstore {
             }
             check(st)?;
         }
-        Ok(Self { h })
+        Ok(Self { h, kept_blob: if keep { Some(blob) } else { None } })
     }
     /// The witness of a bundle as a store of its own (every block CID-checked): what the verifiers replay against.
     pub fn from_witness(blocks: &[ProofBlock], device: i32) -> Result<Self> {
@@ -377,6 +394,41 @@ pub fn generate_event_proof_sharded_gpu(
     })();
     unsafe { sys::ipcfp_event_result_free(out) };
     let _keep = (&spec.sig, &spec.topic, comm.rank);
+    res
+}
+
+/// `generate_event_proof_gpu` with the witness BY REFERENCE (`IPCFP_WITNESS_BY_REFERENCE`): the GPU returns CIDs / offsets / lengths
+/// only and `ProofBlock.data` is sliced out of the store's own host copy of the blocks — 50 bytes per witness block cross PCIe instead
+/// of the block bytes. The store must have been built with `ingest_keeping_blocks`.
+pub fn generate_event_proof_gpu_by_reference(
+    store: &GpuBlockstore,
+    parent: &ApiTipset,
+    child: &ApiTipset,
+    receipts: &[ApiReceipt],
+    event_signature: &str,
+    topic_1: &str,
+    actor_id_filter: Option<u64>,
+) -> Result<EventProofBundle> {
+    let blob = store.kept_blob.as_ref().ok_or_else(|| anyhow!("store was not built with ingest_keeping_blocks"))?;
+    let desc = TipsetDesc::new(parent, child, receipts)?;
+    let spec = spec_c(event_signature, topic_1, actor_id_filter)?;
+    let mut out = std::ptr::null_mut();
+    check(unsafe { sys::ipcfp_generate_event_proof(store.h, &desc.raw(), &spec.raw, sys::IPCFP_WITNESS_BY_REFERENCE, &mut out) })?;
+    let r = unsafe { &*out };
+    let res = (|| -> Result<EventProofBundle> {
+        let w = &r.witness;
+        let mut blocks = Vec::with_capacity(w.n_blocks as usize);
+        for i in 0..w.n_blocks as usize {
+            let cid = cid_from38(unsafe { std::slice::from_raw_parts(w.cids.add(i * CID_LEN), CID_LEN) })?;
+            let off = unsafe { *w.offsets.add(i) } as usize; // into the blob this store was created from
+            let len = unsafe { *w.lengths.add(i) } as usize;
+            let data = blob.get(off..off + len).ok_or_else(|| anyhow!("witness block {} outside the kept blob", i))?.to_vec();
+            blocks.push(ProofBlock { cid, data });
+        }
+        Ok(EventProofBundle { proofs: event_proofs_of(r, parent, child)?, blocks })
+    })();
+    unsafe { sys::ipcfp_event_result_free(out) };
+    let _keep = (&spec.sig, &spec.topic);
     res
 }
 
