@@ -40,6 +40,21 @@ def test_by_reference_general_walk(api, oracle_mod, synth_mod, monkeypatch):
     _check(api, oracle_mod, synth_mod.Tipset(synth_mod.default_params(seed=7, n_receipts=700, events_per_receipt=5, match_ppm=50000, n_parents=3, dup_msgs=4)))
 
 
+def test_public_filecoin_constants_on_the_gpu(api):
+    """The chain's own constants (see tests/test_oracle_cpu.py::test_public_filecoin_constants_pin_the_encodings) through the GPU's
+    Blake2b-256: empty v0 AMT → empty TxMeta, builtin-actors' EMPTY_ARR_CID, the empty HAMT node."""
+    from ipc_filecoin_proofs_b200 import bundle_json as J
+    from tests.test_oracle_cpu import (EMPTY_AMT_V0, EMPTY_AMT_V3, EMPTY_HAMT_NODE, FILECOIN_EMPTY_ARR, FILECOIN_EMPTY_HAMT, FILECOIN_EMPTY_TXMETA)
+    pre = bytes([0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20])
+    d = api.blake2b256_batch([EMPTY_AMT_V0, EMPTY_AMT_V3, EMPTY_HAMT_NODE])
+    cid_v0 = pre + bytes(d[0])
+    txmeta = bytes([0x82]) + (bytes([0xd8, 0x2a, 0x58, 0x27, 0x00]) + cid_v0) * 2
+    d2 = api.blake2b256_batch([txmeta])
+    assert J.cid_to_string(pre + bytes(d2[0])) == FILECOIN_EMPTY_TXMETA
+    assert J.cid_to_string(pre + bytes(d[1])) == FILECOIN_EMPTY_ARR
+    assert J.cid_to_string(pre + bytes(d[2])) == FILECOIN_EMPTY_HAMT
+
+
 def test_json_bundle_verified_through_the_c_abi_alone(api, oracle_mod, synth_mod):
     """The flow a non-Rust host has: EventProofBundle as JSON text → ipcfp_bundle_from_json → witness store with every block
     Blake2b-checked → ipcfp_verify_event_proofs, with the tipset fields exactly as the parser recovered them from the proofs."""
@@ -66,18 +81,3 @@ def test_json_bundle_verified_through_the_c_abi_alone(api, oracle_mod, synth_mod
     finally:
         L.ipcfp_store_destroy(store)
         pb.close()
-
-
-def test_public_filecoin_constants_on_the_gpu(api):
-    """The chain's own constants (see tests/test_oracle_cpu.py::test_public_filecoin_constants_pin_the_encodings) through the GPU's
-    Blake2b-256: empty v0 AMT → empty TxMeta, builtin-actors' EMPTY_ARR_CID, the empty HAMT node."""
-    from ipc_filecoin_proofs_b200 import bundle_json as J
-    from tests.test_oracle_cpu import (EMPTY_AMT_V0, EMPTY_AMT_V3, EMPTY_HAMT_NODE, FILECOIN_EMPTY_ARR, FILECOIN_EMPTY_HAMT, FILECOIN_EMPTY_TXMETA)
-    pre = bytes([0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20])
-    d = api.blake2b256_batch([EMPTY_AMT_V0, EMPTY_AMT_V3, EMPTY_HAMT_NODE])
-    cid_v0 = pre + bytes(d[0])
-    txmeta = bytes([0x82]) + (bytes([0xd8, 0x2a, 0x58, 0x27, 0x00]) + cid_v0) * 2
-    d2 = api.blake2b256_batch([txmeta])
-    assert J.cid_to_string(pre + bytes(d2[0])) == FILECOIN_EMPTY_TXMETA
-    assert J.cid_to_string(pre + bytes(d[1])) == FILECOIN_EMPTY_ARR
-    assert J.cid_to_string(pre + bytes(d[2])) == FILECOIN_EMPTY_HAMT
