@@ -61,3 +61,40 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "receipts/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_rust_shim_uses_only_declared_bindings():
+    """integration/rust/gpu.rs cannot be compiled here (no Rust toolchain); at least every `sys::` item it names must exist in the -sys
+    crate and every call must pass as many arguments as the declaration takes."""
+    sys_rs = open(os.path.join(ROOT, "integration", "rust", "ipcfp-sys", "src", "lib.rs")).read()
+    shim = open(os.path.join(ROOT, "integration", "rust", "gpu.rs")).read()
+    fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (ipcfp_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(?:->[^;]*)?;", sys_rs, re.S)}
+    consts = set(re.findall(r"pub const (IPCFP_[A-Z0-9_]+)", sys_rs))
+    types = set(re.findall(r"pub (?:struct|type) (ipcfp_[a-z0-9_]+)", sys_rs))
+    used = set(re.findall(r"sys::([A-Za-z0-9_]+)", shim))
+    assert used, "the shim names no binding at all?"
+    unknown = {u for u in used if u not in fns and u not in consts and u not in types}
+    assert not unknown, unknown
+
+    def n_args(text):
+        depth, n, any_tok = 0, 0, False
+        for ch in text:
+            if ch in "([{<":
+                depth += 1
+            elif ch in ")]}>":
+                depth -= 1
+            elif ch == "," and depth == 0:
+                n += 1
+                continue
+            if not ch.isspace():
+                any_tok = True
+        return (n + 1) if any_tok and not text.rstrip().endswith(",") else n
+
+    for m in re.finditer(r"sys::(ipcfp_[a-z0-9_]+)\s*\(", shim):
+        name = m.group(1)
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(shim[i], 0)
+            i += 1
+        call_args = shim[m.end():i - 1].replace("->", "")
+        assert n_args(call_args) == n_args(fns[name].replace("->", "")), (name, call_args)
