@@ -769,9 +769,13 @@ struct TipsetIn {
 static TipsetIn tipset_in(const ipcfp_tipset_desc* t) {
     TipsetIn x;
     x.parent_epoch = t->parent_epoch; x.child_epoch = t->child_epoch;
-    for (uint32_t i = 0; i < t->n_parents; i++) { x.parent_cids.push_back(cid_from(t->parent_cids + 38 * i)); x.txmeta.push_back(cid_from(t->parent_txmeta_cids + 38 * i)); }
-    x.child_cid = cid_from(t->child_cid);
-    x.receipts_root = cid_from(t->receipts_root);
+    // a descriptor recovered from a bundle (ipcfp_bundle_from_json) carries only what the verifiers read: no TxMeta CIDs, no receipts root
+    for (uint32_t i = 0; i < t->n_parents; i++) {
+        x.parent_cids.push_back(cid_from(t->parent_cids + 38 * i));
+        if (t->parent_txmeta_cids) x.txmeta.push_back(cid_from(t->parent_txmeta_cids + 38 * i));
+    }
+    if (t->child_cid) x.child_cid = cid_from(t->child_cid);
+    if (t->receipts_root) x.receipts_root = cid_from(t->receipts_root);
     if (t->child_parent_state_root) x.child_state_root_json = cid_from(t->child_parent_state_root);
     x.n_receipts = t->n_receipts; x.events_roots = t->events_roots; x.has_root = t->has_events_root;
     return x;

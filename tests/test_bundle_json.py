@@ -1,5 +1,6 @@
 """JSON wire format of the proof bundles (reference common/bundle.rs, events/bundle.rs, storage/bundle.rs).
 CPU only: the POD results come from the oracle — they have exactly the layout the engine returns through the C ABI."""
+import ctypes as C
 import base64
 import json
 from types import SimpleNamespace
@@ -177,6 +178,15 @@ def test_c_abi_json_parser_round_trip(oracle_mod, ts3_small, ts1):
     f1 = pb1.tipset_fields()
     assert (f1["parent_epoch"], f1["child_epoch"]) == (int(ts1.parent_epoch), int(ts1.child_epoch))
     assert f1["parent_cids"] == bytes(np.asarray(ts1.parent_cids, dtype=np.uint8).reshape(-1)) and f1["child_cid"] == bytes(ts1.child_cid)
+    # the flow of tests/test_zz_witness_by_reference.py::test_json_bundle_verified_through_the_c_abi_alone with the restated verifier in
+    # the GPU verifier's place: witness, proofs AND tipset descriptor exactly as the C parser recovered them (no TxMeta CIDs, no receipts root)
+    n1 = int(pb1.c.n_event_proofs)
+    res = np.zeros(n1, dtype=np.uint8)
+    sp1 = spec_of(ts1)
+    st = oracle_mod.lib().oracle_verify_event_proofs(C.byref(pb1.c.witness), C.byref(pb1.c.tipset), pb1.c.event_proofs, n1, pb1.c.data_blob,
+                                                     C.byref(sp1), res.ctypes.data)
+    assert st == 0 and n1 == len(r1.proofs) > 0 and res.all()
+    pb1.close()
 
 
 def test_c_abi_json_parser_refuses_malformed_input(oracle_mod, ts1):
