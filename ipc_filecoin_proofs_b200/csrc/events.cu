@@ -158,8 +158,14 @@ __global__ void k_check_exec(const uint32_t* __restrict__ match_rel, uint64_t n_
     const uint64_t i = lo + match_rel[t];
     if (i >= *n_exec) report_error(err, ST_PASS2, i, 0 /* DC_MISSING_EXEC, ranked before every other code at the same receipt */, 0);
 }
+// a.per_warp: one matching receipt per WARP (lane 0 walks). A matching receipt is a chain of dependent accesses (hash probe → record →
+// strict decode of a 349–413 B node, 7 levels at 1 M receipts, then its events AMT), and 32 lanes on 32 different paths execute that
+// chain serialised by divergence: 1 020 matches in 8 CTAs kept 8 of 148 SMs busy for 0.14 ms (profiles/r1_ncu_full_final.txt). One warp
+// per match is the shape that took k_read_slots from 0.85 to 0.125 ms (storage.cu); above 16 384 matches the grid fills the machine
+// either way and one match per thread is kept. Same per-item code, so results are identical by construction.
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.per_warp) { if (threadIdx.x & 31) return; t >>= 5; }
     if (t >= a.n_match) return;
     pass2_item(a, t);
 }
@@ -836,7 +842,8 @@ ipcfp_event_result* generate_event_proof(Store* s, const ipcfp_tipset_desc* /*t*
         p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = exec_raw.p; p2.exec_idx = exec_idx.p; p2.n_exec = n_exec_dev;
         p2.wbits = wbits.p; p2.err = dw; p2.cnt = cnt.p; p2.proof_base = pbase.p; p2.byte_base = bbase.p;
         p2.proofs = d_proofs.p; p2.blob = d_blob.p; p2.any_skip = any_skip_dev; p2.resolve_msg = sharded ? 0 : 1;
-        k_pass2<<<div_up(M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
+        p2.per_warp = (M <= 16384 && !getenv("IPCFP_PASS2_PER_THREAD")) ? 1 : 0;
+        k_pass2<<<div_up(p2.per_warp ? M * 32 : M, 128), 128, 0, st>>>(p2); IPCFP_LAUNCH_CHECK();
     }
     if (xch) {
         // pass 2 did not wait for the cross-shard exchange; now that both are done: the global n_exec, the raw positions of this rank's

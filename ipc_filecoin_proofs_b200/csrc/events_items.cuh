@@ -185,6 +185,7 @@ struct Pass2Args {
     ipcfp_event_proof* proofs;
     uint8_t* blob;
     uint32_t* any_skip;            // set when a matching receipt is absent from the receipts AMT
+    uint32_t per_warp;             // 1: one matching receipt per warp (lane 0 walks); 0: one per thread
     uint32_t resolve_msg;          // 1: exec.get(i) check + message CID from exec_cids; 0: neither (shard: the execution order spans shards and
                                    // is resolved afterwards — by the caller, or by the in-library protocol with k_check_exec)
 };

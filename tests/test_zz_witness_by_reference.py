@@ -40,6 +40,17 @@ def test_by_reference_general_walk(api, oracle_mod, synth_mod, monkeypatch):
     _check(api, oracle_mod, synth_mod.Tipset(synth_mod.default_params(seed=7, n_receipts=700, events_per_receipt=5, match_ppm=50000, n_parents=3, dup_msgs=4)))
 
 
+def test_pass2_one_match_per_thread_variant(api, oracle_mod, synth_mod, monkeypatch):
+    """k_pass2 runs one matching receipt per warp up to 16 384 matches and one per thread above; IPCFP_PASS2_PER_THREAD forces the latter
+    so that both launch shapes stay covered at test sizes (same per-item code: pass2_item)."""
+    monkeypatch.setenv("IPCFP_PASS2_PER_THREAD", "1")
+    for ts in (synth_mod.Tipset(synth_mod.config_params(2)),
+               synth_mod.Tipset(synth_mod.default_params(seed=11, n_receipts=3000, events_per_receipt=6, match_ppm=200000, n_parents=2, dup_msgs=3))):
+        exp = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec_of(ts))
+        got = api.BlockStore.from_tipset(ts, verify_cids=True).generate_event_proof(ts, spec_of(ts))
+        assert_event_results_equal(got, exp)
+
+
 def test_public_filecoin_constants_on_the_gpu(api):
     """The chain's own constants (see tests/test_oracle_cpu.py::test_public_filecoin_constants_pin_the_encodings) through the GPU's
     Blake2b-256: empty v0 AMT → empty TxMeta, builtin-actors' EMPTY_ARR_CID, the empty HAMT node."""
