@@ -589,7 +589,7 @@ static std::array<uint8_t, 32> ascii_to_bytes32(const char* s) {
 static std::array<uint8_t, 32> left_pad_32(const Bytes& v) {
     std::array<uint8_t, 32> out{};
     if (v.size() >= 32) { memcpy(out.data(), v.data() + v.size() - 32, 32); return out; }
-    memcpy(out.data() + 32 - v.size(), v.data(), v.size());
+    if (!v.empty()) memcpy(out.data() + 32 - v.size(), v.data(), v.size());
     return out;
 }
 // events/generator.rs:23-41

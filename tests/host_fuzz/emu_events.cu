@@ -86,14 +86,14 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     std::vector<uint32_t> wbits((B.n + 31) / 32 + 8, 0);
     // ---- k_setup
     bool missing_base = false;
-    auto base = [&](const uint8_t* cid) { int32_t b = store_lookup(sv, cid); if (b < 0) missing_base = true; else witness_mark(wbits.data(), (uint32_t)b); };
+    auto base = [&](const uint8_t* cid) { int32_t b = store_lookup_host_cid(sv, cid); if (b < 0) missing_base = true; else witness_mark(wbits.data(), (uint32_t)b); };
     for (uint32_t b = 0; b < P; b++) base(td.parent_cids + 38 * b);
     base(td.child_cid); base(td.receipts_root);
     for (uint32_t b = 0; b < P; b++) base(td.parent_txmeta_cids + 38 * b);
     std::vector<uint32_t> heights(namt, 0), f_blk(namt, 0), f_meta(namt, AMT_SENTINEL);
     std::vector<uint64_t> counts(namt, 0);
     for (uint32_t b = 0; b < P; b++) {
-        int32_t tb = store_lookup(sv, td.parent_txmeta_cids + 38 * b);
+        int32_t tb = store_lookup_host_cid(sv, td.parent_txmeta_cids + 38 * b);
         if (tb < 0) { report_tx_error(&txerr, 3 * b, 0, 31, DC_MISSING, 0); continue; }
         witness_mark(wbits.data(), (uint32_t)tb);
         uint32_t len;
@@ -120,7 +120,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     }
     uint32_t receipts_root_blk = 0;
     {
-        int32_t rb = store_lookup(sv, td.receipts_root);
+        int32_t rb = store_lookup_host_cid(sv, td.receipts_root);
         if (rb < 0) report_error(&err, ST_RECEIPTS_ROOT, 0, DC_MISSING, 0);
         else {
             witness_mark(wbits.data(), (uint32_t)rb);
@@ -195,7 +195,11 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     // ---- matcher (EventMatcher::new)
     Matcher m;
     memset(&m, 0, sizeof m);
-    { Digest d; keccak256((const uint8_t*)sig, (uint32_t)strlen(sig), d); memcpy(m.t0, d.w, 32); }
+    {   // zero padded to whole 8-byte words, 8-byte aligned: what k_setup's staging block holds (csrc/events.cu)
+        std::vector<uint64_t> padded(strlen(sig) / 8 + 2, 0);
+        memcpy(padded.data(), sig, strlen(sig));
+        Digest d; keccak256((const uint8_t*)padded.data(), (uint32_t)strlen(sig), d); memcpy(m.t0, d.w, 32);
+    }
     { uint8_t t1[32]; memset(t1, 0, 32); size_t n1 = strlen(topic1); memcpy(t1, topic1, n1 < 32 ? n1 : 32); memcpy(m.t1, t1, 32); }
     m.actor = actor; m.has_actor = has_actor ? 1 : 0;
     // ---- pass 1 (pass1_body's per-receipt sequence)
@@ -203,7 +207,7 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     std::vector<uint32_t> cnt(N + 1, 0), nby(N + 1, 0), match_rel;
     for (uint64_t i = lo; i < hi; i++) {
         if (!td.has_events_root[i]) continue;
-        int32_t blk = store_lookup(sv, td.events_roots + 38 * i);
+        int32_t blk = store_lookup_host_cid(sv, td.events_roots + 38 * i);
         if (blk < 0) { report_error(&err, ST_PASS1, i, DC_MISSING, 0); continue; }
         o.touched.push_back((uint32_t)blk);
         uint32_t len;
@@ -236,9 +240,13 @@ static bool engine(const Blocks& B, const ipcfp_tipset_desc& td, const char* sig
     std::vector<ipcfp_event_proof> proofs(n_proofs + 1);
     std::vector<uint8_t> blob(n_bytes + 16);
     uint32_t any_skip = 0;
+    // the device copy of the events roots is n*38 + 64 bytes (csrc/events.cu, tipset upload): CIDs are loaded as aligned 8-byte words
+    std::vector<uint8_t> roots_padded(td.n_receipts * 38 + 64, 0);
+    if (td.n_receipts) memcpy(roots_padded.data(), td.events_roots, td.n_receipts * 38);
     Pass2Args p2;
+    p2.per_warp = 0;
     memset(&p2, 0, sizeof p2);
-    p2.store = sv; p2.store_dev = &sv; p2.m_dev = &m; p2.m = m; p2.events_roots = td.events_roots; p2.lo = 0; p2.match_rel = match_rel.data(); p2.n_match = match_rel.size();
+    p2.store = sv; p2.store_dev = &sv; p2.m_dev = &m; p2.m = m; p2.events_roots = roots_padded.data(); p2.lo = 0; p2.match_rel = match_rel.data(); p2.n_match = match_rel.size();
     p2.receipts_root_blk = receipts_root_blk; p2.exec_cids = vals.data(); p2.exec_idx = exec_idx.data(); p2.n_exec = &n_exec;
     p2.wbits = wbits.data(); p2.err = &err; p2.cnt = cnt.data(); p2.proof_base = pbase.data(); p2.byte_base = bbase.data();
     p2.proofs = proofs.data(); p2.blob = blob.data(); p2.any_skip = &any_skip; p2.resolve_msg = sharded ? 0 : 1;
@@ -351,7 +359,8 @@ int main(int argc, char** argv) {
     uint64_t muts = argc > 2 ? strtoull(argv[2], nullptr, 10) : 60;
     rs = argc > 3 ? strtoull(argv[3], nullptr, 10) : 0xE7E47ull;
     {   // keccak on the host build (the matcher depends on it)
-        Digest d; keccak256((const uint8_t*)"abc", 3, d);
+        alignas(8) static const uint8_t abc[16] = {'a', 'b', 'c'};   // the device keccak reads whole aligned 8-byte words: zero padded, as k_setup's input is
+        Digest d; keccak256(abc, 3, d);
         uint8_t ref[32]; oracle_keccak256((const uint8_t*)"abc", 3, ref);
         if (memcmp(d.w, ref, 32)) { fprintf(stderr, "host build of keccak256 is broken\n"); return 2; }
     }

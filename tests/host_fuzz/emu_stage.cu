@@ -51,14 +51,14 @@ static void put_head(std::vector<uint8_t>& o, int major, uint64_t v) {
 }
 static uint8_t T0[32], T1[32];
 static bool g_canonical = false;   // the named synthetic shape: 8 events of t1, t2, d (32 bytes each), emitter < 2^16, bw 5
-static void put_entry(std::vector<uint8_t>& o, uint64_t flags, const char* key, uint64_t codec, size_t vlen, const uint8_t* fixed = nullptr) {
+static void put_entry(std::vector<uint8_t>& o, uint64_t flags, const char* key, uint64_t codec, size_t vlen, const uint8_t* fixed = nullptr, size_t fixed_len = 32) {
     put_head(o, 4, 4);
     put_head(o, 0, flags);
     put_head(o, 3, strlen(key));
     o.insert(o.end(), key, key + strlen(key));
     put_head(o, 0, codec);
     put_head(o, 2, vlen);
-    for (size_t i = 0; i < vlen; i++) o.push_back(fixed ? fixed[i] : (uint8_t)rnd());
+    for (size_t i = 0; i < vlen; i++) o.push_back(fixed && i < fixed_len ? fixed[i] : (uint8_t)rnd());   // (a 33..39-byte value with a fixed 32-byte head: found by ASan)
 }
 static void make_event(std::vector<uint8_t>& o) {
     if (g_canonical) {
@@ -74,7 +74,7 @@ static void make_event(std::vector<uint8_t>& o) {
     if (shape == 0) {
         put_head(o, 4, 2);
         uint8_t tp[64]; memcpy(tp, T0, 32); memcpy(tp + 32, T1, 32);
-        put_entry(o, 3, "topics", 0x55, hit ? 64 : 32 * (rnd() % 5), hit ? tp : nullptr);
+        put_entry(o, 3, "topics", 0x55, hit ? 64 : 32 * (rnd() % 5), hit ? tp : nullptr, 64);
         put_entry(o, 3, "data", 0x55, rnd() % 300);
     } else {
         unsigned nt = 1 + (unsigned)(rnd() % 4);

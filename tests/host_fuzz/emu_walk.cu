@@ -55,13 +55,13 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
         const uint64_t lo = td.n_receipts * rank / world, hi = td.n_receipts * (rank + 1) / world;
         // ---- what k_setup does (csrc/events.cu): base witness marks, TxMeta → AMT roots → frontier seeds
         std::vector<uint32_t> wbits((n + 31) / 32 + 8, 0);
-        auto mark_cid = [&](const uint8_t* cid) { int32_t b = store_lookup(sv, cid); if (b < 0) return false; witness_mark(wbits.data(), (uint32_t)b); return true; };
+        auto mark_cid = [&](const uint8_t* cid) { int32_t b = store_lookup_host_cid(sv, cid); if (b < 0) return false; witness_mark(wbits.data(), (uint32_t)b); return true; };
         for (uint32_t b = 0; b < P; b++) if (!mark_cid(td.parent_cids + 38 * b) || !mark_cid(td.parent_txmeta_cids + 38 * b)) return fail("base block missing");
         if (!mark_cid(td.child_cid) || !mark_cid(td.receipts_root)) return fail("base block missing");
         std::vector<uint32_t> heights(namt), f_blk(namt), f_meta(namt);
         std::vector<uint64_t> counts(namt), f_base(namt, 0);
         for (uint32_t b = 0; b < P; b++) {
-            int32_t tb = store_lookup(sv, td.parent_txmeta_cids + 38 * b);
+            int32_t tb = store_lookup_host_cid(sv, td.parent_txmeta_cids + 38 * b);
             uint32_t len;
             const uint8_t* p = store_block(sv, (uint32_t)tb, len);
             Rd r(p, len);
@@ -141,7 +141,7 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
         for (uint64_t i = 0; i < er->witness.n_blocks; i++) exp.insert(std::vector<uint8_t>(er->witness.cids + 38 * i, er->witness.cids + 38 * i + 38));
         {   // ---- the GENERAL walk over the same share must give the same list and the same recorded blocks
             std::vector<uint32_t> wb2((n + 31) / 32 + 8, 0);
-            auto mark2 = [&](const uint8_t* cid) { int32_t b = store_lookup(sv, cid); if (b >= 0) witness_mark(wb2.data(), (uint32_t)b); };
+            auto mark2 = [&](const uint8_t* cid) { int32_t b = store_lookup_host_cid(sv, cid); if (b >= 0) witness_mark(wb2.data(), (uint32_t)b); };
             for (uint32_t b = 0; b < P; b++) { mark2(td.parent_cids + 38 * b); mark2(td.parent_txmeta_cids + 38 * b); }
             mark2(td.child_cid); mark2(td.receipts_root);
             for (uint32_t k = 0; k < namt; k++) witness_mark(wb2.data(), f_blk[k]);
@@ -163,7 +163,7 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
             for (uint32_t k = 0; k < namt; k++) fprintf(stderr, "  amt %u: count %llu height %u range [%llu,%llu) clipped [%llu,%llu)\n", k, (unsigned long long)counts[k], heights[k],
                     (unsigned long long)rlo[k], (unsigned long long)rhi[k], (unsigned long long)plan.per_amt[2ull * namt + k], (unsigned long long)plan.per_amt[3ull * namt + k]);
             for (auto& c : exp) if (!got.count(c)) {
-                int32_t b = store_lookup(sv, c.data());
+                int32_t b = store_lookup_host_cid(sv, c.data());
                 uint32_t len = 0;
                 const uint8_t* p = b >= 0 ? store_block(sv, (uint32_t)b, len) : nullptr;
                 fprintf(stderr, "  only in the oracle's witness: block %d (%u bytes):", b, len);

@@ -51,4 +51,13 @@ struct HostStore {
 };
 
 
+// store_lookup on a CID that lives in an exactly-38-byte HOST buffer. The device code loads CIDs with aligned 8-byte words and funnel
+// shifts (load_digest, common.cuh), i.e. it may touch up to 7 bytes either side of the 38; every DEVICE buffer a kernel reads CIDs from
+// is padded for that (arena pads, `+ 64` on the tipset arrays). The emulation gives the same guarantee with a padded copy, so that the
+// harnesses can run under AddressSanitizer and everything it still reports is a real out-of-bounds access of the device code.
+static inline int32_t store_lookup_host_cid(const StoreView& sv, const uint8_t* cid38) {
+    alignas(16) uint8_t pad[64] = {0};
+    memcpy(pad + 8, cid38, 38);
+    return store_lookup(sv, pad + 8);
+}
 }  // namespace ipcfp

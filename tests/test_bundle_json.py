@@ -228,3 +228,39 @@ def test_c_abi_json_parser_refuses_malformed_input(oracle_mod, ts1):
     if len(doc["proofs"]) > 1:                                                                                                # proofs of two tipsets in one bundle
         assert status(mutated(lambda d: d["proofs"][1].__setitem__("child_epoch", d["proofs"][1]["child_epoch"] + 1))) == A.ERR_UNSUPPORTED
     assert status(mutated(lambda d: d["proofs"][0].pop("event_index"))) == A.ERR_INVALID_ARG                                  # missing field
+
+
+def test_c_abi_json_parser_mutation_fuzz_under_sanitizers(oracle_mod, ts3_small, ts1, tmp_path):
+    """tests/host_fuzz/fuzz_json.cpp: csrc/bundle_parse.cpp built with AddressSanitizer + UBSan (plain g++), fed mutated copies of an
+    EventProofBundle and a UnifiedProofBundle as exact-size heap buffers. Accepted texts must name only bytes inside the returned
+    object's own buffers; refused ones must carry a documented status; no over-read of the input, no leak."""
+    import os
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    build = os.path.join(root, "tests", "host_fuzz", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "fuzz_json")
+    cc = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                         os.path.join(root, "tests", "host_fuzz", "fuzz_json.cpp"), os.path.join(root, "ipc_filecoin_proofs_b200", "csrc", "bundle_parse.cpp"),
+                         os.path.join(root, "ipc_filecoin_proofs_b200", "csrc", "bundle_json.cpp")], capture_output=True, text=True)
+    if cc.returncode != 0 and "sanitize" in cc.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    r1 = oracle_mod.Store.from_tipset(ts1).generate_event_proof(ts1, spec_of(ts1))
+    slot = oracle_mod.compute_mapping_slot((b"calib-subnet-1" + bytes(32))[:32], 0)
+    b = oracle_mod.Store.from_tipset(ts3_small).generate_proof_bundle(ts3_small, [(1001, slot), (1003, slot)], [spec_of(ts3_small)])
+    seeds = []
+    for name, doc in (("ev.json", J.event_bundle(ts1, r1)), ("uni.json", J.unified_bundle(ts3_small, b))):
+        p = tmp_path / name
+        p.write_text(J.dumps(doc))
+        seeds.append(str(p))
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+    out = subprocess.run([exe, "6000", "20260923"] + seeds, capture_output=True, text=True, env=env)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert out.stdout.startswith("ok: 12000 mutated bundles parsed"), out.stdout
+    accepted = int(out.stdout.split("parsed:")[1].split()[0])
+    assert 200 < accepted < 11000, out.stdout   # both outcomes must be exercised
