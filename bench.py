@@ -549,7 +549,9 @@ def run_engine(args, world, rank, local):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": n_total / (e2e_ms / 1e3), "unit": "receipts/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(stats["d2h_bytes"]),
-                    "parts_ms_rank0": {"store_create": [p[0] for p in e2e_parts[3:]], "generate": [p[1] for p in e2e_parts[3:]], "destroy": [p[2] for p in e2e_parts[3:]]}},
+                    "parts_ms_rank0": {"store_create": [p[0] for p in e2e_parts[3:]], "generate": [p[1] for p in e2e_parts[3:]], "destroy": [p[2] for p in e2e_parts[3:]]},
+                    # what bounds e2e: the H2D of every block over PCIe (ingest = copy + index + Cid ranks + Blake2b check, all under the copy)
+                    "ingest_h2d_gbs_rank0": float(h2d_bytes / (max(np.median([p[0] for p in e2e_parts[3:]]), 1e-6) / 1e3) / 1e9)},
             "storage": storage,
             "gpu_launches": int(launches),
             "clocks": clocks,

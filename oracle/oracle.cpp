@@ -37,6 +37,8 @@
 #include <variant>
 #include <vector>
 
+// memcpy whose source may be an empty container's data() (nullptr with n == 0 — flagged by UBSan, harmless in practice)
+static inline void copy_bytes(void* dst, const void* src, size_t n) { if (n) memcpy(dst, src, n); }
 namespace orc {
 
 typedef std::vector<uint8_t> Bytes;
@@ -91,9 +93,9 @@ static bool cid_less(const Cid& a, const Cid& b) {
 }
 struct CidLess { bool operator()(const Cid& a, const Cid& b) const { return cid_less(a, b); } };
 struct CidHash {
-    size_t operator()(const Cid& c) const { uint64_t h; memcpy(&h, c.b.data() + 6, 8); uint64_t g; memcpy(&g, c.b.data() + 30, 8); return (size_t)(h ^ (g * 0x9E3779B97F4A7C15ULL)); }
+    size_t operator()(const Cid& c) const { uint64_t h; copy_bytes(&h, c.b.data() + 6, 8); uint64_t g; copy_bytes(&g, c.b.data() + 30, 8); return (size_t)(h ^ (g * 0x9E3779B97F4A7C15ULL)); }
 };
-static Cid cid_from(const uint8_t* p) { Cid c; memcpy(c.b.data(), p, 38); return c; }
+static Cid cid_from(const uint8_t* p) { Cid c; copy_bytes(c.b.data(), p, 38); return c; }
 static std::string cid_hex(const Cid& c) {
     static const char* hx = "0123456789abcdef";
     std::string s;
@@ -490,7 +492,7 @@ template <class V> static HamtNode<V> decode_hamt_node(const Bytes& raw) {
     Bytes bf = d.bytes();
     if (bf.size() > 32) fail_decode("hamt: bitfield too long");
     memset(nd.bitfield, 0, 32);
-    memcpy(nd.bitfield + 32 - bf.size(), bf.data(), bf.size());
+    copy_bytes(nd.bitfield + 32 - bf.size(), bf.data(), bf.size());
     uint64_t np = d.array();
     if (np > d.n) fail_decode("hamt: pointers too long");
     for (uint64_t i = 0; i < np; i++) {
@@ -555,7 +557,7 @@ static std::optional<EvmLog> extract_evm_log(const ActorEvent& ev) {
         const Bytes& tb = *it->second;
         if (tb.size() % 32 != 0) return std::nullopt;
         EvmLog log;
-        for (size_t o = 0; o < tb.size(); o += 32) { std::array<uint8_t, 32> t; memcpy(t.data(), tb.data() + o, 32); log.topics.push_back(t); }
+        for (size_t o = 0; o < tb.size(); o += 32) { std::array<uint8_t, 32> t; copy_bytes(t.data(), tb.data() + o, 32); log.topics.push_back(t); }
         auto dt = m.find("data");
         if (dt != m.end()) log.data = *dt->second;
         return log;
@@ -567,7 +569,7 @@ static std::optional<EvmLog> extract_evm_log(const ActorEvent& ev) {
         if (k == m.end()) break;
         if (k->second->size() != 32) return std::nullopt;
         std::array<uint8_t, 32> t;
-        memcpy(t.data(), k->second->data(), 32);
+        copy_bytes(t.data(), k->second->data(), 32);
         log.topics.push_back(t);
     }
     if (log.topics.empty()) return std::nullopt;
@@ -583,13 +585,13 @@ static std::array<uint8_t, 32> hash_event_signature(const char* s) {
 static std::array<uint8_t, 32> ascii_to_bytes32(const char* s) {
     std::array<uint8_t, 32> r{};
     size_t n = std::min<size_t>(strlen(s), 32);
-    memcpy(r.data(), s, n);
+    copy_bytes(r.data(), s, n);
     return r;
 }
 static std::array<uint8_t, 32> left_pad_32(const Bytes& v) {
     std::array<uint8_t, 32> out{};
-    if (v.size() >= 32) { memcpy(out.data(), v.data() + v.size() - 32, 32); return out; }
-    if (!v.empty()) memcpy(out.data() + 32 - v.size(), v.data(), v.size());
+    if (v.size() >= 32) { copy_bytes(out.data(), v.data() + v.size() - 32, 32); return out; }
+    if (!v.empty()) copy_bytes(out.data() + 32 - v.size(), v.data(), v.size());
     return out;
 }
 // events/generator.rs:23-41
@@ -796,7 +798,7 @@ static std::vector<Cid> collect_exec_list(const Blockstore& bs, const std::vecto
             for (const Cid* c : {&roots.first, &roots.second}) { const uint8_t h[5] = {0xd8, 0x2a, 0x58, 0x27, 0x00}; enc.insert(enc.end(), h, h + 5); enc.insert(enc.end(), c->b.begin(), c->b.end()); }
             Cid re;
             const uint8_t pre[6] = {0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20};
-            memcpy(re.b.data(), pre, 6);
+            copy_bytes(re.b.data(), pre, 6);
             cpu_crypto::blake2b256(enc.data(), enc.size(), re.b.data() + 6);
             if (re != tx) throw Err(IPCFP_ERR_CID_MISMATCH, "TxMeta mismatch", b);
         }
@@ -1001,7 +1003,7 @@ static StorageProofRec generate_storage_proof(const Blockstore& net, const Tipse
     collector.collect_from_recording(storage_recorder);
     StorageProofRec p;
     p.actor_id = actor_id; p.actor_state_cid = actor.state; p.storage_root = storage_root;
-    memcpy(p.slot.data(), slot, 32);
+    copy_bytes(p.slot.data(), slot, 32);
     p.found = raw.has_value();
     p.raw_len = raw ? (uint32_t)raw->size() : 0;
     p.value = left_pad_32(raw ? *raw : Bytes());
@@ -1040,7 +1042,7 @@ static ipcfp_event_result* box_event(EventGenOut& o) {
         for (auto& t : p.topics) b->data.insert(b->data.end(), t.begin(), t.end());
         q.data_off = b->data.size(); q.data_len = (uint32_t)p.data.size();
         b->data.insert(b->data.end(), p.data.begin(), p.data.end());
-        memcpy(q.message_cid, p.message_cid.b.data(), 38);
+        copy_bytes(q.message_cid, p.message_cid.b.data(), 38);
         b->proofs.push_back(q);
     }
     memset(&b->r, 0, sizeof b->r);
@@ -1073,9 +1075,9 @@ static ipcfp_storage_result* box_storage(std::vector<StorageProofRec>& recs, dou
         ipcfp_storage_proof q;
         memset(&q, 0, sizeof q);
         q.actor_id = p.actor_id;
-        memcpy(q.actor_state_cid, p.actor_state_cid.b.data(), 38);
-        memcpy(q.storage_root, p.storage_root.b.data(), 38);
-        memcpy(q.slot, p.slot.data(), 32); memcpy(q.value, p.value.data(), 32);
+        copy_bytes(q.actor_state_cid, p.actor_state_cid.b.data(), 38);
+        copy_bytes(q.storage_root, p.storage_root.b.data(), 38);
+        copy_bytes(q.slot, p.slot.data(), 32); copy_bytes(q.value, p.value.data(), 32);
         q.found = p.found; q.raw_len = p.raw_len;
         b->proofs.push_back(q);
         for (auto& blk : p.blocks) b->spec_idx.push_back(pos[blk.cid]);
@@ -1152,7 +1154,7 @@ ipcfp_status oracle_message_list(const oracle_store* s, const ipcfp_tipset_desc*
             auto roots = decode_txmeta(raw);
             for (const Cid* r : {&roots.first, &roots.second}) {
                 auto amt = Amt<Cid>::load(*r, s->bs, 0);
-                amt.for_each([&](uint64_t, const Cid& c) { if (k < cap) memcpy(out38 + 38 * k, c.b.data(), 38); k++; });
+                amt.for_each([&](uint64_t, const Cid& c) { if (k < cap) copy_bytes(out38 + 38 * k, c.b.data(), 38); k++; });
             }
         }
         *n = k;
@@ -1168,7 +1170,7 @@ ipcfp_status oracle_hamt_node_lookup(const uint8_t* p, uint64_t n, int vkind, ui
     try {
         Bytes raw(p, p + n), k(key, key + keylen);
         *out_len = 0;
-        auto put = [&](const uint8_t* q, size_t m) { *out_len = m; memcpy(out, q, std::min<size_t>(m, (size_t)out_cap)); };
+        auto put = [&](const uint8_t* q, size_t m) { *out_len = m; copy_bytes(out, q, std::min<size_t>(m, (size_t)out_cap)); };
         auto on_link = [&](const Cid& c) { put(c.b.data(), 38); };
         if (vkind == 0) hamt_node_lookup_t<ActorState>(raw, idx, k, kind, [&](const ActorState& a) { put(a.state.b.data(), 38); }, on_link);
         else hamt_node_lookup_t<RawU8Vec>(raw, idx, k, kind, [&](const RawU8Vec& v) { put(v.v.data(), v.v.size()); }, on_link);
@@ -1190,7 +1192,7 @@ ipcfp_status oracle_decode_receipts_node(const uint8_t* p, uint64_t n, uint32_t 
         for (auto& v : nd.vals) if (v) {
             if (nv < cap) {
                 has_root[nv] = v->events_root ? 1 : 0;
-                if (v->events_root) memcpy(roots38 + 38 * nv, v->events_root->b.data(), 38);
+                if (v->events_root) copy_bytes(roots38 + 38 * nv, v->events_root->b.data(), 38);
             }
             nv++;
         }
@@ -1209,7 +1211,7 @@ ipcfp_status oracle_scan_events_block(const uint8_t* block, uint64_t n, uint64_t
         Cid c;
         memset(c.b.data(), 0, 38);
         static const uint8_t prefix[6] = {0x01, 0x71, 0xa0, 0xe4, 0x02, 0x20};
-        memcpy(c.b.data(), prefix, 6);
+        copy_bytes(c.b.data(), prefix, 6);
         bs.m.emplace(c, std::make_pair(block, (uint32_t)n));
         auto amt = Amt<StampedEvent>::load(c, bs, 3);
         uint64_t k = 0;
@@ -1243,9 +1245,9 @@ ipcfp_status oracle_decode_event(const uint8_t* p, uint64_t n, uint64_t* consume
         *data_len = 0;
         if (log) {
             *ntopics = (uint32_t)log->topics.size();
-            for (size_t k = 0; k < log->topics.size() && 32 * (k + 1) <= topics_cap; k++) memcpy(topics_out + 32 * k, log->topics[k].data(), 32);
+            for (size_t k = 0; k < log->topics.size() && 32 * (k + 1) <= topics_cap; k++) copy_bytes(topics_out + 32 * k, log->topics[k].data(), 32);
             *data_len = log->data.size();
-            memcpy(data_out, log->data.data(), std::min<size_t>(log->data.size(), (size_t)data_cap));
+            copy_bytes(data_out, log->data.data(), std::min<size_t>(log->data.size(), (size_t)data_cap));
         }
         return IPCFP_OK;
     } catch (const Err& e) {
@@ -1307,7 +1309,7 @@ ipcfp_status oracle_read_storage_slots(const oracle_store* s, const uint8_t root
                 b->found[i] = v.has_value();
                 b->raw_len[i] = v ? (uint32_t)v->size() : 0;
                 auto pv = left_pad_32(v ? *v : Bytes());
-                memcpy(&b->values[32 * i], pv.data(), 32);
+                copy_bytes(&b->values[32 * i], pv.data(), 32);
             } catch (Err& e) { e.index = i; throw; }
         }
         WitnessCollector col(s->bs);
@@ -1468,7 +1470,7 @@ void oracle_blake2b256(const uint8_t* in, uint64_t len, uint8_t out[32]) { cpu_c
 void oracle_sha256(const uint8_t* in, uint64_t len, uint8_t out[32]) { cpu_crypto::sha256(in, (size_t)len, out); }
 void oracle_compute_mapping_slot(const uint8_t key32[32], uint64_t slot_index, uint8_t out[32]) {  // storage/utils.rs:5-12
     uint8_t buf[64];
-    memcpy(buf, key32, 32);
+    copy_bytes(buf, key32, 32);
     memset(buf + 32, 0, 24);
     for (int i = 0; i < 8; i++) buf[56 + i] = (uint8_t)(slot_index >> (56 - 8 * i));
     cpu_crypto::keccak256(buf, 64, out);
@@ -1477,7 +1479,7 @@ uint64_t oracle_sort_unique_cids(uint8_t* cids, uint64_t n) {
     std::set<Cid, CidLess> s;
     for (uint64_t i = 0; i < n; i++) s.insert(cid_from(cids + 38 * i));
     uint64_t k = 0;
-    for (auto& c : s) { memcpy(cids + 38 * k, c.b.data(), 38); k++; }
+    for (auto& c : s) { copy_bytes(cids + 38 * k, c.b.data(), 38); k++; }
     return k;
 }
 

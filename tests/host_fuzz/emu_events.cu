@@ -369,8 +369,8 @@ int main(int argc, char** argv) {
         synth_params sp;
         synth_default_params(&sp);
         sp.seed = 4000 + c * 7 + (rs & 0xff);
-        static const uint64_t sizes[] = {1, 9, 40, 257, 700, 2000};
-        sp.n_receipts = sizes[rnd() % 6];
+        static const uint64_t sizes[] = {0, 1, 8, 9, 40, 64, 65, 257, 700, 2000};   // incl. the empty tipset and the AMT width boundaries
+        sp.n_receipts = sizes[rnd() % 10];
         static const uint32_t evs[] = {1, 3, 8, 8, 40, 300};
         sp.events_per_receipt = evs[rnd() % 6];
         if (sp.n_receipts * sp.events_per_receipt > 60000) sp.events_per_receipt = 8;

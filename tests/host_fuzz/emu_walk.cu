@@ -118,8 +118,9 @@ static int run_case(const synth_params& sp, uint32_t world, uint64_t* walked_nod
         }
         if (failflag) return fail("the dense walk raised its flag on a well-formed dense tipset", rank, world);
         // ---- raw list == the oracle's slice
-        const uint64_t glo = sharded ? (uint64_t)((__uint128_t)nraw_total * lo / td.n_receipts) : 0;
-        const uint64_t ghi = sharded ? (uint64_t)((__uint128_t)nraw_total * hi / td.n_receipts) : nraw_total;
+        // (a tipset without receipts has no shares to own: shard_amt_ranges, csrc/walk.cuh, gives every rank the empty range)
+        const uint64_t glo = sharded ? (td.n_receipts ? (uint64_t)((__uint128_t)nraw_total * lo / td.n_receipts) : 0) : 0;
+        const uint64_t ghi = sharded ? (td.n_receipts ? (uint64_t)((__uint128_t)nraw_total * hi / td.n_receipts) : 0) : nraw_total;
         if (plan.nraw != ghi - glo) return fail("share size", plan.nraw, ghi - glo);
         for (uint64_t k = 0; k < plan.nraw; k++) {
             uint8_t c[38];
@@ -199,9 +200,9 @@ int main(int argc, char** argv) {
         synth_default_params(&sp);
         uint64_t z = (seed + c) * 0x9E3779B97F4A7C15ull;
         auto rnd = [&]() { z ^= z << 13; z ^= z >> 7; z ^= z << 17; return z; };
-        static const uint64_t sizes[] = {1, 2, 7, 8, 9, 63, 64, 65, 100, 511, 513, 1000, 4097, 20000};
+        static const uint64_t sizes[] = {0, 1, 2, 7, 8, 9, 63, 64, 65, 100, 511, 513, 1000, 4097, 20000};
         sp.seed = seed * 1000 + c;
-        sp.n_receipts = sizes[rnd() % 14];
+        sp.n_receipts = sizes[rnd() % 15];
         sp.events_per_receipt = 1;
         sp.match_ppm = 0;
         sp.n_parents = 1 + (uint32_t)(rnd() % 4);

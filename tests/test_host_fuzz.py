@@ -15,20 +15,37 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SANITIZE = ["-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler", "-fno-omit-frame-pointer", "-g"]
+SAN_ENV = dict(ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
 
 
-def test_fast_paths_agree_with_strict_decoders():
+def _harness(name, with_synth=True, sanitize=None):
+    """Build tests/host_fuzz/<name>.cu for the HOST (nvcc host pass) with the oracle (and the synthetic builder) linked as the checker.
+    IPCFP_HOST_FUZZ_SANITIZE=1 (or sanitize=True) builds with AddressSanitizer + UBSan: the harnesses give the device code buffers
+    padded exactly as the engine's device buffers are (host_store.h), so an out-of-bounds access of the device code is a report."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
+    if sanitize is None:
+        sanitize = bool(os.environ.get("IPCFP_HOST_FUZZ_SANITIZE"))
     build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
     os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "fuzz_events")
-    src = os.path.join(ROOT, "tests", "host_fuzz", "fuzz_events.cu")
-    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe, src, os.path.join(ROOT, "oracle", "oracle.cpp"), "-lpthread"],
-                          cwd=ROOT)
+    exe = os.path.join(build, name + ("_san" if sanitize else ""))
+    cmd = [nvcc, "-std=c++17", "-O1" if sanitize else "-O2", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20091", "-o", exe,
+           os.path.join(ROOT, "tests", "host_fuzz", name + ".cu"), os.path.join(ROOT, "oracle", "oracle.cpp")]
+    if with_synth:
+        cmd.append(os.path.join(ROOT, "synth", "synth.cpp"))
+    cc = subprocess.run(cmd + (SANITIZE if sanitize else []) + ["-lpthread"], cwd=ROOT, capture_output=True, text=True)
+    if cc.returncode != 0 and sanitize and "sanitize" in cc.stderr:
+        pytest.skip("this host compiler has no sanitizer runtime")
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    return exe, (dict(os.environ, **SAN_ENV) if sanitize else None)
+
+
+def test_fast_paths_agree_with_strict_decoders():
+    exe, env = _harness("fuzz_events", with_synth=False)
     for seed in ("535", "20260922"):
-        out = subprocess.run([exe, "600000", seed], capture_output=True, text=True)
+        out = subprocess.run([exe, "600000", seed], capture_output=True, text=True, env=env)
         assert out.returncode == 0, out.stderr[-2000:]
         lines = [l for l in out.stdout.splitlines() if l.startswith("ok:")]
         assert len(lines) == 5, out.stdout
@@ -46,15 +63,8 @@ def test_dense_walk_emulated_on_cpu_matches_oracle():
     host and run level by level, item by item, lane by lane over a host copy of the block store (arena + BlockRec array + CID
     index laid out as ipcfp_store_create does), for whole tipsets and for every shard at world sizes 1, 2, 3 and 8 — against the
     oracle's raw message list and its recorded block set."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "emu_walk")
-    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(ROOT, "tests", "host_fuzz", "emu_walk.cu"),
-                           os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
-    out = subprocess.run([exe, "60", "11"], capture_output=True, text=True)
+    exe, env = _harness("emu_walk", with_synth=True)
+    out = subprocess.run([exe, "60", "11"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.startswith("ok: dense walk == general walk == oracle on the CPU for 60 tipsets"), out.stdout
 
@@ -65,16 +75,8 @@ def test_storage_path_emulated_on_cpu_matches_oracle():
     synthetic state trees (six EVM actors = the six root shapes A1/A2/A3/B1/B2/C, present / absent / special slots, a missing
     actor) and with one block of a proof path replaced by a mutated copy under the same CID: equal values, found flags, CIDs and
     per-proof recorded block sets, or the same status at the same spec index."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "emu_storage")
-    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20091", "-o", exe,
-                           os.path.join(ROOT, "tests", "host_fuzz", "emu_storage.cu"), os.path.join(ROOT, "oracle", "oracle.cpp"),
-                           os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
-    out = subprocess.run([exe, "8", "250", "77"], capture_output=True, text=True)
+    exe, env = _harness("emu_storage", with_synth=True)
+    out = subprocess.run([exe, "8", "250", "77"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.startswith("ok: storage path on the CPU == oracle for 8 state trees"), out.stdout
     runs_ok, runs_err = int(out.stdout.split(":")[2].split()[0]), int(out.stdout.split("equal,")[1].split()[0])
@@ -89,18 +91,32 @@ def test_event_path_emulated_on_cpu_matches_oracle():
     events AMTs, Case A, malformed events, null roots, duplicate messages), and the same status at the same index when ANY block
     the call reads (events blocks, receipts-AMT nodes, message-AMT nodes, TxMeta, headers) is mutated under its CID or missing —
     the dense walk then raises its flag and the general walk (`amt_item_count` / `amt_item_expand`) takes over, as on the GPU."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    build = os.path.join(ROOT, "tests", "host_fuzz", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "emu_events")
-    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20091", "-o", exe,
-                           os.path.join(ROOT, "tests", "host_fuzz", "emu_events.cu"), os.path.join(ROOT, "oracle", "oracle.cpp"),
-                           os.path.join(ROOT, "synth", "synth.cpp"), "-lpthread"], cwd=ROOT)
-    out = subprocess.run([exe, "24", "120", "5"], capture_output=True, text=True)
+    exe, env = _harness("emu_events", with_synth=True)
+    out = subprocess.run([exe, "24", "120", "5"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.startswith("ok: event path on the CPU == oracle for 24 tipsets"), out.stdout
     runs_ok, runs_err = int(out.stdout.split(":")[2].split()[0]), int(out.stdout.split("field,")[1].split()[0])
     general = int(out.stdout.split("identically,")[1].split()[0])
     assert runs_ok > 200 and runs_err > 1000 and general > 100, out.stdout
+
+
+def test_staged_pass1_lane_logic_emulated_on_cpu():
+    """tests/host_fuzz/emu_stage.cu: the per-lane logic of the (opt-in, IPCFP_PASS1_STAGE) shared-memory-staged pass-1 kernel —
+    `StageLane` / `StageWin` / `lean_stamped_event` of csrc/pass1_stage.cuh — under an adversarial model of the asynchronous fills:
+    staged decode == arena decode for every node, five ring geometries."""
+    exe, env = _harness("emu_stage", with_synth=False)
+    out = subprocess.run([exe, "300", "12"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert "ok: staged pass 1 == arena pass 1 for 5 geometries x 300 warps" in out.stdout, out.stdout
+
+
+def test_event_path_emulation_under_sanitizers():
+    """The emu_events harness once more, built with AddressSanitizer + UBSan (always, whatever IPCFP_HOST_FUZZ_SANITIZE says): hash
+    probes, BlockRec reads, window loads of the decoders, AMT walks and EventProof emission of the device code on intact AND mutated
+    tipsets (incl. the empty tipset) stay inside the buffers the engine gives them (arena pads of 16 / 32 bytes, `+ 64` on the CID
+    arrays). On the GPU such an access is silent or poisons the context; here it is a report with a stack."""
+    exe, env = _harness("emu_events", sanitize=True)
+    out = subprocess.run([exe, "10", "60", "31"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-4000:]
+    assert out.stdout.startswith("ok: event path on the CPU == oracle for 10 tipsets"), out.stdout
+    assert "runtime error" not in out.stderr and "AddressSanitizer" not in out.stderr, out.stderr[-4000:]

@@ -408,3 +408,39 @@ def test_public_filecoin_constants_pin_the_encodings(oracle_mod, synth_mod):
     r = oracle_mod.Store.from_tipset(ts).generate_event_proof(ts, spec)
     wit = {bytes(c) for c in r.witness.cids}
     assert J.cid_from_string(FILECOIN_EMPTY_TXMETA) in wit and cid_v0 in wit
+
+
+# Public Solidity storage-layout vectors (docs.soliditylang.org "Layout of State Variables in Storage": the value of mapping key k
+# at slot p lives at keccak256(h(k) . p); a dynamic array at slot p starts at keccak256(p)) — not from /root/reference, which holds no
+# vectors; any EVM toolchain prints them. They pin compute_mapping_slot (storage/utils.rs:5-12: keccak256(key32 ‖ u256_be(slot_index)))
+# and the Keccak-256 (not SHA3-256) padding against the real EVM rather than against ourselves.
+SOLIDITY_SLOT_VECTORS = [
+    # (key32, slot index, keccak256(key32 ‖ u256(slot)))
+    (bytes(32), 0, "ad3228b676f7d3cd4284a5443f17f1962b36e491b30a40b2405849e597ba5fb5"),
+    (bytes(32), 1, "a6eef7e35abe7026729641147f7915573c7e97b47efa546f5f6e3230263bcb49"),
+    (bytes(31) + b"\x01", 0, "ada5013122d395ba3c54772283fb069b10426056ef8ca54750cb9bb552a59e7d"),
+]
+SOLIDITY_ARRAY_VECTORS = [
+    (bytes(32), "290decd9548b62a8d60345a988386fc84ba6bc95484008f6362f93160ef3e563"),              # keccak256(uint256(0))
+    (bytes(31) + b"\x01", "b10e2d527612073b26eecdfd717e6a320cf44b4afac2b0732d9fcbe2b7fa0cf6"),    # keccak256(uint256(1))
+]
+
+
+def test_public_solidity_storage_layout_vectors(oracle_mod, synth_mod):
+    from oracle import pyoracle as P
+    for key, idx, want in SOLIDITY_SLOT_VECTORS:
+        assert oracle_mod.compute_mapping_slot(key, idx).hex() == want
+        assert P.keccak256(key + idx.to_bytes(32, "big")).hex() == want
+    for msg, want in SOLIDITY_ARRAY_VECTORS:
+        assert oracle_mod.keccak256(msg).hex() == P.keccak256(msg).hex() == synth_mod.keccak256(msg).hex() == want
+
+
+def test_public_filecoin_id_address_bytes():
+    """ID addresses (protocol 0) are `0x00 ‖ unsigned-LEB128(id)` — Filecoin spec, "Address" appendix; f01000 is 00 e8 07 on any node.
+    This is the state-tree HAMT key of get_actor_state (common/decode.rs:34, storage/generator.rs:116)."""
+    from oracle import pyoracle as P
+    assert P._id_address(0) == bytes.fromhex("0000")
+    assert P._id_address(127) == bytes.fromhex("007f")
+    assert P._id_address(128) == bytes.fromhex("008001")
+    assert P._id_address(1000) == bytes.fromhex("00e807")
+    assert P._id_address(2**64 - 1) == bytes.fromhex("00" + "ff" * 9 + "01")

@@ -66,6 +66,15 @@ def test_public_filecoin_constants_on_the_gpu(api):
     assert J.cid_to_string(pre + bytes(d[2])) == FILECOIN_EMPTY_HAMT
 
 
+def test_public_solidity_storage_layout_vectors_on_the_gpu(api):
+    """k_mapping_slots / k_hash_batch<keccak> against the public Solidity storage-layout vectors (tests/test_oracle_cpu.py)."""
+    from tests.test_oracle_cpu import SOLIDITY_ARRAY_VECTORS, SOLIDITY_SLOT_VECTORS
+    got = api.compute_mapping_slots([k for k, _, _ in SOLIDITY_SLOT_VECTORS], [i for _, i, _ in SOLIDITY_SLOT_VECTORS])
+    assert [bytes(g).hex() for g in got] == [w for _, _, w in SOLIDITY_SLOT_VECTORS]
+    got = api.keccak256_batch([m for m, _ in SOLIDITY_ARRAY_VECTORS])
+    assert [bytes(g).hex() for g in got] == [w for _, w in SOLIDITY_ARRAY_VECTORS]
+
+
 def test_json_bundle_verified_through_the_c_abi_alone(api, oracle_mod, synth_mod):
     """The flow a non-Rust host has: EventProofBundle as JSON text → ipcfp_bundle_from_json → witness store with every block
     Blake2b-checked → ipcfp_verify_event_proofs, with the tipset fields exactly as the parser recovered them from the proofs."""
