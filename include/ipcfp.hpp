@@ -21,6 +21,7 @@
 //   verify_event_proof(&bundle, &trusted_ts, &trusted_child, check_event)  same; check_event is an EventProofSpec (create_event_filter, events/verifier.rs:28-41)
 //   verify_storage_proof(&proof, &blocks, &trusted_child)          same                                           (storage/verifier.rs:24-63)
 //   compute_mapping_slot / calculate_storage_slot / ascii_to_bytes32 / left_pad_32   same                         (storage/utils.rs:5-19, common/evm.rs:72-100)
+//   serde_json::to_string(&bundle) / from_str                      to_json(bundle) / bundle_from_json(text)
 //   anyhow::Error                                                  ipcfp::host::Error (status, message, index)
 //
 // All compute happens behind the C ABI on the GPU. There is no CPU path here either: without a CUDA device every call that
@@ -643,6 +644,149 @@ inline UnifiedVerificationResult verify_proof_bundle(const UnifiedProofBundle& b
     eb.blocks = b.blocks;
     r.event_results = verify_event_proof(eb, is_trusted_parent_ts, is_trusted_child_header, check_event, device);
     return r;
+}
+
+// ------------------------------------------------------------------------------------------ wire format (serde_json of the bundle structs)
+// to_json: what `serde_json::to_string(&bundle)` gives in the reference (common/bundle.rs:10-45, events/bundle.rs:5-30,
+// storage/bundle.rs:5-14) — struct field order, compact, ProofBlock.cid as the byte array cid 0.11's Serialize emits, block data as
+// standard base64. Byte for byte what ipcfp_bundle_to_json / ipcfp_event_result_to_json render from the POD results.
+namespace detail {
+inline void json_string(std::string& o, const std::string& s) {   // serde_json's escaping
+    static const char* H = "0123456789abcdef";
+    o.push_back('"');
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\b': o += "\\b"; break;
+            case '\f': o += "\\f"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            default:
+                if (c < 0x20) { o += "\\u00"; o.push_back(H[c >> 4]); o.push_back(H[c & 15]); }
+                else o.push_back((char)c);
+        }
+    }
+    o.push_back('"');
+}
+inline void json_base64(std::string& o, const std::vector<uint8_t>& v) {   // base64::engine::general_purpose::STANDARD
+    static const char* T = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    o.push_back('"');
+    size_t i = 0;
+    const size_t n = v.size();
+    for (; i + 3 <= n; i += 3) {
+        const uint32_t x = (uint32_t)v[i] << 16 | (uint32_t)v[i + 1] << 8 | v[i + 2];
+        o.push_back(T[x >> 18]); o.push_back(T[(x >> 12) & 63]); o.push_back(T[(x >> 6) & 63]); o.push_back(T[x & 63]);
+    }
+    if (n - i == 1) { const uint32_t x = (uint32_t)v[i] << 16; o.push_back(T[x >> 18]); o.push_back(T[(x >> 12) & 63]); o += "=="; }
+    else if (n - i == 2) { const uint32_t x = (uint32_t)v[i] << 16 | (uint32_t)v[i + 1] << 8; o.push_back(T[x >> 18]); o.push_back(T[(x >> 12) & 63]); o.push_back(T[(x >> 6) & 63]); o.push_back('='); }
+    o.push_back('"');
+}
+inline void json_blocks(std::string& o, const std::vector<ProofBlock>& blocks) {
+    o.push_back('[');
+    for (size_t i = 0; i < blocks.size(); i++) {
+        if (i) o.push_back(',');
+        o += "{\"cid\":[";
+        for (int k = 0; k < IPCFP_CID_LEN; k++) { if (k) o.push_back(','); o += std::to_string((unsigned)blocks[i].cid.bytes[k]); }
+        o += "],\"data\":";
+        json_base64(o, blocks[i].data);
+        o.push_back('}');
+    }
+    o.push_back(']');
+}
+inline void json_event_proofs(std::string& o, const std::vector<EventProof>& proofs) {
+    o.push_back('[');
+    for (size_t i = 0; i < proofs.size(); i++) {
+        const EventProof& p = proofs[i];
+        if (i) o.push_back(',');
+        o += "{\"parent_epoch\":" + std::to_string(p.parent_epoch) + ",\"child_epoch\":" + std::to_string(p.child_epoch) + ",\"parent_tipset_cids\":[";
+        for (size_t q = 0; q < p.parent_tipset_cids.size(); q++) { if (q) o.push_back(','); json_string(o, p.parent_tipset_cids[q]); }
+        o += "],\"child_block_cid\":"; json_string(o, p.child_block_cid);
+        o += ",\"message_cid\":"; json_string(o, p.message_cid);
+        o += ",\"exec_index\":" + std::to_string(p.exec_index) + ",\"event_index\":" + std::to_string(p.event_index);
+        o += ",\"event_data\":{\"emitter\":" + std::to_string(p.event_data.emitter) + ",\"topics\":[";
+        for (size_t q = 0; q < p.event_data.topics.size(); q++) { if (q) o.push_back(','); json_string(o, p.event_data.topics[q]); }
+        o += "],\"data\":"; json_string(o, p.event_data.data);
+        o += "}}";
+    }
+    o.push_back(']');
+}
+}  // namespace detail
+inline std::string to_json(const EventProofBundle& b) {
+    std::string o = "{\"proofs\":";
+    detail::json_event_proofs(o, b.proofs);
+    o += ",\"blocks\":";
+    detail::json_blocks(o, b.blocks);
+    o.push_back('}');
+    return o;
+}
+inline std::string to_json(const UnifiedProofBundle& b) {
+    std::string o = "{\"storage_proofs\":[";
+    for (size_t i = 0; i < b.storage_proofs.size(); i++) {
+        const StorageProof& p = b.storage_proofs[i];
+        if (i) o.push_back(',');
+        o += "{\"child_epoch\":" + std::to_string(p.child_epoch) + ",\"child_block_cid\":"; detail::json_string(o, p.child_block_cid);
+        o += ",\"parent_state_root\":"; detail::json_string(o, p.parent_state_root);
+        o += ",\"actor_id\":" + std::to_string(p.actor_id) + ",\"actor_state_cid\":"; detail::json_string(o, p.actor_state_cid);
+        o += ",\"storage_root\":"; detail::json_string(o, p.storage_root);
+        o += ",\"slot\":"; detail::json_string(o, p.slot);
+        o += ",\"value\":"; detail::json_string(o, p.value);
+        o.push_back('}');
+    }
+    o += "],\"event_proofs\":";
+    detail::json_event_proofs(o, b.event_proofs);
+    o += ",\"blocks\":";
+    detail::json_blocks(o, b.blocks);
+    o.push_back('}');
+    return o;
+}
+// serde_json::from_str::<UnifiedProofBundle> / ::<EventProofBundle> through the C ABI's parser (ipcfp_bundle_from_json,
+// csrc/bundle_parse.cpp: unknown fields ignored, trailing characters refused, canonical base64, the three spellings of ProofBlock.cid).
+// An EventProofBundle ({"proofs": …, "blocks": …}) comes back with storage_proofs empty. The C ABI's verifiers take one tipset pair
+// per call, so a bundle whose proofs disagree on the shared fields is refused (IPCFP_ERR_UNSUPPORTED), as by the C parser.
+inline UnifiedProofBundle bundle_from_json(const std::string& text) {
+    ipcfp_parsed_bundle* pb = nullptr;
+    check(ipcfp_bundle_from_json(text.data(), text.size(), &pb), "bundle_from_json");
+    UnifiedProofBundle u;
+    try {
+        const ipcfp_tipset_desc& t = pb->tipset;
+        std::vector<std::string> parents;
+        for (uint32_t i = 0; i < t.n_parents; i++) parents.push_back(Cid::from_bytes(t.parent_cids + IPCFP_CID_LEN * i).to_string());
+        const std::string child = t.child_cid ? Cid::from_bytes(t.child_cid).to_string() : std::string();
+        const std::string psr = t.child_parent_state_root ? Cid::from_bytes(t.child_parent_state_root).to_string() : std::string();
+        for (uint64_t i = 0; i < pb->n_storage_proofs; i++) {
+            const ipcfp_storage_proof& p = pb->storage_proofs[i];
+            StorageProof s;
+            s.child_epoch = t.child_epoch;
+            s.child_block_cid = child;
+            s.parent_state_root = psr;
+            s.actor_id = p.actor_id;
+            s.actor_state_cid = Cid::from_bytes(p.actor_state_cid).to_string();
+            s.storage_root = Cid::from_bytes(p.storage_root).to_string();
+            s.slot = to_hex0x(p.slot, 32);
+            s.value = to_hex0x(p.value, 32);
+            u.storage_proofs.push_back(std::move(s));
+        }
+        for (uint64_t i = 0; i < pb->n_event_proofs; i++) {
+            const ipcfp_event_proof& p = pb->event_proofs[i];
+            EventProof e;
+            e.parent_epoch = t.parent_epoch;
+            e.child_epoch = t.child_epoch;
+            e.parent_tipset_cids = parents;
+            e.child_block_cid = child;
+            e.message_cid = Cid::from_bytes(p.message_cid).to_string();
+            e.exec_index = p.exec_index;
+            e.event_index = p.event_index;
+            e.event_data.emitter = p.emitter;
+            for (uint32_t k = 0; k < p.n_topics; k++) e.event_data.topics.push_back(to_hex0x(pb->data_blob + p.topics_off + 32ull * k, 32));
+            e.event_data.data = to_hex0x(pb->data_blob + p.data_off, p.data_len);
+            u.event_proofs.push_back(std::move(e));
+        }
+        u.blocks = proof_blocks(pb->witness);
+    } catch (...) { ipcfp_parsed_bundle_free(pb); throw; }
+    ipcfp_parsed_bundle_free(pb);
+    return u;
 }
 
 }  // namespace host

@@ -209,6 +209,69 @@ static int run_cpu() {
         }
     }
 
+    // wire format: to_json == the C ABI's rendering of the same (oracle) result byte for byte; bundle_from_json brings every field back
+    {
+        TipsetDesc t(f.parent, f.child, f.receipts);
+        ipcfp_event_spec spec = spec_c(synth_event_signature(f.ts), synth_topic1(f.ts), f.actor_filter(p1));
+        ipcfp_event_result* r = nullptr;
+        REQUIRE(oracle_generate_event_proof(f.os, t.c(), &spec, 0, 1, &r) == IPCFP_OK);
+        EventProofBundle b;
+        b.proofs = event_proofs(*r, t);
+        b.blocks = proof_blocks(r->witness);
+        char* text = nullptr;
+        uint64_t len = 0;
+        REQUIRE(ipcfp_event_result_to_json(r, t.c(), &text, &len) == IPCFP_OK);
+        oracle_event_result_free(r);
+        const std::string mine = to_json(b);
+        REQUIRE(mine.size() == len && mine == std::string(text, len));
+        ipcfp_json_free(text);
+        UnifiedProofBundle back = bundle_from_json(mine);
+        REQUIRE(back.storage_proofs.empty() && back.event_proofs.size() == b.proofs.size() && back.blocks.size() == b.blocks.size());
+        for (size_t i = 0; i < b.proofs.size(); i++) REQUIRE(back.event_proofs[i] == b.proofs[i]);
+        for (size_t i = 0; i < b.blocks.size(); i++) REQUIRE(back.blocks[i] == b.blocks[i]);
+        EventProofBundle again;
+        again.proofs = back.event_proofs;
+        again.blocks = back.blocks;
+        REQUIRE(to_json(again) == mine);
+        REQUIRE(status_of([&] { bundle_from_json(mine.substr(0, mine.size() - 1)); }) == IPCFP_ERR_INVALID_ARG);
+        REQUIRE(status_of([&] { bundle_from_json(mine + "x"); }) == IPCFP_ERR_INVALID_ARG);   // trailing characters
+        std::string esc;
+        detail::json_string(esc, std::string("a\"b\\c\n\x01", 7));
+        REQUIRE(esc == "\"a\\\"b\\\\c\\n\\u0001\"");
+    }
+    {
+        synth_params p3 = config(3);
+        Fixture g(p3);
+        TipsetDesc t(g.parent, g.child, g.receipts);
+        H256 k = ascii_to_bytes32("calib-subnet-1"), special;
+        oracle_compute_mapping_slot(k.data(), 0, special.data());
+        ipcfp_storage_spec cs[2];
+        memset(cs, 0, sizeof cs);
+        cs[0].actor_id = 1001; cs[1].actor_id = 1003;
+        memcpy(cs[0].slot, special.data(), 32); memcpy(cs[1].slot, special.data(), 32);
+        const std::string sig = synth_event_signature(g.ts), t1 = synth_topic1(g.ts);
+        ipcfp_event_spec ce[2] = {spec_c(sig, t1, g.actor_filter(p3)), spec_c(sig, "calib-subnet-2", std::nullopt)};
+        ipcfp_bundle* ob = nullptr;
+        REQUIRE(oracle_generate_proof_bundle(g.os, t.c(), cs, 2, ce, 2, &ob) == IPCFP_OK);
+        UnifiedProofBundle u;
+        for (uint64_t i = 0; i < ob->storage->n_proofs; i++) u.storage_proofs.push_back(storage_proof(ob->storage->proofs[i], t));
+        for (uint64_t q = 0; q < ob->n_event_results; q++) { auto e = event_proofs(*ob->events[q], t); u.event_proofs.insert(u.event_proofs.end(), e.begin(), e.end()); }
+        u.blocks = proof_blocks(ob->witness);
+        char* text = nullptr;
+        uint64_t len = 0;
+        REQUIRE(ipcfp_bundle_to_json(ob, t.c(), &text, &len) == IPCFP_OK);
+        oracle_bundle_free(ob);
+        const std::string mine = to_json(u);
+        REQUIRE(mine == std::string(text, len) && u.storage_proofs.size() == 2 && !u.event_proofs.empty());
+        ipcfp_json_free(text);
+        UnifiedProofBundle back = bundle_from_json(mine);
+        REQUIRE(back.storage_proofs.size() == 2 && back.storage_proofs[0] == u.storage_proofs[0] && back.storage_proofs[1] == u.storage_proofs[1]);
+        REQUIRE(back.event_proofs.size() == u.event_proofs.size() && back.blocks.size() == u.blocks.size());
+        for (size_t i = 0; i < u.event_proofs.size(); i++) REQUIRE(back.event_proofs[i] == u.event_proofs[i]);
+        for (size_t i = 0; i < u.blocks.size(); i++) REQUIRE(back.blocks[i] == u.blocks[i]);
+        REQUIRE(to_json(back) == mine);
+    }
+
     // no CPU path: without a device the store cannot be created (with one, it can — then this is simply a second smoke test)
     ipcfp_status st = status_of([&] { GpuBlockstore s = f.store(); REQUIRE(s.n_blocks() == synth_n_blocks(f.ts)); });
     REQUIRE(st == IPCFP_ERR_NO_DEVICE || st == IPCFP_OK);
@@ -416,6 +479,8 @@ static int run_gpu() {
         UnifiedVerificationResult vr = verify_proof_bundle(got, yes_ts, yes_h);
         REQUIRE(vr.storage_results.size() == 2 && vr.event_results.size() == got.event_proofs.size() && vr.all_valid());
         REQUIRE(!verify_proof_bundle(got, yes_ts, no_h).all_valid());
+        // over the wire and back: serde_json text → bundle → verification
+        REQUIRE(verify_proof_bundle(bundle_from_json(to_json(got)), yes_ts, yes_h).all_valid());
     }
     printf("ok: include/ipcfp.hpp on cuda:0 == the oracle (%d assertions, %llu kernel launches)\n", g_checks, (unsigned long long)ipcfp_kernel_launch_count());
     return 0;
