@@ -32,4 +32,8 @@ oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h synth/cpu_crypto.h includ
 clean:
 	rm -f $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o $(LIB) synth/libipcfp_synth.so oracle/liboracle.so
 
-.PHONY: all clean
+# The host-compiled device headers (tests/host_fuzz) and the JSON parser under AddressSanitizer + UBSan
+sanitize:
+	IPCFP_HOST_FUZZ_SANITIZE=1 python -m pytest tests/test_host_fuzz.py tests/test_bundle_json.py -q
+
+.PHONY: all clean sanitize
