@@ -20,8 +20,16 @@ $(CSRC)/bundle_json.o: $(CSRC)/bundle_json.cpp include/ipcfp.h
 $(CSRC)/bundle_parse.o: $(CSRC)/bundle_parse.cpp include/ipcfp.h
 	$(CXX) -O2 -std=c++17 -fPIC -c $< -o $@
 
-$(LIB): $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o -lcudart -ldl
+# HIDE_INTERNALS=1 links with csrc/exports.map: only ipcfp_* stay in the dynamic symbol table (what a C-ABI library should export).
+# Not the default yet: the default build is the one every GPU measurement and GPU test of round 2 ran on, and the change arrived after
+# the round's GPU minutes were spent (tests/test_abi_layout.py checks the hidden build's export list and its C++-host behaviour on the CPU).
+ifeq ($(HIDE_INTERNALS),1)
+LIB_LDFLAGS := -Xlinker --version-script=$(CSRC)/exports.map
+endif
+LIB_OUT ?= $(LIB)
+
+$(LIB_OUT): $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o $(CSRC)/exports.map
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a $(LIB_LDFLAGS) -o $@ $(CU_OBJS) $(CSRC)/bundle_json.o $(CSRC)/bundle_parse.o -lcudart -ldl
 
 synth/libipcfp_synth.so: synth/synth.cpp synth/synth.h synth/cpu_crypto.h
 	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -o $@ synth/synth.cpp
