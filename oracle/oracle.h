@@ -13,6 +13,9 @@
  *       node): tests/test_oracle_cpu.py::test_public_filecoin_constants_pin_the_encodings — the basic encodings (DAG-CBOR tuples
  *       and links, AMT v0/v3 and HAMT node layouts, Blake2b-256 CIDs) are checked against the real network, not only against
  *       ourselves.
+ *   (5) the only known answers the reference TREE holds for anything on the path: Keccak-256 constants of its vendored forge-std
+ *       (tests/golden/reference_keccak_vectors.json, extracted by tests/golden/make_reference_keccak_vectors.py) — they pin
+ *       oracle_keccak256 / oracle_compute_mapping_slot's hash, nothing else.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library. The product library never links or calls it.

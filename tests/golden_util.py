@@ -58,3 +58,53 @@ def check_storage_result(z, res):
         wo += wl
         got_w = res.witness.cids[res.spec_witness[k]]
         assert np.array_equal(got_w, exp_w)
+
+
+# ------------------------------------------------------------------ Keccak-256 known answers held by the reference tree itself
+REF_KECCAK_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_keccak_vectors.json")
+
+
+def check_reference_keccak_vectors(keccak256):
+    """Evaluates every vector of tests/golden/reference_keccak_vectors.json (extracted from the reference's vendored forge-std by
+    tests/golden/make_reference_keccak_vectors.py) with the given `keccak256(bytes) -> 32 bytes`. Returns the number of hash calls."""
+    import json
+    doc = json.load(open(REF_KECCAK_PATH))
+    calls = [0]
+
+    def k(m):
+        calls[0] += 1
+        d = bytes(keccak256(bytes(m)))
+        assert len(d) == 32
+        return d
+
+    def addr(s):
+        return bytes.fromhex(s[2:])
+
+    def create(deployer20, nonce):   # keccak256(rlp([deployer, nonce]))[12:], nonce < 0x80 (single RLP byte, 0 → 0x80)
+        assert 0 <= nonce < 0x80
+        return k(bytes([0xc0 + 22, 0x80 + 20]) + deployer20 + (bytes([nonce]) if nonce else b"\x80"))[12:]
+
+    for v in doc["vectors"]:
+        kind, src = v["kind"], v["source"]
+        if kind == "digest":
+            assert k(bytes.fromhex(v["message_hex"])).hex() == v["expect"][2:], src
+        elif kind == "low20":
+            assert k(v["message_ascii"].encode())[12:] == addr(v["expect"]), src
+        elif kind == "prefix4":
+            assert k(v["message_ascii"].encode())[:4].hex() == v["expect"][2:], src
+        elif kind == "create2":   # keccak256(0xff ‖ deployer ‖ salt ‖ keccak256(initcode))[12:]
+            init_hash = k(bytes.fromhex(v["initcode_preimage_hex"]))
+            assert k(b"\xff" + addr(v["deployer"]) + bytes.fromhex(v["salt_hex"]) + init_hash)[12:] == addr(v["expect"]), src
+        elif kind == "create_chain":
+            a = addr(v["deployer"])
+            for n in v["nonces"]:
+                a = create(a, n)
+            assert a == addr(v["expect"]), src
+        elif kind == "eip55":   # EIP-55: hex digit i is upper case iff nibble i of keccak256(lower-case hex ascii) >= 8
+            lower = v["address"][2:].lower()
+            d = k(lower.encode()).hex()
+            assert "".join(c.upper() if c in "abcdef" and int(d[i], 16) >= 8 else c for i, c in enumerate(lower)) == v["address"][2:], src
+        else:
+            raise AssertionError(kind)
+    assert len(doc["vectors"]) >= 17
+    return calls[0]

@@ -363,6 +363,17 @@ int main(int argc, char** argv) {
         Digest d; keccak256(abc, 3, d);
         uint8_t ref[32]; oracle_keccak256((const uint8_t*)"abc", 3, ref);
         if (memcmp(d.w, ref, 32)) { fprintf(stderr, "host build of keccak256 is broken\n"); return 2; }
+        // the DEVICE keccak256 (csrc/hashes.cuh, this very code runs in k_setup / k_hash_batch) on two known answers the reference tree
+        // itself holds (vendored forge-std: StdConstants.sol:10 and test/StdUtils.t.sol:267; tests/golden/reference_keccak_vectors.json)
+        alignas(8) static const uint8_t m1[16] = {'h', 'e', 'v', 'm', ' ', 'c', 'h', 'e', 'a', 't', ' ', 'c', 'o', 'd', 'e'};
+        static const uint8_t vm_addr[20] = {0x71, 0x09, 0x70, 0x9E, 0xCf, 0xa9, 0x1a, 0x80, 0x62, 0x6f, 0xF3, 0x98, 0x9D, 0x68, 0xf6, 0x7F, 0x5b, 0x1D, 0xD1, 0x2D};
+        keccak256(m1, 15, d);
+        if (memcmp((const uint8_t*)d.w + 12, vm_addr, 20)) { fprintf(stderr, "device keccak256 != forge-std VM address constant\n"); return 2; }
+        alignas(8) static const uint8_t m2[8] = {0x60, 0x80};
+        static const uint8_t h6080[32] = {0x1a, 0x57, 0x8b, 0x7a, 0x4b, 0x0b, 0x57, 0x55, 0xdb, 0x6d, 0x12, 0x1b, 0x41, 0x18, 0xd4, 0xbc,
+                                          0x68, 0xfe, 0x17, 0x0d, 0xca, 0x84, 0x0c, 0x59, 0xbc, 0x92, 0x2f, 0x14, 0x17, 0x5a, 0x76, 0xb0};
+        keccak256(m2, 2, d);
+        if (memcmp(d.w, h6080, 32)) { fprintf(stderr, "device keccak256 != hashInitCode(hex\"6080\") of forge-std's tests\n"); return 2; }
     }
     uint64_t n_ok = 0, n_err = 0, n_skip = 0;
     for (uint64_t c = 0; c < cases; c++) {

@@ -444,3 +444,33 @@ def test_public_filecoin_id_address_bytes():
     assert P._id_address(128) == bytes.fromhex("008001")
     assert P._id_address(1000) == bytes.fromhex("00e807")
     assert P._id_address(2**64 - 1) == bytes.fromhex("00" + "ff" * 9 + "01")
+
+
+def test_keccak_vectors_held_by_the_reference_tree(oracle_mod, synth_mod):
+    """The only known answers under /root/reference that pin something the hot path computes: Keccak-256 constants of the vendored
+    forge-std (cheat-code / default-sender addresses, hashInitCode(hex"6080"), CREATE / CREATE2 addresses, a function selector, the
+    EIP-55 checksums of its address literals) — tests/golden/reference_keccak_vectors.json, extracted by
+    tests/golden/make_reference_keccak_vectors.py. Checked here with the three CPU implementations; the GPU kernel has its own test."""
+    from oracle import pyoracle as P
+    from tests.golden_util import check_reference_keccak_vectors
+    for impl in (oracle_mod.keccak256, P.keccak256, synth_mod.keccak256):
+        assert check_reference_keccak_vectors(impl) >= 20
+
+
+def test_reference_keccak_fixture_is_what_the_script_extracts(tmp_path):
+    """When the reference tree is present (this container, not the GPU box) the committed fixture must be exactly what the committed
+    script extracts from it."""
+    import json
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "topdown-messenger", "lib", "forge-std")):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "golden", "make_reference_keccak_vectors.py")
+    committed = open(os.path.join(root, "tests", "golden", "reference_keccak_vectors.json")).read()
+    # the script writes next to itself: run a copy from a scratch directory
+    work = tmp_path / "make_reference_keccak_vectors.py"
+    work.write_text(open(script).read())
+    subprocess.check_call([sys.executable, str(work), ref], stdout=subprocess.DEVNULL)
+    assert json.loads((tmp_path / "reference_keccak_vectors.json").read_text()) == json.loads(committed)

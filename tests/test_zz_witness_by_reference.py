@@ -75,6 +75,13 @@ def test_public_solidity_storage_layout_vectors_on_the_gpu(api):
     assert [bytes(g).hex() for g in got] == [w for _, w in SOLIDITY_ARRAY_VECTORS]
 
 
+def test_keccak_vectors_held_by_the_reference_tree_on_the_gpu(api):
+    """k_hash_batch<keccak> against the Keccak-256 constants the reference's own tree holds (vendored forge-std; fixture
+    tests/golden/reference_keccak_vectors.json, see tests/test_oracle_cpu.py::test_keccak_vectors_held_by_the_reference_tree)."""
+    from tests.golden_util import check_reference_keccak_vectors
+    assert check_reference_keccak_vectors(lambda m: api.keccak256_batch([m])[0]) >= 20
+
+
 def test_json_bundle_verified_through_the_c_abi_alone(api, oracle_mod, synth_mod):
     """The flow a non-Rust host has: EventProofBundle as JSON text → ipcfp_bundle_from_json → witness store with every block
     Blake2b-checked → ipcfp_verify_event_proofs, with the tipset fields exactly as the parser recovered them from the proofs."""
