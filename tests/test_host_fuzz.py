@@ -120,3 +120,19 @@ def test_event_path_emulation_under_sanitizers():
     assert out.returncode == 0, (out.stdout + out.stderr)[-4000:]
     assert out.stdout.startswith("ok: event path on the CPU == oracle for 10 tipsets"), out.stdout
     assert "runtime error" not in out.stderr and "AddressSanitizer" not in out.stderr, out.stderr[-4000:]
+
+
+def test_verifiers_emulated_on_cpu_match_oracle():
+    """tests/host_fuzz/emu_verify.cu: the per-item device code of the GPU-batched verifiers (csrc/verify_items.cuh — verify_tipset_item,
+    verify_txmeta_item, verify_event_item, verify_storage_item, the very functions the kernels of verify.cu call) compiled for the host
+    and driven as verify.cu drives the kernels, against the restated verifiers of the oracle on bundles the oracle generated: intact
+    (every proof accepted), with forged claims in every proof field, foreign / matching check_event, changed tipset fields, a witness
+    block mutated under its CID, a witness block missing — the same Vec<bool>, or the same status at the same proof index."""
+    exe, env = _harness("emu_verify")
+    out = subprocess.run([exe, "10", "60", "19"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert out.stdout.startswith("ok: verifiers on the CPU == oracle for 10 bundles"), out.stdout
+    ev_ok, ev_err = int(out.stdout.split("events")[1].split()[0]), int(out.stdout.split("verdicts,")[1].split()[0])
+    st_ok, st_err = int(out.stdout.split("storage")[1].split()[0]), int(out.stdout.split("equal,")[1].split()[0])
+    accepted, rejected = int(out.stdout.split("identically;")[2].split()[0]), int(out.stdout.split("accepted,")[1].split()[0])
+    assert ev_ok > 200 and ev_err > 50 and st_ok > 80 and st_err > 50 and accepted > 1000 and rejected > 1000, out.stdout
