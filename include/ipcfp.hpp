@@ -21,6 +21,7 @@
 //   verify_event_proof(&bundle, &trusted_ts, &trusted_child, check_event)  same; check_event is an EventProofSpec (create_event_filter, events/verifier.rs:28-41)
 //   verify_storage_proof(&proof, &blocks, &trusted_child)          same                                           (storage/verifier.rs:24-63)
 //   compute_mapping_slot / calculate_storage_slot / ascii_to_bytes32 / left_pad_32   same                         (storage/utils.rs:5-19, common/evm.rs:72-100)
+//   keccak256 / hash_event_signature / create_event_filter / parse_cid / parse_cids  same                         (common/evm.rs:62-88, events/verifier.rs:28-41, common/witness.rs:60-72)
 //   serde_json::to_string(&bundle) / from_str                      to_json(bundle) / bundle_from_json(text)
 //   anyhow::Error                                                  ipcfp::host::Error (status, message, index)
 //
@@ -535,6 +536,31 @@ inline UnifiedProofBundle generate_proof_bundle(GpuBlockstore& store, const ApiT
     ipcfp_bundle_free(b);
     return u;
 }
+
+// keccak256 / hash_event_signature (common/evm.rs:62-69, :81-88), on the GPU
+inline H256 keccak256(const std::vector<uint8_t>& bytes, int device = 0) {
+    H256 out{};
+    const uint64_t off = 0;
+    const uint32_t len = (uint32_t)bytes.size();
+    const uint8_t none = 0;
+    check(ipcfp_keccak256_batch(bytes.empty() ? &none : bytes.data(), bytes.size(), &off, &len, 1, device, out.data()), "keccak256");
+    return out;
+}
+inline H256 hash_event_signature(const std::string& s, int device = 0) { return keccak256(std::vector<uint8_t>(s.begin(), s.end()), device); }
+// create_event_filter(event_sig, subnet_id) (events/verifier.rs:28-41): the predicate verify_event_proof takes as check_event
+inline EventProofSpec create_event_filter(const std::string& event_sig, const std::string& subnet_id) { return EventProofSpec{event_sig, subnet_id, std::nullopt}; }
+// parse_cid / parse_cids (common/witness.rs:60-72): the error names what was being parsed
+inline Cid parse_cid(const std::string& cid_str, const std::string& context) {
+    try { return Cid::try_from(cid_str); } catch (const Error& e) { throw Error(e.status, "invalid " + context + " CID: " + e.what()); }
+}
+inline std::vector<Cid> parse_cids(const std::vector<std::string>& cid_strs, const std::string& context) {
+    std::vector<Cid> out;
+    out.reserve(cid_strs.size());
+    for (const auto& s : cid_strs) out.push_back(parse_cid(s, context));
+    return out;
+}
+// (RecordingBlockStore and WitnessCollector — common/blockstore.rs:8-39, common/witness.rs:9-57 — have no host-side counterpart:
+// recording and materialisation happen inside the GPU call; what they produce is the `blocks` of the returned bundle, in `Cid` order.)
 
 // compute_mapping_slot / calculate_storage_slot (storage/utils.rs:5-19): keccak256(key32 ‖ u256_be(slot_index)), on the GPU
 inline H256 compute_mapping_slot(const H256& key, uint64_t slot_index, int device = 0) {

@@ -146,6 +146,18 @@ static int run_cpu() {
         for (uint64_t i = 0; i < n; i++) REQUIRE(memcmp(v[i].bytes.data(), flat.data() + 38 * i, 38) == 0);
     }
 
+    // parse_cid / parse_cids / create_event_filter (common/witness.rs:60-72, events/verifier.rs:28-41)
+    {
+        const std::string good = "bafy2bzaceamp42wmmgr2g2ymg46euououzfyck7szknvfacqscohrvaikwfay";
+        REQUIRE(parse_cid(good, "child block").to_string() == good);
+        REQUIRE(parse_cids({good, good}, "parent tipset").size() == 2);
+        bool named = false;
+        try { parse_cid("nonsense", "child block"); } catch (const Error& e) { named = e.status == IPCFP_ERR_INVALID_ARG && std::string(e.what()).find("child block") != std::string::npos; }
+        REQUIRE(named);
+        EventProofSpec f = create_event_filter("NewTopDownMessage(bytes32,uint256)", "calib-subnet-1");
+        REQUIRE(f.event_signature == "NewTopDownMessage(bytes32,uint256)" && f.topic_1 == "calib-subnet-1" && !f.actor_id_filter);
+    }
+
     // hex / padding helpers (common/evm.rs:72-100)
     {
         const uint8_t b[3] = {0x00, 0xab, 0xff};
@@ -405,6 +417,9 @@ static int run_gpu() {
         oracle_compute_mapping_slot(key, 0, want);
         REQUIRE(memcmp(slot77.data(), want, 32) == 0);
         REQUIRE(to_hex0x(compute_mapping_slot(H256{}, 1).data(), 32) == "0xa6eef7e35abe7026729641147f7915573c7e97b47efa546f5f6e3230263bcb49");   // public Solidity vector
+        REQUIRE(to_hex0x(hash_event_signature("Transfer(address,address,uint256)").data(), 32) == "0xddf252ad1be2c89b69c2b068fc378daa952ba7f163c4a11628f55a4df523b3ef");
+        REQUIRE(to_hex0x(keccak256({}).data(), 32) == "0xc5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470");
+        REQUIRE(to_hex0x(keccak256({0x60, 0x80}).data(), 32) == "0x1a578b7a4b0b5755db6d121b4118d4bc68fe170dca840c59bc922f14175a76b0");   // held by the reference tree (forge-std)
 
         // read_storage_slot: Some(bytes) / None
         const Cid root = Cid::from_bytes(synth_storage_root(f.ts));
