@@ -22,6 +22,7 @@
 //   verify_storage_proof(&proof, &blocks, &trusted_child)          same                                           (storage/verifier.rs:24-63)
 //   compute_mapping_slot / calculate_storage_slot / ascii_to_bytes32 / left_pad_32   same                         (storage/utils.rs:5-19, common/evm.rs:72-100)
 //   keccak256 / hash_event_signature / create_event_filter / parse_cid / parse_cids  same                         (common/evm.rs:62-88, events/verifier.rs:28-41, common/witness.rs:60-72)
+//   (future work "Parallel Generation", README.md:384)             ShardedComm, generate_event_proof_sharded → ShardedEventProof
 //   serde_json::to_string(&bundle) / from_str                      to_json(bundle) / bundle_from_json(text)
 //   anyhow::Error                                                  ipcfp::host::Error (status, message, index)
 //
@@ -570,6 +571,68 @@ inline H256 compute_mapping_slot(const H256& key, uint64_t slot_index, int devic
 }
 inline H256 calculate_storage_slot(const std::string& subnet_ascii, uint64_t subnets_slot_index, int device = 0) {
     return compute_mapping_slot(ascii_to_bytes32(subnet_ascii), subnets_slot_index, device);
+}
+
+// ------------------------------------------------------------------------------------------ one tipset over several GPUs
+// The reference's future-work "Parallel Generation" (README.md:384): one process per GPU, one communicator per process. Rank 0 makes
+// the id (ShardedComm::unique_id) and hands the 128 bytes to the other ranks by any means. The cross-shard protocol (first-seen dedup of
+// the execution order, message-CID fetch, union of the witness CID sets) runs inside the library over NCCL. Compiled
+// here, not run by tests/cpp/host_mirror_test.cpp (it needs NCCL and one GPU per rank): the same C calls are exercised through ctypes by
+// tests/test_parallel.py::test_sharded_call_over_nccl at world sizes 1, 2, 4, 8.
+class ShardedComm {
+  public:
+    static std::array<uint8_t, IPCFP_COMM_ID_BYTES> unique_id() {
+        std::array<uint8_t, IPCFP_COMM_ID_BYTES> id{};
+        check(ipcfp_comm_unique_id(id.data()), "ipcfp_comm_unique_id");
+        return id;
+    }
+    ShardedComm(const std::array<uint8_t, IPCFP_COMM_ID_BYTES>& id, uint32_t world, uint32_t rank, int device) : world_(world), rank_(rank) {
+        check(ipcfp_comm_init(id.data(), world, rank, device, &h_), "ipcfp_comm_init");
+    }
+    ShardedComm(const ShardedComm&) = delete;
+    ShardedComm& operator=(const ShardedComm&) = delete;
+    ~ShardedComm() { if (h_) ipcfp_comm_destroy(h_); }
+    ipcfp_comm* raw() const { return h_; }
+    uint32_t world() const { return world_; }
+    uint32_t rank() const { return rank_; }
+
+  private:
+    ipcfp_comm* h_ = nullptr;
+    uint32_t world_, rank_;
+};
+struct ShardedEventProof {
+    std::vector<EventProof> proofs;   // proofs of the receipts this rank owns; message_cid / exec_index final (execution order resolved across shards)
+    std::vector<ProofBlock> blocks;   // this shard's witness blocks in `Cid` order
+    std::vector<Cid> union_part;      // entries [union_first, union_first + union_part.size()) of the BTreeSet<Cid> union over ALL shards
+    uint64_t union_first = 0, union_total = 0, total_matching = 0, total_proofs = 0;
+};
+// generate_event_proof for ONE tipset split by receipt index: rank r scans receipts bounds[r] .. bounds[r+1] out of a store that holds
+// the blocks that range needs. Every rank must make the call; they succeed or fail together, naming the error the single-store call
+// on the whole tipset would have named.
+inline ShardedEventProof generate_event_proof_sharded(ShardedComm& comm, GpuBlockstore& store, const ApiTipset& parent, const ApiTipset& child,
+                                                      const std::vector<ApiReceipt>& receipts, const std::vector<uint64_t>& bounds,
+                                                      const std::string& event_signature, const std::string& topic_1, std::optional<uint64_t> actor_id_filter) {
+    if (bounds.size() != (size_t)comm.world() + 1) throw Error(IPCFP_ERR_INVALID_ARG, "bounds must hold world + 1 receipt indices");
+    TipsetDesc t(parent, child, receipts);
+    ipcfp_event_spec spec = spec_c(event_signature, topic_1, actor_id_filter);
+    ipcfp_tipset* tip = nullptr;
+    check(ipcfp_tipset_upload(store.raw(), t.c(), &tip), "ipcfp_tipset_upload");
+    ipcfp_event_result* r = nullptr;
+    const ipcfp_status st = ipcfp_generate_event_proof_sharded(comm.raw(), store.raw(), tip, &spec, bounds.data(), IPCFP_SHARDED_UNION_TO_HOST, &r);
+    ipcfp_tipset_free(tip);
+    check(st, "generate_event_proof_sharded");
+    ShardedEventProof out;
+    try {
+        out.proofs = event_proofs(*r, t);
+        out.blocks = proof_blocks(r->witness);
+        for (uint64_t i = 0; i < r->n_union_part; i++) out.union_part.push_back(Cid::from_bytes(r->union_cids + IPCFP_CID_LEN * i));
+        out.union_first = r->union_part_first;
+        out.union_total = r->n_union_cids;
+        out.total_matching = r->total_matching;
+        out.total_proofs = r->total_proofs;
+    } catch (...) { ipcfp_event_result_free(r); throw; }
+    ipcfp_event_result_free(r);
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------ verifiers

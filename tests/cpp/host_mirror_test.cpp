@@ -299,6 +299,12 @@ static int run_cpu() {
         sp.child_block_cid = f.child.cids[0].cid;
         REQUIRE(verify_storage_proof(sp, {}, no_h) == false);
     }
+    {   // the multi-GPU surface compiles, links and fails cleanly where NCCL / a device is missing (run for real by tests/test_parallel.py)
+        auto fp = &generate_event_proof_sharded;
+        REQUIRE(fp != nullptr);
+        const ipcfp_status ids = status_of([] { (void)ShardedComm::unique_id(); });
+        REQUIRE(ids == IPCFP_OK || ids == IPCFP_ERR_NCCL || ids == IPCFP_ERR_NO_DEVICE);
+    }
     printf("ok: cpu checks of include/ipcfp.hpp (%d assertions)%s\n", g_checks, st == IPCFP_OK ? " [a CUDA device was present]" : "");
     return 0;
 }
