@@ -1,6 +1,6 @@
 // verify_items.cuh — the per-item device code of the GPU-batched verifiers (verify.cu): what ONE thread does for the tipset, for one
 // TxMeta block, for one event proof, for one storage proof. Kept apart from the kernels so that tests/host_fuzz/emu_verify.cu can
-// compile the very same code for the host and run it, item by item, against the restated verifiers of oracle/ — on intact and on
+// compile the very same code for the host and run it, item by item, against the restated CPU verifiers of the test tree — on intact and on
 // adversarial bundles, under AddressSanitizer. The kernels in verify.cu only compute the item index and call these.
 #pragma once
 #include "engine.cuh"
