@@ -380,7 +380,8 @@ static int run_gpu() {
         // a store that lacks a block the scan reads: the reference's `missing …` error — same status, same receipt index as the oracle
         if (id == 1) {
             uint64_t r5 = 5;
-            while (!f.receipts[r5].events_root) r5++;
+            while (r5 < f.receipts.size() && !f.receipts[r5].events_root) r5++;
+            REQUIRE(r5 < f.receipts.size());
             const Cid victim = Cid::try_from(f.receipts[r5].events_root->cid);
             std::vector<uint8_t> hc, hb;
             std::vector<uint64_t> ho;
