@@ -36,7 +36,7 @@ def test_cpp_host_mirror_cpu_checks():
     the synthetic builder's descriptor, the result → struct conversions on an oracle result; without a device every call that needs
     one throws with IPCFP_ERR_NO_DEVICE."""
     exe = _build()
-    out = subprocess.run([exe, "cpu"], capture_output=True, text=True)
+    out = subprocess.run([exe, "cpu"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert out.stdout.startswith("ok: cpu checks of include/ipcfp.hpp"), out.stdout
 
@@ -59,7 +59,7 @@ def test_cpp_host_mirror_on_the_gpu():
     check_event; a damaged witness block is a CID mismatch; dropping any single witness block never leaves everything accepted; a
     missing store block and a missing actor fail with the oracle's status and index."""
     exe = _build()
-    out = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert out.stdout.startswith("ok: include/ipcfp.hpp on cuda:0 == the oracle"), out.stdout
     launches = int(out.stdout.split("assertions,")[1].split()[0])
