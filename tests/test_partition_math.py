@@ -29,3 +29,28 @@ def test_default_piece_capacity_is_bounded_by_the_safe_one():
             assert 1 <= default <= safe
             # a perfectly balanced list always fits the default slots
             assert (nw_max + world - 1) // world <= default
+
+
+def test_one_item_per_warp_launch_shape_covers_every_item_once():
+    """k_read_slots / k_pass2 / k_verify_events / k_verify_storage: grid = ceil(32 n / 128) CTAs of 128 threads, lane 0 of warp w handles item w
+    (`if (threadIdx.x & 31) return; t >>= 5; if (t >= n) return;`). Every item exactly once, for sizes around the CTA and warp boundaries."""
+    def items(n, per_warp):
+        threads = 128
+        grid = -(-(n * 32 if per_warp else n) // threads)
+        seen = []
+        for b in range(grid):
+            for tid in range(threads):
+                t = b * threads + tid
+                if per_warp:
+                    if tid & 31:
+                        continue
+                    t >>= 5
+                if t >= n:
+                    continue
+                seen.append(t)
+        return seen
+    for n in list(range(1, 20)) + [31, 32, 33, 127, 128, 129, 1020, 16384]:
+        for per_warp in (True, False):
+            if n == 16384 and not per_warp:
+                continue
+            assert items(n, per_warp) == list(range(n)), (n, per_warp)
